@@ -1,0 +1,76 @@
+"""ctypes binding of the C-ABI library (`include/b200_planesweep.h`).
+
+The product path has no CPU or PyTorch fallback: if the shared library is missing or a
+symbol is absent this module raises at import/first use."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200planesweep.so")
+
+c_f = ctypes.c_void_p  # device pointers travel as plain addresses
+c_i = ctypes.c_int
+c_ll = ctypes.c_longlong
+
+# name -> argument types (return type is always int, 0 = ok)
+SIGNATURES = {
+    "b200_volume_prepare": [c_f] * 12 + [c_i] * 4 + [ctypes.c_void_p],
+    "b200_feats_to_pixel_major": [c_f, c_f, c_i, c_i, c_i, c_ll, c_ll, ctypes.c_void_p],
+    "b200_volume_argmax": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
+    "b200_cv_dot": [c_f] * 7 + [c_i] * 6 + [ctypes.c_void_p],
+    "b200_fv_mlp_simt": [c_f] * 13 + [c_i] * 7 + [ctypes.c_void_p],
+    "b200_umma_probe": [c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
+}
+
+_lib = None
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error(
+            f"{LIB_PATH} not found: build it with `python -m implicit_depth_b200.build` "
+            "(there is no CPU/PyTorch fallback for this path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    lib.b200_last_error.restype = ctypes.c_char_p
+    lib.b200_abi_version.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device address of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise B200Error(f"{name} failed ({rc}): {lib.b200_last_error().decode()}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise B200Error("implicit_depth_b200 kernels need CUDA tensors; there is no CPU fallback")

@@ -1,0 +1,77 @@
+/* C ABI of libb200planesweep.so -- the sm_100a plane-sweep hot path of implicit-depth.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to float32 data unless stated otherwise; buffers are
+ *     dense row-major in the shape given; nothing is allocated or freed by the library;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work on it (no host
+ *     synchronisation), so they can sit between the CUDA events of test_bd.py:196-212;
+ *   - return value 0 = ok; negative = error (-1 bad argument, -2 CUDA error), message via
+ *     b200_last_error().  Nothing aborts.
+ *   - "pixel-major" features: [n_images, h*w, 16], i.e. one 64-byte record per texel.
+ *
+ * Citations are file:line in the reference repository (nianticlabs/implicit-depth).
+ */
+#ifndef B200_PLANESWEEP_H
+#define B200_PLANESWEEP_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int b200_abi_version(void);
+const char* b200_last_error(void);
+
+/* Per-batch set-up, replaces the tensor algebra at the top of every manager's
+ * build_cost_volume: P = (K_src @ T_src<-cur)[:3] (utils/geometry_utils.py:82-84) folded with
+ * invK_cur (:60), the source-camera centres (modules/cost_volume.py:1088), pose_distance
+ * (utils/geometry_utils.py:183-195), the log-spaced depth planes
+ * (modules/cost_volume.py:98-132) and, when W1/b1 are given, the part of the first MLP layer
+ * that is constant over (pixel, plane): mask (==1) and pose channels (:684, :690-692).
+ *   src_Ks, src_extrinsics, src_poses [B,K,4,4]; cur_invK [B,4,4];
+ *   min_depth, max_depth: device scalars (used when planes_in == NULL); planes_in [B,D] or NULL;
+ *   W1 [128, 26K+20] and b1 [128] in the reference's channel order, or NULL;
+ *   out: cams [B,K,32], planes [B,D], bias_eff [B,128] (only with W1). */
+int b200_volume_prepare(const float* src_Ks, const float* src_extrinsics, const float* src_poses,
+                        const float* cur_invK, const float* min_depth, const float* max_depth,
+                        const float* planes_in, const float* W1, const float* b1, float* cams, float* planes,
+                        float* bias_eff, int B, int K, int D, int C, void* stream);
+
+/* [n_img, C=16, HW] planes (image stride / channel stride in elements) -> pixel-major. */
+int b200_feats_to_pixel_major(const float* in, float* out, int n_img, int C, int HW, long long img_stride,
+                              long long ch_stride, void* stream);
+
+/* argmax over planes (first maximum, modules/cost_volume.py:352-356) + gather of the plane depth.
+ *   vol [B,D,N]; planes [B,D]; out: lowest [B,N] float, best_idx [B,N] int32 or NULL. */
+int b200_volume_argmax(const float* vol, const float* planes, float* lowest, int* best_idx, int B, int D, int N,
+                       void* stream);
+
+/* Fused dot-product plane sweep = CostVolumeManager.build_cost_volume + forward
+ * (modules/cost_volume.py:221-358) / EfficientCostVolumeManager (:1245-1304):
+ * warp (grid_sample bilinear/zeros/align_corners=False, :192-198), dot with the current
+ * features, sum over views (:302-311), argmax + depth gather (:352-356).
+ *   cur [B,N,16], src [B,K,N,16] pixel-major; cams/planes from b200_volume_prepare;
+ *   out: cost [B,D,h,w]; lowest [B,h,w] or NULL; best_idx [B,h,w] int32 or NULL. */
+int b200_cv_dot(const float* cur, const float* src, const float* cams, const float* planes, float* cost,
+                float* lowest, int* best_idx, int B, int K, int C, int h, int w, int D, void* stream);
+
+/* Fused metadata-MLP plane sweep = FeatureVolumeManager.build_cost_volume
+ * (modules/cost_volume.py:437-706) / FastFeatureVolumeManager (:938-1146) with the MLP of
+ * modules/networks.py:218-233, strict-fp32 CUDA-core version.
+ *   W1p [KP,128]: first layer, transposed, columns permuted to the kernel's view-major channel
+ *   order (implicit_depth_b200/cost_volume.py: channel_permutation), zero rows up to KP;
+ *   W2t [128,128] = W2^T; b2 [128]; w3 [128]; b3 [1]; bias_eff [B,128] from b200_volume_prepare;
+ *   out: vol [B,D,h,w]; mask_out [B,h,w] uint8 (overall_mask_bhw, last plane only, :603-615) or NULL. */
+int b200_fv_mlp_simt(const float* cur, const float* src, const float* cams, const float* cur_invK,
+                     const float* planes, const float* bias_eff, const float* W1p, const float* W2t,
+                     const float* b2, const float* w3, const float* b3, float* vol, unsigned char* mask_out, int B,
+                     int K, int C, int h, int w, int D, int KP, void* stream);
+
+/* Self-test of the tcgen05/TMEM building blocks: D[128,N] = A[128,K] * Bm[N,K]^T on one CTA.
+ *   mode 0: bf16 operands from shared memory; 1: A from tensor memory; 2/3: split-bf16 (fp32-grade)
+ *   with A from tensor / shared memory.  K in {64,128,192}, N multiple of 16 up to 128. */
+int b200_umma_probe(const float* A, const float* Bm, float* D, int K, int N, int mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

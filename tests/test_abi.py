@@ -1,0 +1,97 @@
+"""CPU-side checks of the drop-in boundary: the library builds for sm_100a without a GPU, loads,
+and exports every symbol that include/*.h declares; host-side argument errors are reported, not
+aborted; the product path refuses to run without CUDA."""
+import ctypes
+import glob
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        src = open(h).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names.update(re.findall(r"\b(b200_\w+)\s*\(", src))
+    return sorted(names)
+
+
+def test_header_declares_entry_points():
+    syms = declared_symbols()
+    assert "b200_cv_dot" in syms and "b200_volume_prepare" in syms and len(syms) >= 6
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+
+
+def test_python_binding_covers_header(lib):
+    from implicit_depth_b200 import _abi
+
+    bound = set(_abi.SIGNATURES) | {"b200_last_error", "b200_abi_version"}
+    assert set(declared_symbols()) <= bound
+    assert lib.b200_abi_version() == 1
+
+
+def test_bad_arguments_return_error_codes(lib):
+    rc = lib.b200_cv_dot(None, None, None, None, None, None, None, 1, 7, 8, 4, 4, 4, None)
+    assert rc == -1 and b"16 feature channels" in lib.b200_last_error()
+    rc = lib.b200_cv_dot(None, None, None, None, None, None, None, 1, 9, 16, 4, 4, 4, None)
+    assert rc == -1 and b"bad sizes" in lib.b200_last_error()
+    rc = lib.b200_volume_argmax(None, None, None, None, 1, 1, 1, None)
+    assert rc == -1
+
+
+def test_sass_contains_tcgen05(lib):
+    """The tensor-core kernels must really be tcgen05 (UTC*MMA / LDTM / STTM in SASS)."""
+    import shutil
+    import subprocess
+
+    from implicit_depth_b200 import _abi
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _abi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "STTM" in sass and "LDTM" in sass
+
+
+def test_product_refuses_cpu_tensors():
+    from implicit_depth_b200 import B200CostVolumeManager, _abi
+
+    m = B200CostVolumeManager(4, 4, num_depth_bins=2)
+    z = torch.zeros
+    with pytest.raises(_abi.B200Error):
+        m(z(1, 16, 4, 4), z(1, 1, 16, 4, 4), z(1, 1, 4, 4), z(1, 1, 4, 4), z(1, 1, 4, 4), z(1, 4, 4),
+          torch.tensor(0.25).view(1, 1, 1, 1), torch.tensor(5.0).view(1, 1, 1, 1))
+
+
+def test_state_dict_keys_match_reference():
+    """Keys recorded from the reference managers (checkpoint row)."""
+    from implicit_depth_b200 import B200CostVolumeManager, B200FeatureVolumeManager
+
+    fv = B200FeatureVolumeManager(6, 8, num_depth_bins=4)
+    keys = set(fv.state_dict().keys())
+    want = {"linear_ramp_1d11", "backprojector.pix_coords_13N", "projector.eps"} | {
+        f"mlp.net.{i}.{p}" for i in (0, 2, 4) for p in ("weight", "bias")}
+    assert keys == want
+    assert tuple(fv.mlp.net[0].weight.shape) == (128, 202)
+    assert set(B200CostVolumeManager(6, 8).state_dict().keys()) == {
+        "linear_ramp_1d11", "backprojector.pix_coords_13N", "projector.eps"}
+
+
+def test_channel_permutation_is_a_permutation_of_the_variable_channels():
+    from implicit_depth_b200 import B200FeatureVolumeManager
+
+    for K in (1, 2, 3, 7):
+        perm = B200FeatureVolumeManager.channel_permutation(K)
+        cin = 26 * K + 20
+        const = set(range(16 * (K + 1), 16 * (K + 1) + K)) | set(range(cin - 3 * K, cin))
+        assert len(perm) == 22 * K + 20 == len(set(perm))
+        assert set(perm) | const == set(range(cin)) and not (set(perm) & const)

@@ -1,0 +1,39 @@
+"""tcgen05 / TMEM building-block self-test (see csrc/umma_probe.cu)."""
+import pytest
+import torch
+
+from implicit_depth_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+
+
+def run_probe(A, Bm, mode):
+    D = torch.full((128, Bm.shape[0]), float("nan"), device="cuda")
+    _abi.call("b200_umma_probe", _abi.ptr(A), _abi.ptr(Bm), _abi.ptr(D), A.shape[1], Bm.shape[0], mode,
+              _abi.stream_ptr())
+    torch.cuda.synchronize()
+    return D
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("K,N", [(64, 128), (192, 128), (128, 64), (64, 16)])
+def test_bf16_mma_matches_host(mode, K, N):
+    torch.manual_seed(K + N + mode)
+    A = torch.randn(128, K, device="cuda")
+    Bm = torch.randn(N, K, device="cuda")
+    D = run_probe(A, Bm, mode)
+    ref = (A.bfloat16().double() @ Bm.bfloat16().double().t()).float()
+    err = (D - ref).abs().max().item()
+    assert err < 1e-3 * ref.abs().max().item(), f"mode {mode} K={K} N={N}: max err {err}"
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("K,N", [(64, 128), (192, 128)])
+def test_split_bf16_is_fp32_grade(mode, K, N):
+    torch.manual_seed(7 * K + mode)
+    A = torch.randn(128, K, device="cuda")
+    Bm = torch.randn(N, K, device="cuda")
+    D = run_probe(A, Bm, mode)
+    ref = (A.double() @ Bm.double().t())
+    rel = ((D.double() - ref).abs().max() / ref.abs().max()).item()
+    assert rel < 2e-5, f"mode {mode}: split-bf16 relative error {rel}"

@@ -1,0 +1,167 @@
+"""GPU parity tests of the plane-sweep volume kernels, called through the reference-shaped
+managers (which go through the C ABI).  Tolerance: 1e-3 relative (max|diff| / max|ref|) as
+BASELINE.json's north_star states; the plane index argmax must be exact except at reference
+near-ties (top-2 margin < 1e-5 of the range), which are counted and bounded."""
+import numpy as np
+import pytest
+import torch
+
+from implicit_depth_b200 import B200CostVolumeManager, B200FeatureVolumeManager, synthetic
+from oracle import planesweep as O
+
+from cases import VOLUME_CASES, argmax_report, load_golden, mlp_weights, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def dev(inp):
+    return {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+
+
+def depth_range():
+    return (torch.tensor(0.25, device="cuda").view(1, 1, 1, 1), torch.tensor(5.0, device="cuda").view(1, 1, 1, 1))
+
+
+def planes_to_idx(lowest, planes):
+    return np.abs(lowest[..., None] - planes[None, None, None, :]).argmin(-1)
+
+
+def load_mlp(mgr, g):
+    with torch.no_grad():
+        for i, li in enumerate((0, 2, 4)):
+            mgr.mlp.net[li].weight.copy_(torch.from_numpy(g[f"mlp_w{i}"]))
+            mgr.mlp.net[li].bias.copy_(torch.from_numpy(g[f"mlp_b{i}"]))
+
+
+@pytest.mark.parametrize("name", list(VOLUME_CASES))
+def test_dot_volume_vs_reference_golden(name):
+    seed, B, K, C, h, w, D = VOLUME_CASES[name]
+    g = load_golden(name)
+    t = dev(synthetic.make_volume_inputs(seed, B, K, C, h, w))
+    mgr = B200CostVolumeManager(h, w, num_depth_bins=D).cuda()
+    mn, mx = depth_range()
+    cost, lowest, planes_bdhw, mask = mgr(min_depth=mn, max_depth=mx, **t)
+    assert mask is None and tuple(cost.shape) == (B, D, h, w) and tuple(planes_bdhw.shape) == (B, D, h, w)
+    cost, lowest = cost.cpu().numpy(), lowest.cpu().numpy()
+    planes = planes_bdhw[0, :, 0, 0].cpu().numpy()
+    np.testing.assert_allclose(planes, g["planes"], rtol=1e-6)
+    assert rel_err(cost, g["dot_cost"]) < TOL
+    idx = planes_to_idx(lowest, planes)
+    np.testing.assert_array_equal(idx, np.argmax(cost, 1))  # kernel argmax == first max of its own volume
+    n_bad, n_near = argmax_report(idx, vol_ref=g["dot_cost"])
+    assert n_bad == n_near, f"{n_bad} argmax mismatches, only {n_near} at near-ties"
+    assert n_bad <= 2e-3 * idx.size
+
+
+@pytest.mark.parametrize("name", list(VOLUME_CASES))
+def test_feature_volume_vs_reference_golden(name):
+    seed, B, K, C, h, w, D = VOLUME_CASES[name]
+    g = load_golden(name)
+    t = dev(synthetic.make_volume_inputs(seed, B, K, C, h, w))
+    mgr = B200FeatureVolumeManager(h, w, num_depth_bins=D, num_source_views=K).cuda()
+    load_mlp(mgr, g)
+    mn, mx = depth_range()
+    vol, lowest, planes_bdhw, mask = mgr(min_depth=mn, max_depth=mx, return_mask=True, **t)
+    assert mask.dtype == torch.bool
+    vol, lowest, mask = vol.cpu().numpy(), lowest.cpu().numpy(), mask.cpu().numpy()
+    assert rel_err(vol, g["fv_vol"]) < TOL
+    assert (mask != g["fv_mask"]).mean() < 1e-3  # px exactly on the 2 / w-2 window edge may flip
+    planes = planes_bdhw[0, :, 0, 0].cpu().numpy()
+    idx = planes_to_idx(lowest, planes)
+    np.testing.assert_array_equal(idx, np.argmax(vol, 1))
+    n_bad, n_near = argmax_report(idx, vol_ref=g["fv_vol"])
+    assert n_bad == n_near, f"{n_bad} argmax mismatches, only {n_near} at near-ties"
+    assert n_bad <= 2e-3 * idx.size
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 7, 9, 1), (2, 4, 33, 17, 3), (1, 8, 5, 130, 2)])
+def test_ragged_shapes_vs_oracle(shape):
+    """Edge sizes: one view / one plane, N not a multiple of any tile, maximum view count."""
+    B, K, h, w, D = shape
+    inp = synthetic.make_volume_inputs(77 + K, B, K, 16, h, w)
+    t = dev(inp)
+    mn, mx = depth_range()
+    mgr = B200CostVolumeManager(h, w, num_depth_bins=D).cuda()
+    cost, lowest, planes_bdhw, _ = mgr(min_depth=mn, max_depth=mx, **t)
+    planes = planes_bdhw[0, :, 0, 0].cpu().numpy()
+    ref, ridx, rlow = O.cost_volume_dot(inp["cur_feats"], inp["src_feats"], inp["src_extrinsics"], inp["src_Ks"],
+                                        inp["cur_invK"], planes)
+    assert rel_err(cost.cpu().numpy(), ref) < TOL
+    fv = B200FeatureVolumeManager(h, w, num_depth_bins=D, num_source_views=K).cuda()
+    torch.manual_seed(3)
+    for p in fv.parameters():
+        torch.nn.init.normal_(p, std=0.1)
+    W = [(fv.mlp.net[i].weight.detach().cpu().numpy(), fv.mlp.net[i].bias.detach().cpu().numpy()) for i in (0, 2, 4)]
+    vol, lowest, _, mask = fv(min_depth=mn, max_depth=mx, return_mask=True, **t)
+    rvol, _, _, rmask = O.feature_volume_mlp(inp["cur_feats"], inp["src_feats"], inp["src_extrinsics"],
+                                             inp["src_poses"], inp["src_Ks"], inp["cur_invK"], planes, W)
+    assert rel_err(vol.cpu().numpy(), rvol) < TOL
+    assert (mask.cpu().numpy() != rmask).mean() < 5e-3
+
+
+def test_noncontiguous_cur_feats_and_user_planes():
+    """cur_feats arrives as the strided slice matching_feats[:, 0] (bd_model.py:170); planes may be
+    passed explicitly as an expanded view (cost_volume.py:128-130)."""
+    seed, B, K, C, h, w, D = VOLUME_CASES["small_24x32_k7_d8"]
+    g = load_golden("small_24x32_k7_d8")
+    inp = synthetic.make_volume_inputs(seed, B, K, C, h, w)
+    t = dev(inp)
+    allf = torch.cat([t["cur_feats"][:, None], t["src_feats"]], 1)
+    t["cur_feats"] = allf[:, 0]
+    assert not t["cur_feats"].is_contiguous()
+    planes_bdhw = torch.from_numpy(g["planes"]).cuda().view(1, D, 1, 1).expand(B, D, h, w)
+    mgr = B200CostVolumeManager(h, w, num_depth_bins=D).cuda()
+    mn, mx = depth_range()
+    cost, lowest, pl, _ = mgr(min_depth=mn, max_depth=mx, depth_planes_bdhw=planes_bdhw, **t)
+    assert rel_err(cost.cpu().numpy(), g["dot_cost"]) < TOL
+    assert pl is planes_bdhw
+    # with the reference's own plane values the gathered depth must be one of them, bit for bit
+    assert np.isin(lowest.cpu().numpy(), g["planes"]).all()
+
+
+def test_all_views_out_of_frustum_gives_zero_and_first_plane():
+    seed, B, K, C, h, w, D = VOLUME_CASES["ragged_20x36_k3_d5"]
+    inp = synthetic.make_volume_inputs(seed, B, K, C, h, w)
+    flip = np.diag([-1.0, 1.0, -1.0, 1.0]).astype(np.float32)
+    inp["src_extrinsics"] = flip @ inp["src_extrinsics"]
+    mgr = B200CostVolumeManager(h, w, num_depth_bins=D).cuda()
+    mn, mx = depth_range()
+    cost, lowest, pl, _ = mgr(min_depth=mn, max_depth=mx, **dev(inp))
+    assert float(cost.abs().max()) == 0.0
+    assert torch.equal(lowest, pl[:, 0])
+
+
+def test_linearity_and_batch_invariance_full_size():
+    """Size-independent properties at the BASELINE cfg2 shape (B=4, 96x128, K=7, D=64): the dot
+    volume is linear in the current features, and a frame's result does not depend on what else is
+    in the batch (the reference runs its encoder unbatched for exactly this reason,
+    depth_model.py:235-241)."""
+    B, K, C, h, w, D = 4, 7, 16, 96, 128, 64
+    t = dev(synthetic.make_volume_inputs(2000, B, K, C, h, w))
+    mgr = B200CostVolumeManager(h, w, num_depth_bins=D).cuda()
+    mn, mx = depth_range()
+    c1, l1, _, _ = mgr(min_depth=mn, max_depth=mx, **t)
+    t2 = dict(t)
+    t2["cur_feats"] = t["cur_feats"] * 2.0
+    c2, l2, _, _ = mgr(min_depth=mn, max_depth=mx, **t2)
+    assert torch.equal(c2, 2.0 * c1) and torch.equal(l1, l2)  # scaling by 2 is exact in fp32
+    one = {k: v[1:2].contiguous() for k, v in t.items()}
+    c3, l3, _, _ = mgr(min_depth=mn, max_depth=mx, **one)
+    assert torch.equal(c3, c1[1:2]) and torch.equal(l3, l1[1:2])
+    fv = B200FeatureVolumeManager(h, w, num_depth_bins=D).cuda()
+    v1, fl1, _, m1 = fv(min_depth=mn, max_depth=mx, return_mask=True, **t)
+    v3, fl3, _, m3 = fv(min_depth=mn, max_depth=mx, return_mask=True, **one)
+    assert torch.equal(v3, v1[1:2]) and torch.equal(fl3, fl1[1:2]) and torch.equal(m3, m1[1:2])
+    assert torch.isfinite(v1).all()
+
+
+def test_error_behaviour():
+    mgr = B200FeatureVolumeManager(8, 8, num_depth_bins=4, num_source_views=7).cuda()
+    t = dev(synthetic.make_volume_inputs(5, 1, 2, 16, 8, 8))
+    mn, mx = depth_range()
+    with pytest.raises(ValueError):  # the reference fails with a shape error for K != 7
+        mgr(min_depth=mn, max_depth=mx, **t)
+    mgr2 = B200CostVolumeManager(4, 4, num_depth_bins=4).cuda()
+    with pytest.raises(ValueError):
+        mgr2(min_depth=mn, max_depth=mx, **t)
