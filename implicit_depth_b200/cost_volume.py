@@ -59,6 +59,25 @@ class MLP(nn.Module):
         self.net = nn.Sequential(*layers)
 
 
+def split_bf16(x):
+    """x ~= hi + lo, both bf16 (16 mantissa bits together): the operand format of the tensor-core kernels."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def sw128_tiles(mat_nk):
+    """[128, 64*c] bf16 (row = output neuron n, K-major) -> bytes of c consecutive 16 KB tiles in the
+    128-byte-swizzled canonical UMMA layout (16-byte chunk j of row r stored at chunk j ^ (r & 7))."""
+    n, k = mat_nk.shape
+    assert n == 128 and k % 64 == 0 and mat_nk.dtype == torch.bfloat16
+    t = mat_nk.view(128, k // 64, 8, 8).permute(1, 0, 2, 3)  # [chunk, row, 16B-chunk, elem]
+    r = torch.arange(128, device=mat_nk.device).view(1, 128, 1, 1)
+    j = torch.arange(8, device=mat_nk.device).view(1, 1, 8, 1)
+    idx = (j ^ (r & 7)).expand(k // 64, 128, 8, 8)
+    return torch.gather(t, 2, idx).contiguous().view(torch.uint8).reshape(-1)
+
+
 def _as_f32c(t):
     if t.dtype != torch.float32:
         t = t.float()
@@ -224,7 +243,15 @@ class B200FeatureVolumeManager(B200CostVolumeManager):
         KP = (kin + 15) // 16 * 16
         W1p = torch.zeros((KP, MLP_HID), device=device, dtype=torch.float32)
         W1p[:kin] = W1[:, perm].t()
+        kc = (kin + 63) // 64 * 64
+        W1n = torch.zeros((MLP_HID, kc), device=device, dtype=torch.float32)
+        W1n[:, :kin] = W1[:, perm]
+        W2 = lin[1].weight.detach().to(device=device, dtype=torch.float32)
+        h1, l1 = split_bf16(W1n)
+        h2, l2 = split_bf16(W2)
+        wimage = torch.cat([sw128_tiles(h1), sw128_tiles(l1), sw128_tiles(h2), sw128_tiles(l2)]).contiguous()
         pk = dict(
+            wimage=wimage,
             W1=W1, b1=lin[0].bias.detach().to(device=device, dtype=torch.float32).contiguous(),
             W1p=W1p.contiguous(), KP=KP,
             W2t=lin[1].weight.detach().to(device=device, dtype=torch.float32).t().contiguous(),
@@ -249,17 +276,26 @@ class B200FeatureVolumeManager(B200CostVolumeManager):
         cams, planes, bias_eff = self._prepare(src_extrinsics, src_poses, src_Ks, cur_invK, min_depth, max_depth,
                                                planes_in, B, K, D, pk["W1"], pk["b1"])
         vol = torch.empty((B, D, h, w), device=dev, dtype=torch.float32)
-        mask = torch.empty((B, h, w), device=dev, dtype=torch.uint8) if return_mask else None
+        mask = torch.empty((B, h, w), device=dev, dtype=torch.bool) if return_mask else None
         invK = _as_f32c(cur_invK)
-        _abi.call("b200_fv_mlp_simt", _abi.ptr(cur_pm), _abi.ptr(src_pm), _abi.ptr(cams), _abi.ptr(invK),
-                  _abi.ptr(planes), _abi.ptr(bias_eff), _abi.ptr(pk["W1p"]), _abi.ptr(pk["W2t"]), _abi.ptr(pk["b2"]),
-                  _abi.ptr(pk["w3"]), _abi.ptr(pk["b3"]), _abi.ptr(vol), _abi.ptr(mask), B, K, FEAT_C, h, w, D,
-                  pk["KP"], _abi.stream_ptr())
+        if self.impl in ("auto", "tc"):
+            _abi.call("b200_fv_mlp_tc", _abi.ptr(cur_pm), _abi.ptr(src_pm), _abi.ptr(cams), _abi.ptr(invK),
+                      _abi.ptr(planes), _abi.ptr(bias_eff), _abi.ptr(pk["wimage"]), _abi.ptr(pk["b2"]),
+                      _abi.ptr(pk["w3"]), _abi.ptr(pk["b3"]), _abi.ptr(vol), _abi.ptr(mask), B, K, FEAT_C, h, w, D,
+                      _abi.stream_ptr())
+        elif self.impl == "simt":
+            _abi.call("b200_fv_mlp_simt", _abi.ptr(cur_pm), _abi.ptr(src_pm), _abi.ptr(cams), _abi.ptr(invK),
+                      _abi.ptr(planes), _abi.ptr(bias_eff), _abi.ptr(pk["W1p"]), _abi.ptr(pk["W2t"]),
+                      _abi.ptr(pk["b2"]), _abi.ptr(pk["w3"]), _abi.ptr(pk["b3"]), _abi.ptr(vol), _abi.ptr(mask), B,
+                      K, FEAT_C, h, w, D,
+                      pk["KP"], _abi.stream_ptr())
+        else:
+            raise ValueError(f"unknown impl {self.impl!r} (auto | tc | simt)")
         lowest = torch.empty((B, h, w), device=dev, dtype=torch.float32)
         _abi.call("b200_volume_argmax", _abi.ptr(vol), _abi.ptr(planes), _abi.ptr(lowest), None, B, D, N,
                   _abi.stream_ptr())
         planes_bdhw = planes.view(B, D, 1, 1).expand(B, D, h, w) if depth_planes_bdhw is None else depth_planes_bdhw
-        return vol, lowest, planes_bdhw, (mask.bool() if return_mask else None)
+        return vol, lowest, planes_bdhw, mask
 
 
 def to_b200(manager):

@@ -66,6 +66,18 @@ int b200_fv_mlp_simt(const float* cur, const float* src, const float* cams, cons
                      const float* b2, const float* w3, const float* b3, float* vol, unsigned char* mask_out, int B,
                      int K, int C, int h, int w, int D, int KP, void* stream);
 
+/* Same contract as b200_fv_mlp_simt on the tcgen05 tensor cores: the input rows are written by their
+ * owning threads straight into tensor memory as split-bf16 A operands, both weight matrices stay in
+ * shared memory, three bf16 MMAs (hi*hi + hi*lo + lo*hi) per k-step give fp32-grade results.
+ *   wimage: b200_fv_tc_wimage_bytes(K) bytes = pre-swizzled split-bf16 image of the permuted, zero-padded
+ *   W1 [128, 64*ceil((22K+20)/64)] (hi tiles, lo tiles) followed by W2 [128,128] (hi tiles, lo tiles);
+ *   16 KB tiles of [128 x 64] bf16 in the 128-byte-swizzled K-major UMMA layout, 16-byte aligned. */
+int b200_fv_mlp_tc(const float* cur, const float* src, const float* cams, const float* cur_invK,
+                   const float* planes, const float* bias_eff, const void* wimage, const float* b2,
+                   const float* w3, const float* b3, float* vol, unsigned char* mask_out, int B, int K, int C,
+                   int h, int w, int D, void* stream);
+int b200_fv_tc_wimage_bytes(int K);
+
 /* Self-test of the tcgen05/TMEM building blocks: D[128,N] = A[128,K] * Bm[N,K]^T on one CTA.
  *   mode 0: bf16 operands from shared memory; 1: A from tensor memory; 2/3: split-bf16 (fp32-grade)
  *   with A from tensor / shared memory.  K in {64,128,192}, N multiple of 16 up to 128. */

@@ -54,12 +54,13 @@ def test_dot_volume_vs_reference_golden(name):
     assert n_bad <= 2e-3 * idx.size
 
 
+@pytest.mark.parametrize("impl", ["tc", "simt"])
 @pytest.mark.parametrize("name", list(VOLUME_CASES))
-def test_feature_volume_vs_reference_golden(name):
+def test_feature_volume_vs_reference_golden(name, impl):
     seed, B, K, C, h, w, D = VOLUME_CASES[name]
     g = load_golden(name)
     t = dev(synthetic.make_volume_inputs(seed, B, K, C, h, w))
-    mgr = B200FeatureVolumeManager(h, w, num_depth_bins=D, num_source_views=K).cuda()
+    mgr = B200FeatureVolumeManager(h, w, num_depth_bins=D, num_source_views=K, impl=impl).cuda()
     load_mlp(mgr, g)
     mn, mx = depth_range()
     vol, lowest, planes_bdhw, mask = mgr(min_depth=mn, max_depth=mx, return_mask=True, **t)
@@ -75,8 +76,10 @@ def test_feature_volume_vs_reference_golden(name):
     assert n_bad <= 2e-3 * idx.size
 
 
-@pytest.mark.parametrize("shape", [(1, 1, 7, 9, 1), (2, 4, 33, 17, 3), (1, 8, 5, 130, 2)])
-def test_ragged_shapes_vs_oracle(shape):
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+@pytest.mark.parametrize("shape", [(1, 1, 7, 9, 1), (2, 4, 33, 17, 3), (1, 8, 5, 130, 2), (3, 5, 11, 40, 4),
+                                   (1, 6, 16, 16, 9)])
+def test_ragged_shapes_vs_oracle(shape, impl):
     """Edge sizes: one view / one plane, N not a multiple of any tile, maximum view count."""
     B, K, h, w, D = shape
     inp = synthetic.make_volume_inputs(77 + K, B, K, 16, h, w)
@@ -88,7 +91,7 @@ def test_ragged_shapes_vs_oracle(shape):
     ref, ridx, rlow = O.cost_volume_dot(inp["cur_feats"], inp["src_feats"], inp["src_extrinsics"], inp["src_Ks"],
                                         inp["cur_invK"], planes)
     assert rel_err(cost.cpu().numpy(), ref) < TOL
-    fv = B200FeatureVolumeManager(h, w, num_depth_bins=D, num_source_views=K).cuda()
+    fv = B200FeatureVolumeManager(h, w, num_depth_bins=D, num_source_views=K, impl=impl).cuda()
     torch.manual_seed(3)
     for p in fv.parameters():
         torch.nn.init.normal_(p, std=0.1)
@@ -149,11 +152,16 @@ def test_linearity_and_batch_invariance_full_size():
     one = {k: v[1:2].contiguous() for k, v in t.items()}
     c3, l3, _, _ = mgr(min_depth=mn, max_depth=mx, **one)
     assert torch.equal(c3, c1[1:2]) and torch.equal(l3, l1[1:2])
-    fv = B200FeatureVolumeManager(h, w, num_depth_bins=D).cuda()
-    v1, fl1, _, m1 = fv(min_depth=mn, max_depth=mx, return_mask=True, **t)
-    v3, fl3, _, m3 = fv(min_depth=mn, max_depth=mx, return_mask=True, **one)
-    assert torch.equal(v3, v1[1:2]) and torch.equal(fl3, fl1[1:2]) and torch.equal(m3, m1[1:2])
-    assert torch.isfinite(v1).all()
+    for impl in ("tc", "simt"):
+        fv = B200FeatureVolumeManager(h, w, num_depth_bins=D, impl=impl).cuda()
+        v1, fl1, _, m1 = fv(min_depth=mn, max_depth=mx, return_mask=True, **t)
+        v3, fl3, _, m3 = fv(min_depth=mn, max_depth=mx, return_mask=True, **one)
+        assert torch.equal(v3, v1[1:2]) and torch.equal(fl3, fl1[1:2]) and torch.equal(m3, m1[1:2])
+        assert torch.isfinite(v1).all()
+        if impl == "tc":
+            vtc = v1
+    # tensor-core (split-bf16) and strict-fp32 CUDA-core kernels agree to fp32 grade at full size
+    assert ((vtc - v1).abs().max() / v1.abs().max()).item() < 1e-4
 
 
 def test_error_behaviour():
