@@ -25,6 +25,11 @@ SIGNATURES = {
     "b200_fv_mlp_simt": [c_f] * 13 + [c_i] * 7 + [ctypes.c_void_p],
     "b200_fv_mlp_tc": [c_f] * 12 + [c_i] * 6 + [ctypes.c_void_p],
     "b200_fv_tc_wimage_bytes": [c_i],
+    "b200_conv_create": [ctypes.c_void_p, ctypes.c_void_p],
+    "b200_conv_run": [ctypes.c_void_p, ctypes.c_void_p],
+    "b200_conv_destroy": [ctypes.c_void_p],
+    "b200_conv_ntile": [c_i],
+    "b200_conv_wimage_bytes": [ctypes.c_void_p, ctypes.c_void_p, c_i, c_i],
     "b200_umma_probe": [c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
 }
 
@@ -50,6 +55,7 @@ def load():
         fn.restype = ctypes.c_int
     lib.b200_last_error.restype = ctypes.c_char_p
     lib.b200_abi_version.restype = ctypes.c_int
+    lib.b200_conv_wimage_bytes.restype = ctypes.c_longlong
     _lib = lib
     return lib
 

@@ -1,0 +1,139 @@
+"""Host side of the tensor-core convolution path: split-bf16 NHWC activations, weight packing and
+plan objects for `b200_conv_*` (csrc/conv_tc.cu)."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _abi
+
+ACT = {"none": 0, "lrelu": 1, "elu": 2, "relu": 3}
+MAX_SEG = 4
+
+
+class _Seg(ctypes.Structure):
+    _fields_ = [("in_hi", ctypes.c_void_p), ("in_lo", ctypes.c_void_p), ("H", ctypes.c_int), ("W", ctypes.c_int),
+                ("C", ctypes.c_int), ("ksize", ctypes.c_int), ("stride", ctypes.c_int), ("pad", ctypes.c_int)]
+
+
+class _Desc(ctypes.Structure):
+    _fields_ = [("seg", _Seg * MAX_SEG), ("nseg", ctypes.c_int), ("wimage", ctypes.c_void_p),
+                ("bias", ctypes.c_void_p), ("res_hi", ctypes.c_void_p), ("res_lo", ctypes.c_void_p),
+                ("out_hi", ctypes.c_void_p), ("out_lo", ctypes.c_void_p), ("out_f32", ctypes.c_void_p),
+                ("B", ctypes.c_int), ("OH", ctypes.c_int), ("OW", ctypes.c_int), ("Cout", ctypes.c_int),
+                ("act", ctypes.c_int), ("slope", ctypes.c_float)]
+
+
+class SplitAct:
+    """An activation tensor in the tensor-core path's storage format: two NHWC bf16 planes with
+    x = hi + lo (16 mantissa bits; same bytes as fp32)."""
+
+    def __init__(self, B, H, W, C, device):
+        self.B, self.H, self.W, self.C = B, H, W, C
+        self.hi = torch.empty((B, H, W, C), device=device, dtype=torch.bfloat16)
+        self.lo = torch.empty((B, H, W, C), device=device, dtype=torch.bfloat16)
+
+    @property
+    def shape(self):
+        return (self.B, self.H, self.W, self.C)
+
+    def float_nchw(self):
+        """Debug/test helper (torch ops): reassemble an fp32 NCHW tensor."""
+        return (self.hi.float() + self.lo.float()).permute(0, 3, 1, 2).contiguous()
+
+    @staticmethod
+    def from_nchw_torch(x):
+        """Debug/test helper (torch ops); the product path uses b200_nchw_to_split."""
+        B, C, H, W = x.shape
+        a = SplitAct(B, H, W, C, x.device)
+        xh = x.permute(0, 2, 3, 1).contiguous().float()
+        a.hi.copy_(xh.to(torch.bfloat16))
+        a.lo.copy_((xh - a.hi.float()).to(torch.bfloat16))
+        return a
+
+
+def ntile(cout):
+    return cout if cout <= 128 else 128
+
+
+def _sw128_rows(mat):
+    """[R, 64] bf16 (R multiple of 8) -> swizzled bytes (R x 128 B, 16-byte chunk j of row r at j ^ (r & 7))."""
+    R = mat.shape[0]
+    t = mat.reshape(R, 8, 8)
+    r = torch.arange(R, device=mat.device).view(R, 1, 1)
+    j = torch.arange(8, device=mat.device).view(1, 8, 1)
+    idx = (j ^ (r & 7)).expand(R, 8, 8)
+    return torch.gather(t, 1, idx).contiguous().view(torch.uint8).reshape(-1)
+
+
+def pack_conv_weights(weights, seg_channels, cout):
+    """weights: list (one per segment) of [Cout, C_s, k, k] fp32 tensors.  Returns the uint8 image
+    [n_ntiles][chunk][hi NT x 64 | lo NT x 64] in the producer's chunk order (segment, tap, 64-channel block)."""
+    dev = weights[0].device
+    NT = ntile(cout)
+    n_nt = (cout + NT - 1) // NT
+    chunks = []
+    for w, C in zip(weights, seg_channels):
+        k = w.shape[-1]
+        assert w.shape[0] == cout and w.shape[1] == C
+        for dy in range(k):
+            for dx in range(k):
+                for cb in range((C + 63) // 64):
+                    blk = torch.zeros((cout, 64), device=dev, dtype=torch.float32)
+                    c1 = min(C, cb * 64 + 64)
+                    blk[:, : c1 - cb * 64] = w[:, cb * 64:c1, dy, dx]
+                    chunks.append(blk)
+    allw = torch.stack(chunks, 0)  # [chunks, Cout, 64]
+    hi = allw.to(torch.bfloat16)
+    lo = (allw - hi.float()).to(torch.bfloat16)
+    parts = []
+    for nt in range(n_nt):
+        for q in range(allw.shape[0]):
+            parts.append(_sw128_rows(hi[q, nt * NT:(nt + 1) * NT]))
+            parts.append(_sw128_rows(lo[q, nt * NT:(nt + 1) * NT]))
+    return torch.cat(parts).contiguous()
+
+
+class ConvPlan:
+    """One convolution launch with everything (tensor maps, weight image, buffers) fixed at plan time."""
+
+    def __init__(self, segs, wimage, bias, out, B, cout, act="none", slope=0.2, residual=None, out_f32=None):
+        """segs: list of (SplitAct, ksize, stride, pad); out: SplitAct or None; residual: SplitAct or None."""
+        d = _Desc()
+        d.nseg = len(segs)
+        for i, (a, k, s, p) in enumerate(segs):
+            d.seg[i].in_hi = a.hi.data_ptr()
+            d.seg[i].in_lo = a.lo.data_ptr()
+            d.seg[i].H, d.seg[i].W, d.seg[i].C = a.H, a.W, a.C
+            d.seg[i].ksize, d.seg[i].stride, d.seg[i].pad = k, s, p
+        a0, k0, s0, p0 = segs[0]
+        OH = (a0.H + 2 * p0 - k0) // s0 + 1
+        OW = (a0.W + 2 * p0 - k0) // s0 + 1
+        d.wimage = wimage.data_ptr()
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.res_hi = residual.hi.data_ptr() if residual is not None else None
+        d.res_lo = residual.lo.data_ptr() if residual is not None else None
+        d.out_hi = out.hi.data_ptr() if out is not None else None
+        d.out_lo = out.lo.data_ptr() if out is not None else None
+        d.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+        d.B, d.OH, d.OW, d.Cout = B, OH, OW, cout
+        d.act = ACT[act]
+        d.slope = slope
+        self._keep = (segs, wimage, bias, out, residual, out_f32)  # keep buffers alive
+        self.handle = ctypes.c_void_p()
+        lib = _abi.load()
+        rc = lib.b200_conv_create(ctypes.byref(d), ctypes.byref(self.handle))
+        if rc != 0:
+            raise _abi.B200Error(f"b200_conv_create failed ({rc}): {lib.b200_last_error().decode()}")
+        self.OH, self.OW = OH, OW
+
+    def run(self):
+        _abi.call("b200_conv_run", self.handle, _abi.stream_ptr())
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _abi.load().b200_conv_destroy(self.handle)
+        except Exception:
+            pass

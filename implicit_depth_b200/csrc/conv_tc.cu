@@ -1,0 +1,395 @@
+// Implicit-GEMM 2-D convolution on the tcgen05 tensor cores, NHWC split-bf16 activations.
+//
+//   out[b,oy,ox,:] = act( sum_seg sum_tap W_seg,tap @ in_seg[b, s*oy+dy-p, s*ox+dx-p, :] + bias (+ residual) )
+//
+// * A conv is a list of up to 4 K-SEGMENTS (input tensor, 1x1/3x3, stride 1/2).  Channel concatenation
+//   (torch.cat before a conv: CVEncoder networks.py:208-215, BDDecoderPP :71-77, SkipDecoder
+//   networks_fast.py:42-43) and the BasicBlock shortcut conv (layers.py:64-71, 89-92) are just extra
+//   segments accumulating into the same TMEM tile -- nothing is concatenated or added in memory.
+// * Activations are stored as two bf16 planes (hi, lo) with x = hi + lo (16 mantissa bits, same bytes as
+//   fp32); weights are pre-split the same way.  Each 64-channel K-chunk issues hi*hi, hi*lo, lo*hi MMAs
+//   into one fp32 accumulator: fp32-grade results (the CPU-oracle parity bar) at bf16 MMA rates.
+// * Warp-specialised, persistent: warp 0 = TMA producer (4-D tiled loads of a 8x16-pixel x 64-channel
+//   box per tap: zero padding and channel tails come from TMA out-of-bounds fill, stride-2 from the
+//   tensor map's element strides; weights by 1-D bulk copies of pre-swizzled tiles), warp 1 = MMA
+//   issuer, warps 2-5 = epilogue (TMEM -> registers -> bias/activation/residual -> split -> NHWC).
+//   TMEM holds two accumulator tiles so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <string.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+#define CV_THREADS 192
+#define CV_TH 8
+#define CV_TW 16
+#define CV_MAX_SEG 4
+
+enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_ELU = 2, ACT_RELU = 3 };
+
+struct ConvKParams {
+  CUtensorMap maps[2 * CV_MAX_SEG];  // [2s] = hi plane, [2s+1] = lo plane of segment s
+  int seg_C[CV_MAX_SEG], seg_ksize[CV_MAX_SEG], seg_stride[CV_MAX_SEG], seg_pad[CV_MAX_SEG];
+  int nseg;
+  const uint8_t* wimage;  // [n_ntiles][total_chunks][hi NT x 64 | lo NT x 64] bf16, SW128 tiles
+  const float* bias;      // [Cout] or null
+  const __nv_bfloat16* res_hi;  // optional residual, NHWC [B,OH,OW,Cout]
+  const __nv_bfloat16* res_lo;
+  __nv_bfloat16* out_hi;  // NHWC [B,OH,OW,Cout] (may be null if only out_f32 is wanted)
+  __nv_bfloat16* out_lo;
+  float* out_f32;         // optional NHWC fp32 copy
+  int B, OH, OW, Cout, NT, n_ntiles, act, total_chunks, tiles_x, tiles_y, stages;
+  float slope;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == ACT_LRELU) return v >= 0.f ? v : v * slope;
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_ELU) return v > 0.f ? v : expm1f(v);
+  return v;
+}
+
+__global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvKParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int NT = prm.NT;
+  const uint32_t b_bytes = (uint32_t)NT * 256u;               // hi + lo weight tiles of one chunk
+  const uint32_t stage_bytes = 32768u + ((b_bytes + 1023u) & ~1023u);
+  const int S = prm.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)S * stage_bytes);
+  uint64_t* empty = full + S;
+  uint64_t* acc_full = empty + S;    // [2]
+  uint64_t* acc_empty = acc_full + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m_tiles = prm.B * prm.tiles_y * prm.tiles_x;
+  const int items = m_tiles * prm.n_ntiles;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * NT) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < 2 * prm.nseg; ++s) tc::prefetch_tmap(&prm.maps[s]);
+    for (int s = 0; s < S; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(&acc_full[a], 1);
+      tc::mbar_init(&acc_empty[a], 128);
+    }
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, tmem_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // =========================== TMA producer ===========================
+      uint32_t it = 0;  // global chunk counter -> stage ring
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int nt = item % prm.n_ntiles;
+        const int mt = item / prm.n_ntiles;
+        const int tx = mt % prm.tiles_x;
+        const int ty = (mt / prm.tiles_x) % prm.tiles_y;
+        const int b = mt / (prm.tiles_x * prm.tiles_y);
+        const uint8_t* wsrc = prm.wimage + (size_t)nt * prm.total_chunks * b_bytes;
+        for (int s = 0; s < prm.nseg; ++s) {
+          const int ks = prm.seg_ksize[s], st = prm.seg_stride[s], pd = prm.seg_pad[s];
+          const int cblocks = (prm.seg_C[s] + 63) >> 6;
+          for (int tap = 0; tap < ks * ks; ++tap) {
+            const int dy = tap / ks, dx = tap % ks;
+            const int x0 = (tx * CV_TW) * st + dx - pd;
+            const int y0 = (ty * CV_TH) * st + dy - pd;
+            for (int cb = 0; cb < cblocks; ++cb, ++it) {
+              const int stage = it % S;
+              const uint32_t round = it / S;
+              if (round > 0) tc::mbar_wait(&empty[stage], (round - 1) & 1u);
+              uint8_t* sa = base + (size_t)stage * stage_bytes;
+              tc::mbar_expect_tx(&full[stage], 32768u + b_bytes);
+              tc::tma_load_4d(sa, &prm.maps[2 * s], cb * 64, x0, y0, b, &full[stage]);
+              tc::tma_load_4d(sa + 16384, &prm.maps[2 * s + 1], cb * 64, x0, y0, b, &full[stage]);
+              tc::bulk_load(sa + 32768, wsrc, b_bytes, &full[stage]);
+              wsrc += b_bytes;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // =========================== MMA issuer ===========================
+      const uint32_t idesc = tc::idesc_bf16_f32(128, NT);
+      uint32_t it = 0, tile_i = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
+        const uint32_t a = tile_i & 1u;
+        const uint32_t use = tile_i >> 1;  // how often accumulator a was used before
+        if (use > 0) tc::mbar_wait(&acc_empty[a], (use - 1) & 1u);
+        tc::fence_after_sync();
+        const uint32_t acc = tmem + a * NT;
+        uint32_t first = 1;
+        for (int s = 0; s < prm.nseg; ++s) {
+          const int taps = prm.seg_ksize[s] * prm.seg_ksize[s];
+          const int C = prm.seg_C[s];
+          const int cblocks = (C + 63) >> 6;
+          for (int tap = 0; tap < taps; ++tap) {
+            for (int cb = 0; cb < cblocks; ++cb, ++it) {
+              const int stage = it % S;
+              tc::mbar_wait(&full[stage], (it / S) & 1u);
+              tc::fence_after_sync();
+              const uint32_t sa = tc::smem_u32(base + (size_t)stage * stage_bytes);
+              const uint32_t sb = sa + 32768u;
+              const int ksteps = (min(64, C - cb * 64) + 15) >> 4;
+#pragma unroll
+              for (int pass = 0; pass < 3; ++pass) {  // hi*hi, hi*lo, lo*hi
+                const uint32_t aa = sa + (pass == 2 ? 16384u : 0u);
+                const uint32_t bb = sb + (pass == 1 ? (uint32_t)NT * 128u : 0u);
+                for (int k = 0; k < ksteps; ++k) {
+                  tc::mma_ss(acc, tc::smem_desc_sw128(aa + k * 32), tc::smem_desc_sw128(bb + k * 32), idesc,
+                             first ? 0u : 1u);
+                  first = 0;
+                }
+              }
+              tc::mma_commit(&empty[stage]);
+            }
+          }
+        }
+        tc::mma_commit(&acc_full[a]);
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 2..5) ===========================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    uint32_t tile_i = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
+      const int nt = item % prm.n_ntiles;
+      const int mt = item / prm.n_ntiles;
+      const int tx = mt % prm.tiles_x;
+      const int ty = (mt / prm.tiles_x) % prm.tiles_y;
+      const int b = mt / (prm.tiles_x * prm.tiles_y);
+      const uint32_t a = tile_i & 1u;
+      tc::mbar_wait(&acc_full[a], (tile_i >> 1) & 1u);
+      tc::fence_after_sync();
+      const int oy = ty * CV_TH + (row >> 4), ox = tx * CV_TW + (row & 15);
+      const bool live = (oy < prm.OH) && (ox < prm.OW);
+      const size_t pix = ((size_t)b * prm.OH + oy) * prm.OW + ox;
+      const int n_base = nt * NT;
+      for (int n0 = 0; n0 < NT; n0 += 16) {
+        uint32_t r[16];
+        tc::tmem_ld16(tmem + lane_base + a * NT + n0, r);
+        tc::wait_ld();
+        if (live) {
+          const int n = n_base + n0;
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (prm.bias ? __ldg(prm.bias + n + j) : 0.f);
+          if (prm.res_hi) {
+            const uint4* rh = reinterpret_cast<const uint4*>(prm.res_hi + pix * prm.Cout + n);
+            const uint4* rl = reinterpret_cast<const uint4*>(prm.res_lo + pix * prm.Cout + n);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const uint4 h4 = __ldg(rh + q), l4 = __ldg(rl + q);
+              const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[8 * q + 2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+                v[8 * q + 2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], prm.act, prm.slope);
+          if (prm.out_hi) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tc::split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+            uint4* oh = reinterpret_cast<uint4*>(prm.out_hi + pix * prm.Cout + n);
+            uint4* ol = reinterpret_cast<uint4*>(prm.out_lo + pix * prm.Cout + n);
+            oh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            oh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          }
+          if (prm.out_f32) {
+            float4* of = reinterpret_cast<float4*>(prm.out_f32 + pix * prm.Cout + n);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) of[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        }
+      }
+      tc::fence_before_sync();
+      tc::mbar_arrive(&acc_empty[a]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: plan objects (tensor maps are encoded once, launches are cheap and graph-capturable)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct ConvPlan {
+  ConvKParams k;
+  size_t smem;
+  int grid;
+};
+
+// C-ABI description of one segment / one conv (plain pointers and sizes)
+struct b200_conv_seg {
+  const void* in_hi;  // NHWC bf16 [B,H,W,C]
+  const void* in_lo;
+  int H, W, C, ksize, stride, pad;
+};
+struct b200_conv_desc {
+  b200_conv_seg seg[CV_MAX_SEG];
+  int nseg;
+  const void* wimage;
+  const float* bias;
+  const void* res_hi;
+  const void* res_lo;
+  void* out_hi;
+  void* out_lo;
+  float* out_f32;
+  int B, OH, OW, Cout, act;
+  float slope;
+};
+
+extern "C" int b200_conv_ntile(int Cout) { return Cout <= 128 ? Cout : 128; }
+
+extern "C" long long b200_conv_wimage_bytes(const int* seg_C, const int* seg_ksize, int nseg, int Cout) {
+  long long chunks = 0;
+  for (int s = 0; s < nseg; ++s) chunks += (long long)seg_ksize[s] * seg_ksize[s] * ((seg_C[s] + 63) / 64);
+  const int NT = b200_conv_ntile(Cout);
+  return chunks * ((Cout + NT - 1) / NT) * NT * 256;
+}
+
+extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
+  B200_CHECK_ARG(d && plan_out, "conv_create: null pointer");
+  B200_CHECK_ARG(d->nseg >= 1 && d->nseg <= CV_MAX_SEG, "conv_create: 1..%d segments (got %d)", CV_MAX_SEG, d->nseg);
+  B200_CHECK_ARG(d->Cout % 16 == 0 && d->Cout >= 16, "conv_create: Cout must be a multiple of 16 (got %d)", d->Cout);
+  B200_CHECK_ARG(d->Cout <= 128 || d->Cout % 128 == 0, "conv_create: Cout > 128 must be a multiple of 128 (got %d)",
+                 d->Cout);
+  B200_CHECK_ARG(d->wimage && (d->out_hi || d->out_f32), "conv_create: missing weights or output");
+  B200_CHECK_ARG((d->out_hi == nullptr) == (d->out_lo == nullptr), "conv_create: out_hi/out_lo must come together");
+  EncodeTiledFn enc = get_encode();
+  B200_CHECK_ARG(enc != nullptr, "conv_create: cuTensorMapEncodeTiled not available from the driver");
+  ConvPlan* p = new ConvPlan();
+  ConvKParams& k = p->k;
+  memset(&k, 0, sizeof(k));
+  k.nseg = d->nseg;
+  k.total_chunks = 0;
+  for (int s = 0; s < d->nseg; ++s) {
+    const b200_conv_seg& sg = d->seg[s];
+    if (!(sg.in_hi && sg.in_lo) || sg.C % 8 != 0 || sg.C < 8 || !(sg.ksize == 1 || sg.ksize == 3) ||
+        !(sg.stride == 1 || sg.stride == 2) || ((uintptr_t)sg.in_hi & 15) || ((uintptr_t)sg.in_lo & 15)) {
+      delete p;
+      b200_set_error("conv_create: segment %d invalid (C=%d must be a multiple of 8, ksize 1|3, stride 1|2, "
+                     "16-byte aligned planes)", s, sg.C);
+      return -1;
+    }
+    // output size implied by this segment must match
+    const int oh = (sg.H + 2 * sg.pad - sg.ksize) / sg.stride + 1, ow = (sg.W + 2 * sg.pad - sg.ksize) / sg.stride + 1;
+    if (oh != d->OH || ow != d->OW) {
+      delete p;
+      b200_set_error("conv_create: segment %d gives %dx%d outputs, conv says %dx%d", s, oh, ow, d->OH, d->OW);
+      return -1;
+    }
+    k.seg_C[s] = sg.C;
+    k.seg_ksize[s] = sg.ksize;
+    k.seg_stride[s] = sg.stride;
+    k.seg_pad[s] = sg.pad;
+    k.total_chunks += sg.ksize * sg.ksize * ((sg.C + 63) / 64);
+    cuuint64_t gdim[4] = {(cuuint64_t)sg.C, (cuuint64_t)sg.W, (cuuint64_t)sg.H, (cuuint64_t)d->B};
+    cuuint64_t gstr[3] = {(cuuint64_t)sg.C * 2, (cuuint64_t)sg.W * sg.C * 2, (cuuint64_t)sg.H * sg.W * sg.C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(CV_TW * sg.stride), (cuuint32_t)(CV_TH * sg.stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)sg.stride, (cuuint32_t)sg.stride, 1};
+    for (int part = 0; part < 2; ++part) {
+      CUresult r = enc(&k.maps[2 * s + part], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                       const_cast<void*>(part ? sg.in_lo : sg.in_hi), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        delete p;
+        b200_set_error("conv_create: cuTensorMapEncodeTiled failed (%d) for segment %d (C=%d H=%d W=%d stride=%d)",
+                       (int)r, s, sg.C, sg.H, sg.W, sg.stride);
+        return -2;
+      }
+    }
+  }
+  k.wimage = (const uint8_t*)d->wimage;
+  k.bias = d->bias;
+  k.res_hi = (const __nv_bfloat16*)d->res_hi;
+  k.res_lo = (const __nv_bfloat16*)d->res_lo;
+  k.out_hi = (__nv_bfloat16*)d->out_hi;
+  k.out_lo = (__nv_bfloat16*)d->out_lo;
+  k.out_f32 = d->out_f32;
+  k.B = d->B;
+  k.OH = d->OH;
+  k.OW = d->OW;
+  k.Cout = d->Cout;
+  k.NT = b200_conv_ntile(d->Cout);
+  k.n_ntiles = (d->Cout + k.NT - 1) / k.NT;
+  k.act = d->act;
+  k.slope = d->slope;
+  k.tiles_x = (d->OW + CV_TW - 1) / CV_TW;
+  k.tiles_y = (d->OH + CV_TH - 1) / CV_TH;
+  const size_t stage_bytes = 32768 + (((size_t)k.NT * 256 + 1023) & ~(size_t)1023);
+  int S = (int)((200 * 1024) / stage_bytes);
+  if (S > 6) S = 6;
+  if (S > k.total_chunks) S = k.total_chunks < 2 ? 2 : k.total_chunks;
+  k.stages = S;
+  p->smem = 1024 + S * stage_bytes + (2 * S + 4) * 8 + 16;
+  int dev = 0, n_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int items = k.B * k.tiles_x * k.tiles_y * k.n_ntiles;
+  p->grid = items < n_sm ? items : n_sm;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      delete p;
+      b200_set_error("conv_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return -2;
+    }
+    attr_done = true;
+  }
+  *plan_out = p;
+  return 0;
+}
+
+extern "C" int b200_conv_run(void* plan, void* stream) {
+  B200_CHECK_ARG(plan, "conv_run: null plan");
+  ConvPlan* p = (ConvPlan*)plan;
+  conv_tc_kernel<<<p->grid, CV_THREADS, p->smem, (cudaStream_t)stream>>>(p->k);
+  B200_CHECK_LAUNCH("conv_run");
+  return 0;
+}
+
+extern "C" int b200_conv_destroy(void* plan) {
+  delete (ConvPlan*)plan;
+  return 0;
+}

@@ -4,6 +4,9 @@
 //   mode 1: A as bf16 from tensor memory (TS), B from smem     -> checks the TMEM A layout
 //   mode 2: split-bf16 (hi*hi + hi*lo + lo*hi), A from TMEM    -> checks the fp32-grade number format
 //   mode 3: split-bf16, A from shared memory
+//   mode 4: bf16 SS with the A rows taken from inside a larger swizzled "halo patch": M-tile row r lives
+//           at patch row (r/8)*10 + (r%8) + 11, i.e. descriptor start shifted by a non-multiple of 8 rows
+//           and an 8-row-group stride of 1280 B -- the addressing an implicit-GEMM conv tap needs
 // The GPU tests compare D against a host matmul, so a layout mistake shows up as a numeric error
 // in a 30-line kernel instead of inside the fused ones.
 #include "common.cuh"
@@ -28,7 +31,8 @@ umma_probe_kernel(const float* __restrict__ A, const float* __restrict__ Bm, flo
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const bool split = mode >= 2;
+  const bool split = (mode == 2 || mode == 3);
+  const bool halo = (mode == 4);
   const bool a_in_tmem = (mode == 1 || mode == 2);
 
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
@@ -65,9 +69,10 @@ umma_probe_kernel(const float* __restrict__ A, const float* __restrict__ Bm, flo
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           int k = k0 + 2 * j;
-          uint32_t off = (k / 64) * 16384 + tc::sw128_offset(row, k % 64);
+          const int srow = halo ? (row / 8) * 10 + (row % 8) + 11 : row;
+          uint32_t off = (k / 64) * 16384 + tc::sw128_offset(srow, k % 64);
           *reinterpret_cast<uint32_t*>(a_hi + off) = hi[j];
-          *reinterpret_cast<uint32_t*>(a_lo + off) = lo[j];
+          if (!halo) *reinterpret_cast<uint32_t*>(a_lo + off) = lo[j];  // the halo patch spills into a_lo's space
         }
       }
     }
@@ -93,7 +98,8 @@ umma_probe_kernel(const float* __restrict__ A, const float* __restrict__ Bm, flo
         if (a_in_tmem) {
           tc::mma_ts(tmem, a_t + ks * 8, bdesc, idesc, accum);
         } else {
-          const uint64_t adesc = tc::smem_desc_sw128(tc::smem_u32(as + chunk * 16384) + sub * 32);
+          const uint64_t adesc = halo ? tc::smem_desc_sw128(tc::smem_u32(as) + 11 * 128 + sub * 32, 1280)
+                                      : tc::smem_desc_sw128(tc::smem_u32(as + chunk * 16384) + sub * 32);
           tc::mma_ss(tmem, adesc, bdesc, idesc, accum);
         }
         accum = 1;
@@ -119,7 +125,8 @@ extern "C" int b200_umma_probe(const float* A, const float* Bm, float* D, int K,
   B200_CHECK_ARG(A && Bm && D, "umma_probe: null pointer");
   B200_CHECK_ARG(K % 64 == 0 && K >= 64 && K <= PROBE_MAX_K, "umma_probe: K must be 64, 128 or 192");
   B200_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= PROBE_MAX_N, "umma_probe: N must be a multiple of 16 up to 128");
-  B200_CHECK_ARG(mode >= 0 && mode <= 3, "umma_probe: mode 0..3");
+  B200_CHECK_ARG(mode >= 0 && mode <= 4, "umma_probe: mode 0..4");
+  B200_CHECK_ARG(mode != 4 || K == 64, "umma_probe: mode 4 needs K == 64");
   const int nchunk = K / 64;
   size_t smem = 1024 + (size_t)nchunk * (2 * 16384 + 2 * N * 128) + 64;
   B200_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

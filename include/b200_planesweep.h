@@ -78,6 +78,37 @@ int b200_fv_mlp_tc(const float* cur, const float* src, const float* cams, const 
                    int h, int w, int D, void* stream);
 int b200_fv_tc_wimage_bytes(int K);
 
+/* ---- tensor-core convolution (csrc/conv_tc.cu) ------------------------------------------------
+ * Implicit-GEMM conv over NHWC split-bf16 activations (two bf16 planes hi/lo with x = hi + lo).
+ * Replaces nn.Conv2d + bias + activation + residual + torch.cat of modules/layers.py:8-95 (BasicBlock),
+ * modules/networks.py:186-215 (CVEncoder), :20-84 (BDDecoderPP), modules/networks_fast.py:10-99.
+ * A conv is described once (b200_conv_create encodes the TMA tensor maps) and then launched any number
+ * of times (b200_conv_run only enqueues a kernel, so it is CUDA-graph capturable). */
+typedef struct {
+  const void* in_hi; /* NHWC bf16 [B,H,W,C], 16-byte aligned, C % 8 == 0 */
+  const void* in_lo;
+  int H, W, C, ksize /*1|3*/, stride /*1|2*/, pad;
+} b200_conv_seg;
+typedef struct {
+  b200_conv_seg seg[4]; /* K-segments: concatenated inputs and/or the shortcut conv of a BasicBlock */
+  int nseg;
+  const void* wimage;   /* packed weights, b200_conv_wimage_bytes() bytes: [n-tile][chunk][hi|lo] SW128 tiles,
+                           chunks ordered (segment, tap row-major, 64-channel block), zero-padded channel tails */
+  const float* bias;    /* [Cout] or NULL */
+  const void* res_hi;   /* optional identity residual NHWC [B,OH,OW,Cout] (layers.py:92) */
+  const void* res_lo;
+  void* out_hi;         /* NHWC [B,OH,OW,Cout] bf16 planes (both or neither) */
+  void* out_lo;
+  float* out_f32;       /* optional NHWC fp32 copy of the output */
+  int B, OH, OW, Cout /* %16==0; >128 => %128==0 */, act /*0 none,1 leaky(slope),2 ELU,3 ReLU*/;
+  float slope;
+} b200_conv_desc;
+int b200_conv_ntile(int Cout);
+long long b200_conv_wimage_bytes(const int* seg_C, const int* seg_ksize, int nseg, int Cout);
+int b200_conv_create(const b200_conv_desc* desc, void** plan_out);
+int b200_conv_run(void* plan, void* stream);
+int b200_conv_destroy(void* plan);
+
 /* Self-test of the tcgen05/TMEM building blocks: D[128,N] = A[128,K] * Bm[N,K]^T on one CTA.
  *   mode 0: bf16 operands from shared memory; 1: A from tensor memory; 2/3: split-bf16 (fp32-grade)
  *   with A from tensor / shared memory.  K in {64,128,192}, N multiple of 16 up to 128. */

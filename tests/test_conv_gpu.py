@@ -1,0 +1,69 @@
+"""Tensor-core convolution kernel vs torch fp64 conv2d (test-side reference of the same op)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from implicit_depth_b200.conv import ConvPlan, SplitAct, pack_conv_weights
+
+pytestmark = pytest.mark.gpu
+
+
+def act_ref(x, act, slope):
+    if act == "lrelu":
+        return F.leaky_relu(x, slope)
+    if act == "elu":
+        return F.elu(x)
+    if act == "relu":
+        return F.relu(x)
+    return x
+
+
+# (B, H, W, [segment channel counts], Cout, ksize, stride, act, residual)
+CASES = [
+    (1, 8, 16, [64], 64, 3, 1, "none", False),
+    (2, 24, 32, [64], 64, 3, 1, "lrelu", True),
+    (1, 16, 16, [24], 64, 3, 1, "lrelu", False),      # channel tail via TMA OOB fill
+    (1, 12, 16, [64, 48], 64, 3, 1, "lrelu", False),  # concat as two K-segments
+    (2, 15, 20, [128], 128, 3, 1, "elu", False),      # ragged spatial size
+    (1, 16, 32, [64], 128, 1, 1, "none", False),      # 1x1
+    (1, 16, 32, [64], 128, 3, 2, "lrelu", False),     # stride 2 through tensor-map element strides
+    (1, 24, 32, [160, 256], 256, 3, 1, "lrelu", False),  # two N tiles
+    (1, 8, 16, [128], 16, 3, 1, "none", False),       # narrow N (matching head)
+    (3, 6, 8, [384, 256], 384, 3, 1, "relu", False),  # coarsest level, three N tiles
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_matches_fp64(case):
+    B, H, W, segC, Cout, k, stride, act, use_res = case
+    torch.manual_seed(sum(segC) + Cout + k + stride)
+    xs = [torch.randn(B, C, H, W, device="cuda") for C in segC]
+    ws = [torch.randn(Cout, C, k, k, device="cuda") / (C * k * k) ** 0.5 for C in segC]
+    bias = torch.randn(Cout, device="cuda")
+    pad = k // 2
+    acts = [SplitAct.from_nchw_torch(x) for x in xs]
+    OH = (H + 2 * pad - k) // stride + 1
+    OW = (W + 2 * pad - k) // stride + 1
+    out = SplitAct(B, OH, OW, Cout, "cuda")
+    out.hi.fill_(float("nan")); out.lo.fill_(float("nan"))
+    out_f32 = torch.full((B, OH, OW, Cout), float("nan"), device="cuda")
+    res = None
+    if use_res:
+        rx = torch.randn(B, Cout, OH, OW, device="cuda")
+        res = SplitAct.from_nchw_torch(rx)
+    wimage = pack_conv_weights(ws, segC, Cout)
+    plan = ConvPlan([(a, k, stride, pad) for a in acts], wimage, bias, out, B, Cout, act=act, slope=0.2,
+                    residual=res, out_f32=out_f32)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = sum(F.conv2d(a.float_nchw().double(), w.double(), None, stride, pad) for a, w in zip(acts, ws))
+    ref = ref + bias.double().view(1, -1, 1, 1)
+    if use_res:
+        ref = ref + res.float_nchw().double()
+    ref = act_ref(ref, act, 0.2)
+    got = out.float_nchw().double()
+    got32 = out_f32.permute(0, 3, 1, 2).double()
+    scale = ref.abs().max().item()
+    assert torch.isfinite(got).all()
+    assert (got32 - ref).abs().max().item() < 2e-5 * scale
+    assert (got - ref).abs().max().item() < 3e-5 * scale  # + split-bf16 storage rounding (2^-17)

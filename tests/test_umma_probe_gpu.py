@@ -37,3 +37,14 @@ def test_split_bf16_is_fp32_grade(mode, K, N):
     ref = (A.double() @ Bm.double().t())
     rel = ((D.double() - ref).abs().max() / ref.abs().max()).item()
     assert rel < 2e-5, f"mode {mode}: split-bf16 relative error {rel}"
+
+
+def test_halo_patch_descriptor():
+    """Shifted start address (11 rows) + 1280-byte group stride inside a swizzled patch."""
+    torch.manual_seed(5)
+    A = torch.randn(128, 64, device="cuda")
+    Bm = torch.randn(128, 64, device="cuda")
+    D = run_probe(A, Bm, 4)
+    ref = (A.bfloat16().double() @ Bm.bfloat16().double().t()).float()
+    err = (D - ref).abs().max().item()
+    assert err < 1e-3 * ref.abs().max().item(), f"halo descriptor: max err {err}"

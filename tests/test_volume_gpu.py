@@ -152,8 +152,12 @@ def test_linearity_and_batch_invariance_full_size():
     one = {k: v[1:2].contiguous() for k, v in t.items()}
     c3, l3, _, _ = mgr(min_depth=mn, max_depth=mx, **one)
     assert torch.equal(c3, c1[1:2]) and torch.equal(l3, l1[1:2])
+    torch.manual_seed(11)
+    ref_mlp = B200FeatureVolumeManager(h, w, num_depth_bins=D).mlp
     for impl in ("tc", "simt"):
-        fv = B200FeatureVolumeManager(h, w, num_depth_bins=D, impl=impl).cuda()
+        fv = B200FeatureVolumeManager(h, w, num_depth_bins=D, impl=impl)
+        fv.mlp = ref_mlp  # same weights for both kernels (moved by reference like to_fast, cost_volume.py:714)
+        fv = fv.cuda()
         v1, fl1, _, m1 = fv(min_depth=mn, max_depth=mx, return_mask=True, **t)
         v3, fl3, _, m3 = fv(min_depth=mn, max_depth=mx, return_mask=True, **one)
         assert torch.equal(v3, v1[1:2]) and torch.equal(fl3, fl1[1:2]) and torch.equal(m3, m1[1:2])
