@@ -30,6 +30,15 @@ SIGNATURES = {
     "b200_conv_destroy": [ctypes.c_void_p],
     "b200_conv_ntile": [c_i],
     "b200_conv_wimage_bytes": [ctypes.c_void_p, ctypes.c_void_p, c_i, c_i],
+    "b200_f32_to_split": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_ll, c_ll, c_ll, c_ll, ctypes.c_void_p],
+    "b200_split_to_nchw": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, ctypes.c_void_p],
+    "b200_upsample2x": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, ctypes.c_void_p],
+    "b200_instance_norm": [c_f] * 7 + [c_i] * 6 + [ctypes.c_float, ctypes.c_float, ctypes.c_void_p],
+    "b200_instance_norm_ws_bytes": [c_i, c_i, ctypes.c_void_p, ctypes.c_void_p],
+    "b200_stem_conv7": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
+    "b200_maxblurpool": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, ctypes.c_void_p],
+    "b200_pack_depth_prior": [c_f, c_ll, c_f, c_ll, c_f, c_f, c_i, c_i, ctypes.c_void_p],
+    "b200_gather_channel": [c_f, c_i, c_i, c_f, c_ll, c_i, c_i, ctypes.c_void_p],
     "b200_umma_probe": [c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
 }
 

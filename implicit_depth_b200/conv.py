@@ -57,42 +57,37 @@ def ntile(cout):
     return cout if cout <= 128 else 128
 
 
-def _sw128_rows(mat):
-    """[R, 64] bf16 (R multiple of 8) -> swizzled bytes (R x 128 B, 16-byte chunk j of row r at j ^ (r & 7))."""
-    R = mat.shape[0]
-    t = mat.reshape(R, 8, 8)
-    r = torch.arange(R, device=mat.device).view(R, 1, 1)
-    j = torch.arange(8, device=mat.device).view(1, 8, 1)
-    idx = (j ^ (r & 7)).expand(R, 8, 8)
-    return torch.gather(t, 1, idx).contiguous().view(torch.uint8).reshape(-1)
+def _swizzle_last(t):
+    """[..., R, 64] bf16 with R % 8 == 0 -> same shape, 16-byte chunk j of row r moved to chunk j ^ (r & 7)."""
+    R = t.shape[-2]
+    v = t.reshape(*t.shape[:-1], 8, 8)
+    r = torch.arange(R, device=t.device).view(R, 1, 1)
+    j = torch.arange(8, device=t.device).view(1, 8, 1)
+    idx = (j ^ (r & 7)).expand(R, 8, 8).expand(v.shape)
+    return torch.gather(v, -2, idx).reshape(t.shape)
 
 
 def pack_conv_weights(weights, seg_channels, cout):
     """weights: list (one per segment) of [Cout, C_s, k, k] fp32 tensors.  Returns the uint8 image
     [n_ntiles][chunk][hi NT x 64 | lo NT x 64] in the producer's chunk order (segment, tap, 64-channel block)."""
-    dev = weights[0].device
     NT = ntile(cout)
     n_nt = (cout + NT - 1) // NT
     chunks = []
     for w, C in zip(weights, seg_channels):
         k = w.shape[-1]
-        assert w.shape[0] == cout and w.shape[1] == C
-        for dy in range(k):
-            for dx in range(k):
-                for cb in range((C + 63) // 64):
-                    blk = torch.zeros((cout, 64), device=dev, dtype=torch.float32)
-                    c1 = min(C, cb * 64 + 64)
-                    blk[:, : c1 - cb * 64] = w[:, cb * 64:c1, dy, dx]
-                    chunks.append(blk)
-    allw = torch.stack(chunks, 0)  # [chunks, Cout, 64]
+        assert w.shape[0] == cout and w.shape[1] == C and w.shape[2] == k
+        Cp = (C + 63) // 64 * 64
+        wp = torch.zeros((cout, Cp, k, k), device=w.device, dtype=torch.float32)
+        wp[:, :C] = w.detach().float()
+        # [Cout, Cp/64, 64, k, k] -> [k, k, Cp/64, Cout, 64] -> [chunks, Cout, 64]
+        chunks.append(wp.view(cout, Cp // 64, 64, k, k).permute(3, 4, 1, 0, 2).reshape(-1, cout, 64))
+    allw = torch.cat(chunks, 0)  # [Q, Cout, 64]
+    Q = allw.shape[0]
     hi = allw.to(torch.bfloat16)
     lo = (allw - hi.float()).to(torch.bfloat16)
-    parts = []
-    for nt in range(n_nt):
-        for q in range(allw.shape[0]):
-            parts.append(_sw128_rows(hi[q, nt * NT:(nt + 1) * NT]))
-            parts.append(_sw128_rows(lo[q, nt * NT:(nt + 1) * NT]))
-    return torch.cat(parts).contiguous()
+    both = torch.stack([hi, lo], 1).view(Q, 2, n_nt, NT, 64)  # [Q, part, nt, NT, 64]
+    both = _swizzle_last(both).permute(2, 0, 1, 3, 4).contiguous()  # [nt, Q, part, NT, 64]
+    return both.view(torch.uint8).reshape(-1)
 
 
 class ConvPlan:

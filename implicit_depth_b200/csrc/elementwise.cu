@@ -1,0 +1,450 @@
+// Memory-bound helper kernels of the conv path.  Activations are NHWC split-bf16 (hi, lo planes).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// load 8 consecutive channels of a split activation as fp32
+__device__ __forceinline__ void load8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t off, float v[8]) {
+  const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + off));
+  const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + off));
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e] = bf_lo(hw[e]) + bf_lo(lw[e]);
+    v[2 * e + 1] = bf_hi(hw[e]) + bf_hi(lw[e]);
+  }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, const float v[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) tc::split2(v[2 * e], v[2 * e + 1], h[e], l[e]);
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ---------------------------------------------------------------------------------------
+// fp32 [B,C,H,W] with arbitrary strides (NCHW or channels_last) -> NHWC split-bf16.
+// 32 pixels x 32 channels through shared memory so both sides are coalesced.
+// ---------------------------------------------------------------------------------------
+__global__ void f32_to_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, int C, int HW, int W, long long sB, long long sC,
+                                    long long sH, long long sW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 256 threads: 8 rows of 32
+  const bool chan_fast = (sC == 1);
+  for (int r = ty; r < 32; r += 8) {
+    // read: make the fastest-varying input index follow tx
+    const int c = chan_fast ? c0 + tx : c0 + r;
+    const int p = chan_fast ? p0 + r : p0 + tx;
+    float v = 0.f;
+    if (c < C && p < HW) {
+      const int y = p / W, x = p - y * W;
+      v = in[(size_t)b * sB + (size_t)c * sC + (size_t)y * sH + (size_t)x * sW];
+    }
+    if (chan_fast) tile[r][tx] = v; else tile[tx][r] = v;  // tile[pixel][channel]
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r, c = c0 + tx;
+    if (p < HW && c < C) {
+      const float v = tile[r][tx];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const size_t o = ((size_t)b * HW + p) * C + c;
+      hi[o] = h;
+      lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+extern "C" int b200_f32_to_split(const float* in, void* hi, void* lo, int B, int C, int H, int W, long long sB,
+                                 long long sC, long long sH, long long sW, void* stream) {
+  B200_CHECK_ARG(in && hi && lo && B > 0 && C > 0 && H > 0 && W > 0, "f32_to_split: bad arguments");
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, B);
+  f32_to_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, C, H * W, W,
+                                                             sB, sC, sH, sW);
+  B200_CHECK_LAUNCH("f32_to_split");
+  return 0;
+}
+
+// NHWC split-bf16 -> fp32 NCHW (dense)
+__global__ void split_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                     float* __restrict__ out, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r, c = c0 + tx;
+    float v = 0.f;
+    if (p < HW && c < C) {
+      const size_t o = ((size_t)b * HW + p) * C + c;
+      v = __bfloat162float(hi[o]) + __bfloat162float(lo[o]);
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, p = p0 + tx;
+    if (c < C && p < HW) out[((size_t)b * C + c) * HW + p] = tile[tx][r];
+  }
+}
+
+extern "C" int b200_split_to_nchw(const void* hi, const void* lo, float* out, int B, int C, int H, int W,
+                                  void* stream) {
+  B200_CHECK_ARG(hi && lo && out && B > 0 && C > 0 && H > 0 && W > 0, "split_to_nchw: bad arguments");
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, B);
+  split_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, out,
+                                                              C, H * W);
+  B200_CHECK_LAUNCH("split_to_nchw");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// x2 upsampling: mode 0 = bilinear, align_corners=False (utils/generic_utils.py:94-103, used by
+// BDDecoderPP networks.py:72,75); mode 1 = nearest (networks_fast.py:42).  One thread = one output
+// pixel x 8 channels.
+// ---------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ ih, const __nv_bfloat16* __restrict__ il,
+                                  __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, int B, int H, int W,
+                                  int C, int mode) {
+  const int cg = C >> 3;
+  const size_t total = (size_t)B * (2 * H) * (2 * W) * cg;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg);
+    size_t r = i / cg;
+    const int ox = (int)(r % (2 * W));
+    r /= (2 * W);
+    const int oy = (int)(r % (2 * H));
+    const int b = (int)(r / (2 * H));
+    float v[8];
+    const size_t img = (size_t)b * H * W;
+    if (mode == 1) {
+      load8(ih, il, (img + (size_t)(oy >> 1) * W + (ox >> 1)) * C + c8 * 8, v);
+    } else {
+      // ATen upsample_bilinear2d: src = max(0, (dst + 0.5) * 0.5 - 0.5)
+      const float sy = fmaxf(0.f, (oy + 0.5f) * 0.5f - 0.5f), sx = fmaxf(0.f, (ox + 0.5f) * 0.5f - 0.5f);
+      const int y0 = (int)sy, x0 = (int)sx;
+      const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+      const float ly = sy - y0, lx = sx - x0;
+      float a[8], bq[8], c[8], d[8];
+      load8(ih, il, (img + (size_t)y0 * W + x0) * C + c8 * 8, a);
+      load8(ih, il, (img + (size_t)y0 * W + x1) * C + c8 * 8, bq);
+      load8(ih, il, (img + (size_t)y1 * W + x0) * C + c8 * 8, c);
+      load8(ih, il, (img + (size_t)y1 * W + x1) * C + c8 * 8, d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        v[e] = (1.f - ly) * ((1.f - lx) * a[e] + lx * bq[e]) + ly * ((1.f - lx) * c[e] + lx * d[e]);
+    }
+    store8(oh, ol, (((size_t)b * 2 * H + oy) * 2 * W + ox) * C + c8 * 8, v);
+  }
+}
+
+extern "C" int b200_upsample2x(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int B, int H, int W,
+                               int C, int mode, void* stream) {
+  B200_CHECK_ARG(in_hi && in_lo && out_hi && out_lo && B > 0 && H > 0 && W > 0, "upsample2x: bad arguments");
+  B200_CHECK_ARG(C % 8 == 0, "upsample2x: C must be a multiple of 8 (got %d)", C);
+  B200_CHECK_ARG(mode == 0 || mode == 1, "upsample2x: mode 0 (bilinear) or 1 (nearest)");
+  const size_t total = (size_t)B * 4 * H * W * (C / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample2x_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo,
+                                                             (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, B, H, W,
+                                                             C, mode);
+  B200_CHECK_LAUNCH("upsample2x");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// InstanceNorm2d (affine=False, eps=1e-5, biased variance; networks.py:277,283).
+// Deterministic two-stage reduction (no atomics): results of one image never depend on what else
+// is in the batch -- the property the reference protects by running its encoder unbatched
+// (bd_model.py:149-160, depth_model.py:235-241).
+// ---------------------------------------------------------------------------------------
+#define IN_SLICES 32
+__global__ void instnorm_partial_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                        double* __restrict__ partial, int HW, int C) {
+  const int b = blockIdx.y, sl = blockIdx.x;
+  const int c = threadIdx.x;  // blockDim.x == C
+  const int p_begin = (int)((long long)HW * sl / IN_SLICES), p_end = (int)((long long)HW * (sl + 1) / IN_SLICES);
+  double s = 0.0, ss = 0.0;
+  for (int p = p_begin; p < p_end; ++p) {
+    const size_t o = ((size_t)b * HW + p) * C + c;
+    const float v = __bfloat162float(hi[o]) + __bfloat162float(lo[o]);
+    s += v;
+    ss += (double)v * v;
+  }
+  double* dst = partial + (((size_t)b * IN_SLICES + sl) * C + c) * 2;
+  dst[0] = s;
+  dst[1] = ss;
+}
+__global__ void instnorm_final_kernel(const double* __restrict__ partial, float* __restrict__ stats, int HW, int C,
+                                      float eps) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  double s = 0.0, ss = 0.0;
+  for (int sl = 0; sl < IN_SLICES; ++sl) {
+    const double* src = partial + (((size_t)b * IN_SLICES + sl) * C + c) * 2;
+    s += src[0];
+    ss += src[1];
+  }
+  const double mean = s / HW;
+  const double var = fmax(ss / HW - mean * mean, 0.0);
+  stats[((size_t)b * C + c) * 2] = (float)mean;
+  stats[((size_t)b * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+// apply: y = (x - mean) * rstd, optional LeakyReLU; output either split NHWC with a replicated border of
+// `pad` pixels (feeds the padding_mode="replicate" conv of networks.py:279-282 as a plain valid conv) or
+// fp32 pixel-major [B, HW, C] (the matching features the volume kernels gather).
+__global__ void instnorm_apply_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                      const float* __restrict__ stats, __nv_bfloat16* __restrict__ oh,
+                                      __nv_bfloat16* __restrict__ ol, float* __restrict__ of32, int B, int H, int W,
+                                      int C, int pad, int act, float slope) {
+  const int cg = C >> 3;
+  const int OH = H + 2 * pad, OW = W + 2 * pad;
+  const size_t total = (size_t)B * OH * OW * cg;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg);
+    size_t r = i / cg;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const int b = (int)(r / OH);
+    const int y = min(max(oy - pad, 0), H - 1), x = min(max(ox - pad, 0), W - 1);
+    float v[8];
+    load8(hi, lo, (((size_t)b * H + y) * W + x) * C + c8 * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float* st = stats + ((size_t)b * C + c8 * 8 + e) * 2;
+      float t = (v[e] - st[0]) * st[1];
+      if (act == 1) t = t >= 0.f ? t : t * slope;
+      v[e] = t;
+    }
+    const size_t o = (((size_t)b * OH + oy) * OW + ox) * C + c8 * 8;
+    if (oh) store8(oh, ol, o, v);
+    if (of32) {
+      *reinterpret_cast<float4*>(of32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(of32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
+extern "C" int b200_instance_norm(const void* in_hi, const void* in_lo, double* partial_ws, float* stats_ws,
+                                  void* out_hi, void* out_lo, float* out_f32, int B, int H, int W, int C, int pad,
+                                  int act, float slope, float eps, void* stream) {
+  B200_CHECK_ARG(in_hi && in_lo && partial_ws && stats_ws && (out_hi || out_f32), "instance_norm: null pointer");
+  B200_CHECK_ARG(C % 8 == 0 && C <= 1024, "instance_norm: C must be a multiple of 8, at most 1024 (got %d)", C);
+  B200_CHECK_ARG(!(out_f32 && pad != 0), "instance_norm: fp32 output has no border");
+  cudaStream_t st = (cudaStream_t)stream;
+  instnorm_partial_kernel<<<dim3(IN_SLICES, B), C, 0, st>>>((const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo,
+                                                            partial_ws, H * W, C);
+  instnorm_final_kernel<<<B, C, 0, st>>>(partial_ws, stats_ws, H * W, C, eps);
+  const size_t total = (size_t)B * (H + 2 * pad) * (W + 2 * pad) * (C / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  instnorm_apply_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo, stats_ws,
+                                               (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32, B, H, W, C,
+                                               pad, act, slope);
+  B200_CHECK_LAUNCH("instance_norm");
+  return 0;
+}
+extern "C" int b200_instance_norm_ws_bytes(int B, int C, long long* partial_bytes, long long* stats_bytes) {
+  *partial_bytes = (long long)B * IN_SLICES * C * 2 * sizeof(double);
+  *stats_bytes = (long long)B * C * 2 * sizeof(float);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Matching-encoder stem, antialiased ResNet-18 (antialiased-cnns 0.3, networks.py:250-270):
+//   conv 7x7 stride 2 pad 3 (3 -> 64, BatchNorm folded into weights/bias) + ReLU
+// fp32 NCHW image in, NHWC split-bf16 out.  CUDA-core kernel: 16x16 output pixels per CTA, input patch
+// and all weights in shared memory, 4 output pixels x 16 channels per thread.
+// ---------------------------------------------------------------------------------------
+#define STEM_T 16
+#define STEM_PATCH (2 * STEM_T + 5)  // 37
+__global__ void __launch_bounds__(256)
+stem_conv7_kernel(const float* __restrict__ img, const float* __restrict__ wt /*[147][64]*/,
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, int H,
+                  int W, int OH, int OW) {
+  extern __shared__ float sm[];
+  float* w_s = sm;                 // [147][64]
+  float* p_s = w_s + 147 * 64;     // [3][37][38]
+  const int n = blockIdx.z, oy0 = blockIdx.y * STEM_T, ox0 = blockIdx.x * STEM_T;
+  for (int i = threadIdx.x; i < 147 * 64; i += 256) w_s[i] = wt[i];
+  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+  for (int i = threadIdx.x; i < 3 * STEM_PATCH * STEM_PATCH; i += 256) {
+    const int c = i / (STEM_PATCH * STEM_PATCH), r = (i / STEM_PATCH) % STEM_PATCH, q = i % STEM_PATCH;
+    const int y = iy0 + r, x = ix0 + q;
+    float v = 0.f;
+    if (y >= 0 && y < H && x >= 0 && x < W) v = img[((size_t)n * 3 + c) * H * W + (size_t)y * W + x];
+    p_s[(c * STEM_PATCH + r) * (STEM_PATCH + 1) + q] = v;
+  }
+  __syncthreads();
+  // thread -> (pixel group of 4 along x, channel group of 16): 64 pixel groups x 4 channel groups
+  const int cgp = threadIdx.x & 3, pg = threadIdx.x >> 2;
+  const int py = pg >> 2, px4 = (pg & 3) * 4;
+  float acc[4][16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+  for (int c = 0; c < 3; ++c)
+    for (int dy = 0; dy < 7; ++dy) {
+      const float* prow = p_s + (c * STEM_PATCH + 2 * py + dy) * (STEM_PATCH + 1) + 2 * px4;
+#pragma unroll
+      for (int dx = 0; dx < 7; ++dx) {
+        const float* wp = w_s + ((c * 7 + dy) * 7 + dx) * 64 + cgp * 16;
+        float wv[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t = *reinterpret_cast<const float4*>(wp + 4 * q);
+          wv[4 * q] = t.x; wv[4 * q + 1] = t.y; wv[4 * q + 2] = t.z; wv[4 * q + 3] = t.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float xin = prow[2 * i + dx];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[i][j] = fmaf(xin, wv[j], acc[i][j]);
+        }
+      }
+    }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int oy = oy0 + py, ox = ox0 + px4 + i;
+    if (oy < OH && ox < OW) {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(acc[i][j] + bias[cgp * 16 + j], 0.f);
+      const size_t o = (((size_t)n * OH + oy) * OW + ox) * 64 + cgp * 16;
+      store8(oh, ol, o, v);
+      store8(oh, ol, o + 8, v + 8);
+    }
+  }
+}
+
+extern "C" int b200_stem_conv7(const float* img, const float* wt, const float* bias, void* out_hi, void* out_lo,
+                               int n_img, int H, int W, void* stream) {
+  B200_CHECK_ARG(img && wt && bias && out_hi && out_lo && n_img > 0 && H > 0 && W > 0, "stem_conv7: bad arguments");
+  const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
+  const size_t smem = sizeof(float) * (147 * 64 + 3 * STEM_PATCH * (STEM_PATCH + 1));
+  static bool done = false;
+  if (!done) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(stem_conv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done = true;
+  }
+  dim3 grid((OW + STEM_T - 1) / STEM_T, (OH + STEM_T - 1) / STEM_T, n_img);
+  stem_conv7_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(img, wt, bias, (__nv_bfloat16*)out_hi,
+                                                              (__nv_bfloat16*)out_lo, H, W, OH, OW);
+  B200_CHECK_LAUNCH("stem_conv7");
+  return 0;
+}
+
+// MaxPool2d(kernel 2, stride 1) followed by BlurPool(filt 4 = [1,3,3,1]^2/64, stride 2, reflect pad
+// (1,2,1,2)) -- the anti-aliased "maxpool" of antialiased-cnns 0.3 -- fused; H,W -> H/2,W/2 for even sizes.
+__global__ void maxblurpool_kernel(const __nv_bfloat16* __restrict__ ih, const __nv_bfloat16* __restrict__ il,
+                                   __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, int B, int H, int W,
+                                   int C, int OH, int OW) {
+  const int cg = C >> 3;
+  const int MH = H - 1, MW = W - 1;  // max-pooled size
+  const size_t total = (size_t)B * OH * OW * cg;
+  const float f[4] = {1.f, 3.f, 3.f, 1.f};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg);
+    size_t r = i / cg;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const int b = (int)(r / OH);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int a = 0; a < 4; ++a) {
+      int my = 2 * oy + a - 1;  // index into the reflect-padded max-pooled map (pad top 1)
+      my = my < 0 ? -my : (my >= MH ? 2 * (MH - 1) - my : my);
+      for (int q = 0; q < 4; ++q) {
+        int mx = 2 * ox + q - 1;
+        mx = mx < 0 ? -mx : (mx >= MW ? 2 * (MW - 1) - mx : mx);
+        float m[8], t[8];
+        const size_t base = ((size_t)b * H + my) * W + mx;
+        load8(ih, il, base * C + c8 * 8, m);
+        load8(ih, il, (base + 1) * C + c8 * 8, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], t[e]);
+        load8(ih, il, (base + W) * C + c8 * 8, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], t[e]);
+        load8(ih, il, (base + W + 1) * C + c8 * 8, t);
+        const float wgt = f[a] * f[q] * (1.f / 64.f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, fmaxf(m[e], t[e]), acc[e]);
+      }
+    }
+    store8(oh, ol, (((size_t)b * OH + oy) * OW + ox) * C + c8 * 8, acc);
+  }
+}
+
+extern "C" int b200_maxblurpool(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int B, int H, int W,
+                                int C, void* stream) {
+  B200_CHECK_ARG(in_hi && in_lo && out_hi && out_lo && B > 0 && H > 2 && W > 2, "maxblurpool: bad arguments");
+  B200_CHECK_ARG(C % 8 == 0, "maxblurpool: C must be a multiple of 8");
+  const int OH = (H - 1 + 3 - 4) / 2 + 1, OW = (W - 1 + 3 - 4) / 2 + 1;
+  const size_t total = (size_t)B * OH * OW * (C / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  maxblurpool_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo,
+                                                              (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, B, H, W,
+                                                              C, OH, OW);
+  B200_CHECK_LAUNCH("maxblurpool");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Binary-occupancy MLP glue (bd_model.py:412-442): the per-plane inputs that change with the
+// rendered depth plane -- depth (channel 0) and the optional temporal prior (channel 1) -- as an
+// 8-channel split NHWC tensor (zero padded) that enters the first layer as a 1x1-conv K-segment,
+// and the extraction of the single logit channel from the padded 16-channel last layer.
+// ---------------------------------------------------------------------------------------
+__global__ void pack_depth_prior_kernel(const float* __restrict__ depth, long long d_sB, const float* __restrict__ prior,
+                                        long long p_sB, __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol,
+                                        int B, int HW) {
+  const size_t total = (size_t)B * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW), p = (int)(i % HW);
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    v[0] = depth[(size_t)b * d_sB + p];
+    if (prior) v[1] = prior[(size_t)b * p_sB + p];
+    store8(oh, ol, i * 8, v);
+  }
+}
+extern "C" int b200_pack_depth_prior(const float* depth, long long depth_batch_stride, const float* prior,
+                                     long long prior_batch_stride, void* out_hi, void* out_lo, int B, int HW,
+                                     void* stream) {
+  B200_CHECK_ARG(depth && out_hi && out_lo && B > 0 && HW > 0, "pack_depth_prior: bad arguments");
+  int blocks = (int)(((size_t)B * HW + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_depth_prior_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(depth, depth_batch_stride, prior,
+                                                                   prior_batch_stride, (__nv_bfloat16*)out_hi,
+                                                                   (__nv_bfloat16*)out_lo, B, HW);
+  B200_CHECK_LAUNCH("pack_depth_prior");
+  return 0;
+}
+
+__global__ void gather_channel_kernel(const float* __restrict__ in, int C, int ch, float* __restrict__ out,
+                                      long long o_sB, int B, int HW) {
+  const size_t total = (size_t)B * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW), p = (int)(i % HW);
+    out[(size_t)b * o_sB + p] = in[i * C + ch];
+  }
+}
+extern "C" int b200_gather_channel(const float* in_nhwc, int C, int ch, float* out, long long out_batch_stride, int B,
+                                   int HW, void* stream) {
+  B200_CHECK_ARG(in_nhwc && out && ch >= 0 && ch < C && B > 0 && HW > 0, "gather_channel: bad arguments");
+  int blocks = (int)(((size_t)B * HW + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gather_channel_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in_nhwc, C, ch, out, out_batch_stride, B, HW);
+  B200_CHECK_LAUNCH("gather_channel");
+  return 0;
+}

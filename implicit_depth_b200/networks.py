@@ -1,0 +1,543 @@
+"""B200 versions of the reference's convolutional networks.
+
+Each class keeps the reference module's constructor arguments and state-dict keys (so its checkpoints
+load) but holds no PyTorch compute: `forward` builds -- once per input shape -- a static launch plan of
+hand-written sm_100a kernels (tcgen05 implicit-GEMM convs over NHWC split-bf16 activations, plus the
+layout / upsample / instance-norm kernels) and replays it.
+
+  ResnetMatchingEncoder  modules/networks.py:236-287   (antialiased ResNet-18 stem + IN head)
+  CVEncoder              modules/networks.py:186-215
+  BDDecoderPP            modules/networks.py:20-84     (UNet++)
+  SkipDecoder            modules/networks_fast.py:49-99
+  BinaryMLPNetwork       modules/networks.py:87-115    (+ BDModel.run_mlp_val, bd_model.py:412-442)
+  BasicBlock             modules/layers.py:34-95
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _abi
+from .conv import ConvPlan, SplitAct, pack_conv_weights
+
+LRELU = 0.2  # nn.LeakyReLU(0.2) of BasicBlock (layers.py:60) and the matching head (networks.py:278)
+
+
+# =====================================================================================
+# static launch plan
+# =====================================================================================
+class Plan:
+    """Preallocated buffers + an ordered list of kernel launches (CUDA-graph capturable)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.ops = []
+        self.n_launches = 0
+        self._keep = []
+
+    def act(self, B, H, W, C):
+        return SplitAct(B, H, W, C, self.device)
+
+    def empty(self, shape, dtype=torch.float32):
+        t = torch.empty(shape, device=self.device, dtype=dtype)
+        self._keep.append(t)
+        return t
+
+    def add(self, fn, launches=1):
+        self.ops.append(fn)
+        self.n_launches += launches
+
+    def run(self):
+        for fn in self.ops:
+            fn()
+
+    # ---- op builders --------------------------------------------------------------------
+    def conv(self, segs, bias, cout, act="none", slope=LRELU, residual=None, want_f32=False, want_split=True,
+             out=None, out_f32=None):
+        """segs: list of (SplitAct, weight [Cout, C, k, k], stride, pad).  Returns (SplitAct | None, f32 | None).
+        `out` / `out_f32` may name existing buffers to overwrite (re-used scratch)."""
+        a0, w0, s0, p0 = segs[0]
+        k0 = w0.shape[-1]
+        B = a0.B
+        OH = (a0.H + 2 * p0 - k0) // s0 + 1
+        OW = (a0.W + 2 * p0 - k0) // s0 + 1
+        if out is None and want_split:
+            out = self.act(B, OH, OW, cout)
+        if out_f32 is None and want_f32:
+            out_f32 = self.empty((B, OH, OW, cout))
+        wimage = pack_conv_weights([w for _, w, _, _ in segs], [a.C for a, _, _, _ in segs], cout)
+        b = None if bias is None else bias.detach().to(self.device, torch.float32).contiguous()
+        plan = ConvPlan([(a, w.shape[-1], s, p) for a, w, s, p in segs], wimage, b, out, B, cout, act=act,
+                        slope=slope, residual=residual, out_f32=out_f32)
+        self.add(plan.run)
+        return out, out_f32
+
+    def upsample2x(self, a, mode):
+        out = self.act(a.B, 2 * a.H, 2 * a.W, a.C)
+        m = {"bilinear": 0, "nearest": 1}[mode]
+        self.add(lambda: _abi.call("b200_upsample2x", _abi.ptr(a.hi), _abi.ptr(a.lo), _abi.ptr(out.hi),
+                                   _abi.ptr(out.lo), a.B, a.H, a.W, a.C, m, _abi.stream_ptr()))
+        return out
+
+    def from_f32(self, getter, B, C, H, W):
+        """fp32 [B,C,H,W] tensor (any strides, fetched at run time through `getter`) -> SplitAct."""
+        out = self.act(B, H, W, C)
+
+        def op():
+            t = getter()
+            if t.dtype != torch.float32:
+                t = t.float()
+            assert tuple(t.shape) == (B, C, H, W), f"expected {(B, C, H, W)}, got {tuple(t.shape)}"
+            _abi.require_cuda(t)
+            _abi.call("b200_f32_to_split", _abi.ptr(t), _abi.ptr(out.hi), _abi.ptr(out.lo), B, C, H, W, t.stride(0),
+                      t.stride(1), t.stride(2), t.stride(3), _abi.stream_ptr())
+
+        self.add(op)
+        return out
+
+    def to_nchw(self, a):
+        out = self.empty((a.B, a.C, a.H, a.W))
+        self.add(lambda: _abi.call("b200_split_to_nchw", _abi.ptr(a.hi), _abi.ptr(a.lo), _abi.ptr(out), a.B, a.C, a.H,
+                                   a.W, _abi.stream_ptr()))
+        return out
+
+    def instance_norm(self, a, pad=0, act="none", slope=LRELU, eps=1e-5, f32_pixel_major=False):
+        partial = self.empty((a.B, 32, a.C, 2), torch.float64)
+        stats = self.empty((a.B, a.C, 2))
+        out = None if f32_pixel_major else self.act(a.B, a.H + 2 * pad, a.W + 2 * pad, a.C)
+        out32 = self.empty((a.B, a.H * a.W, a.C)) if f32_pixel_major else None
+        self.add(lambda: _abi.call("b200_instance_norm", _abi.ptr(a.hi), _abi.ptr(a.lo), _abi.ptr(partial),
+                                   _abi.ptr(stats), _abi.ptr(out.hi) if out else None,
+                                   _abi.ptr(out.lo) if out else None, _abi.ptr(out32), a.B, a.H, a.W, a.C, pad,
+                                   1 if act == "lrelu" else 0, slope, eps, _abi.stream_ptr()), launches=3)
+        return out if out is not None else out32
+
+
+def _split_weight(w, parts):
+    """Split a conv weight [Cout, sum(C_i), k, k] along its input channels like torch.cat's inputs."""
+    sizes = [p.C for p in parts]
+    assert sum(sizes) == w.shape[1], f"concat widths {sizes} do not match conv input {w.shape[1]}"
+    return list(torch.split(w.detach(), sizes, dim=1))
+
+
+# =====================================================================================
+# parameter containers (state-dict compatible with the reference) + plan builders
+# =====================================================================================
+class BasicBlock(nn.Module):
+    """Residual block of modules/layers.py:34-95 with norm_layer=nn.Identity (biased convs):
+    conv3x3 -> LeakyReLU(0.2) -> conv3x3 -> (+ identity | 1x1 conv | 3x3 stride-2 conv) -> LeakyReLU(0.2)."""
+
+    def __init__(self, inplanes, planes, stride=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride, 1, bias=True)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=True)
+        if inplanes == planes and stride == 1:
+            self.downsample = None
+        else:
+            k = 1 if stride == 1 else 3
+            self.downsample = nn.Sequential(nn.Conv2d(inplanes, planes, k, stride, k // 2, bias=True), nn.Identity())
+        self.stride = stride
+
+    def plan(self, g: Plan, parts, act="lrelu", want_f32=False):
+        """parts: list of SplitActs that the reference would torch.cat along channels."""
+        planes = self.conv1.out_channels
+        w1 = _split_weight(self.conv1.weight, parts)
+        h, _ = g.conv([(p, w, self.stride, 1) for p, w in zip(parts, w1)], self.conv1.bias, planes, act=act)
+        if self.downsample is None:
+            assert len(parts) == 1
+            return g.conv([(h, self.conv2.weight, 1, 1)], self.conv2.bias, planes, act=act, residual=parts[0],
+                          want_f32=want_f32)
+        ds = self.downsample[0]
+        k = ds.kernel_size[0]
+        wd = _split_weight(ds.weight, parts)
+        segs = [(h, self.conv2.weight, 1, 1)] + [(p, w, self.stride, k // 2) for p, w in zip(parts, wd)]
+        return g.conv(segs, self.conv2.bias.detach() + ds.bias.detach(), planes, act=act, want_f32=want_f32)
+
+
+class _PlannedModule(nn.Module):
+    """Caches one launch plan per input signature; invalidated when parameters change."""
+
+    def __init__(self):
+        super().__init__()
+        self._plans = {}
+
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + tuple(
+            (b.data_ptr(), b._version) for b in self.buffers())
+
+    def _get_plan(self, sig, build):
+        key = (sig, self._param_key())
+        if key not in self._plans:
+            self._plans = {key: build()}  # keep only the latest signature
+        return self._plans[key]
+
+    def _apply(self, fn, *a, **k):
+        self._plans = {}
+        return super()._apply(fn, *a, **k)
+
+
+class CVEncoder(_PlannedModule):
+    """modules/networks.py:186-215: per level BasicBlock(stride 1|2) -> cat image feature -> 2 BasicBlocks."""
+
+    def __init__(self, num_ch_cv, num_ch_enc, num_ch_outs):
+        super().__init__()
+        self.convs = nn.ModuleDict()
+        self.num_ch_enc = []
+        self.num_blocks = len(num_ch_outs)
+        for i in range(self.num_blocks):
+            cin = num_ch_cv if i == 0 else num_ch_outs[i - 1]
+            cout = num_ch_outs[i]
+            self.convs[f"ds_conv_{i}"] = BasicBlock(cin, cout, stride=1 if i == 0 else 2)
+            self.convs[f"conv_{i}"] = nn.Sequential(BasicBlock(num_ch_enc[i] + cout, cout), BasicBlock(cout, cout))
+            self.num_ch_enc.append(cout)
+
+    def plan(self, g: Plan, x, img_feats):
+        outs = []
+        for i in range(self.num_blocks):
+            x, _ = self.convs[f"ds_conv_{i}"].plan(g, [x])
+            x, _ = self.convs[f"conv_{i}"][0].plan(g, [x, img_feats[i]])
+            x, _ = self.convs[f"conv_{i}"][1].plan(g, [x])
+            outs.append(x)
+        return outs
+
+    @torch.no_grad()
+    def forward(self, x, img_feats):
+        sig = (tuple(x.shape),) + tuple(tuple(f.shape) for f in img_feats)
+
+        def build():
+            g = Plan(x.device)
+            slots = {}
+            xa = g.from_f32(lambda: slots["x"], *x.shape)
+            fa = [g.from_f32((lambda i=i: slots[f"f{i}"]), *f.shape) for i, f in enumerate(img_feats)]
+            outs = [g.to_nchw(o) for o in self.plan(g, xa, fa)]
+            return g, slots, outs
+
+        g, slots, outs = self._get_plan(sig, build)
+        slots["x"] = x
+        for i, f in enumerate(img_feats):
+            slots[f"f{i}"] = f
+        g.run()
+        return [o.clone() for o in outs]
+
+
+def _double_basic_block(cin, cout):
+    seq = nn.Sequential(BasicBlock(cin, cout))
+    seq.add_module("conv_0", BasicBlock(cout, cout))  # key layout of networks.py:13-17
+    return seq
+
+
+class BDDecoderPP(_PlannedModule):
+    """UNet++ decoder of modules/networks.py:20-84.  `outputs` selects which feature_s{i}_b1hw maps are
+    produced; the BD inference path reads only feature_s0 (bd_model.py:414), whose output_0 is the identity,
+    so with outputs=(0,) every output_* BasicBlock (dead work in the reference) is skipped."""
+
+    def __init__(self, num_ch_enc, scales=range(4), num_output_channels=16, use_skips=True, outputs=(0, 1, 2, 3)):
+        super().__init__()
+        self.num_ch_enc = list(num_ch_enc)
+        self.num_ch_dec = np.array([64, 64, 128, 256])
+        self.outputs = tuple(outputs)
+        self.convs = nn.ModuleDict()
+        dec = [int(c) for c in self.num_ch_dec]
+        for j in range(1, 5):
+            for i in range(4 - j, -1, -1):
+                cout = dec[i]
+                total = 0
+                self.convs[f"diag_conv_{i + 1}{j - 1}"] = BasicBlock(self.num_ch_enc[i + 1] if j == 1 else dec[i + 1], cout)
+                total += cout
+                self.convs[f"right_conv_{i}{j - 1}"] = BasicBlock(self.num_ch_enc[i] if j == 1 else dec[i], cout)
+                total += cout
+                if i + j != 4:
+                    self.convs[f"up_conv_{i + 1}{j}"] = BasicBlock(dec[i + 1], cout)
+                    total += cout
+                self.convs[f"in_conv_{i}{j}"] = _double_basic_block(total, cout)
+                self.convs[f"output_{i}"] = nn.Sequential(BasicBlock(cout, cout) if i != 0 else nn.Identity())
+
+    def plan(self, g: Plan, feats, outputs=None, want_f32=()):
+        """feats: 5 SplitActs (/2 ... /32).  Returns {i: SplitAct} (+ {i: fp32 NHWC} for i in want_f32)."""
+        outputs = self.outputs if outputs is None else tuple(outputs)
+        prev = list(feats)
+        outs = []
+        result, result_f32 = {}, {}
+        for j in range(1, 5):
+            for i in range(4 - j, -1, -1):
+                parts = [self.convs[f"right_conv_{i}{j - 1}"].plan(g, [prev[i]])[0]]
+                d, _ = self.convs[f"diag_conv_{i + 1}{j - 1}"].plan(g, [prev[i + 1]])
+                parts.append(g.upsample2x(d, "bilinear"))
+                if i + j != 4:
+                    u, _ = self.convs[f"up_conv_{i + 1}{j}"].plan(g, [outs[-1]])
+                    parts.append(g.upsample2x(u, "bilinear"))
+                blk = self.convs[f"in_conv_{i}{j}"]
+                x, _ = blk[0].plan(g, parts)
+                last = (j == 4 - i) and (i in outputs)
+                is_final_feature = last and i == 0  # output_0 is the identity
+                x, x32 = blk[1].plan(g, [x], want_f32=is_final_feature and (0 in want_f32))
+                outs.append(x)
+                if last:
+                    if i == 0:
+                        result[0] = x
+                        if x32 is not None:
+                            result_f32[0] = x32
+                    else:
+                        o, o32 = self.convs[f"output_{i}"][0].plan(g, [x], want_f32=i in want_f32)
+                        result[i] = o
+                        if o32 is not None:
+                            result_f32[i] = o32
+            prev = outs[::-1]
+        return result, result_f32
+
+    @torch.no_grad()
+    def forward(self, input_features):
+        sig = tuple(tuple(f.shape) for f in input_features)
+
+        def build():
+            g = Plan(input_features[0].device)
+            slots = {}
+            fa = [g.from_f32((lambda i=i: slots[i]), *f.shape) for i, f in enumerate(input_features)]
+            res, _ = self.plan(g, fa)
+            return g, slots, {i: g.to_nchw(a) for i, a in res.items()}
+
+        g, slots, outs = self._get_plan(sig, build)
+        for i, f in enumerate(input_features):
+            slots[i] = f
+        g.run()
+        return {f"feature_s{i}_b1hw": o.clone() for i, o in outs.items()}
+
+
+class _ConvBlock(nn.Module):
+    """modules/networks_fast.py:10-28: conv3x3 -> ELU -> conv3x3 -> ELU."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+
+    def plan(self, g, parts, want_f32=False):
+        cout = self.conv1.out_channels
+        w1 = _split_weight(self.conv1.weight, parts)
+        h, _ = g.conv([(p, w, 1, 1) for p, w in zip(parts, w1)], self.conv1.bias, cout, act="elu")
+        return g.conv([(h, self.conv2.weight, 1, 1)], self.conv2.bias, cout, act="elu", want_f32=want_f32)
+
+
+class _UpConcatBlock(nn.Module):
+    """modules/networks_fast.py:31-46."""
+
+    def __init__(self, cin, cout, skip):
+        super().__init__()
+        self.pre_concat_conv = _ConvBlock(cin, cout)
+        self.post_concat_conv = _ConvBlock(cout + skip, cout)
+
+    def plan(self, g, x, skip, want_f32=False):
+        x, _ = self.pre_concat_conv.plan(g, [x])
+        x = g.upsample2x(x, "nearest")
+        return self.post_concat_conv.plan(g, [x, skip], want_f32=want_f32)
+
+
+class SkipDecoder(_PlannedModule):
+    """Plain U-Net decoder of modules/networks_fast.py:49-99."""
+
+    def __init__(self, input_channels, use_bn=False):
+        super().__init__()
+        ic = list(input_channels)[::-1]
+        self.input_channels = ic
+        self.output_channels = [256, 128, 64, 64]
+        self.num_ch_dec = self.output_channels[::-1]
+        for n in range(4):
+            setattr(self, f"block{n + 1}", _UpConcatBlock(ic[n], self.output_channels[n], ic[n + 1]))
+
+    def plan(self, g, feats, outputs=(0, 1, 2, 3), want_f32=()):
+        x = feats[-1]
+        result, result_f32 = {}, {}
+        for n in range(4):
+            scale = 3 - n
+            x, x32 = getattr(self, f"block{n + 1}").plan(g, x, feats[-2 - n], want_f32=scale in want_f32)
+            if scale in outputs:
+                result[scale] = x
+                if x32 is not None:
+                    result_f32[scale] = x32
+        return result, result_f32
+
+    @torch.no_grad()
+    def forward(self, features):
+        sig = tuple(tuple(f.shape) for f in features)
+
+        def build():
+            g = Plan(features[0].device)
+            slots = {}
+            fa = [g.from_f32((lambda i=i: slots[i]), *f.shape) for i, f in enumerate(features)]
+            res, _ = self.plan(g, fa)
+            return g, slots, {i: g.to_nchw(a) for i, a in res.items()}
+
+        g, slots, outs = self._get_plan(sig, build)
+        for i, f in enumerate(features):
+            slots[i] = f
+        g.run()
+        return {f"feature_s{i}_b1hw": o.clone() for i, o in outs.items()}
+
+
+# ---- matching encoder ---------------------------------------------------------------
+class _BlurPool(nn.Module):
+    def __init__(self, channels):
+        super().__init__()
+        a = torch.tensor([1.0, 3.0, 3.0, 1.0])
+        f = a[:, None] * a[None, :]
+        self.register_buffer("filt", (f / f.sum())[None, None].repeat(channels, 1, 1, 1))
+
+
+class _ResBlockBN(nn.Module):
+    """torchvision-style BasicBlock(64, 64) with BatchNorm + ReLU (layer1 of the antialiased ResNet-18)."""
+
+    def __init__(self, planes):
+        super().__init__()
+        self.conv1 = nn.Conv2d(planes, planes, 3, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(planes, planes, 3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+
+
+def _fold_bn(conv_w, bn):
+    """Eval-mode BatchNorm folded into the preceding bias-free conv."""
+    s = bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)
+    return conv_w.detach() * s.view(-1, 1, 1, 1), bn.bias.detach() - bn.running_mean.detach() * s
+
+
+class ResnetMatchingEncoder(_PlannedModule):
+    """modules/networks.py:236-287 with num_layers=18, antialiased=True: `net` = [conv1, bn1, relu,
+    maxpool(+BlurPool), layer1, 1x1 conv 64->128, InstanceNorm, LeakyReLU(0.2), 3x3 replicate-pad conv
+    128->C, InstanceNorm].  Arithmetic of the third-party stem restated from antialiased-cnns 0.3
+    (parity unpinned for that part).  Output: [n, C, H/4, W/4]."""
+
+    def __init__(self, num_layers=18, num_ch_out=16, pretrained=False, antialiased=True):
+        super().__init__()
+        if num_layers != 18 or not antialiased:
+            raise ValueError("B200 matching encoder implements the antialiased ResNet-18 stem only")
+        self.num_ch_enc = np.array([64, 64])
+        self.num_ch_out = num_ch_out
+        self.net = nn.Sequential(
+            nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False),
+            nn.BatchNorm2d(64),
+            nn.ReLU(inplace=True),
+            nn.Sequential(nn.MaxPool2d(kernel_size=2, stride=1), _BlurPool(64)),
+            nn.Sequential(_ResBlockBN(64), _ResBlockBN(64)),
+            nn.Conv2d(64, 128, (1, 1)),
+            nn.InstanceNorm2d(128),
+            nn.LeakyReLU(0.2, True),
+            nn.Conv2d(128, num_ch_out, (3, 3), padding=1, padding_mode="replicate"),
+            nn.InstanceNorm2d(num_ch_out),
+        )
+
+    def plan(self, g: Plan, get_images, n, H, W):
+        """Returns the fp32 pixel-major feature tensor [n, (H/4)*(W/4), C] the volume kernels consume."""
+        net = self.net
+        dev = g.device
+        w7, b7 = _fold_bn(net[0].weight, net[1])
+        wt = w7.permute(1, 2, 3, 0).reshape(147, 64).to(dev, torch.float32).contiguous()
+        b7 = b7.to(dev, torch.float32).contiguous()
+        H2, W2 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+        s1 = g.act(n, H2, W2, 64)
+
+        def stem():
+            img = get_images()
+            assert tuple(img.shape) == (n, 3, H, W) and img.is_contiguous() and img.dtype == torch.float32
+            _abi.call("b200_stem_conv7", _abi.ptr(img), _abi.ptr(wt), _abi.ptr(b7), _abi.ptr(s1.hi), _abi.ptr(s1.lo), n,
+                      H, W, _abi.stream_ptr())
+
+        g.add(stem)
+        H4, W4 = (H2 - 2) // 2 + 1, (W2 - 2) // 2 + 1
+        x = g.act(n, H4, W4, 64)
+        g.add(lambda: _abi.call("b200_maxblurpool", _abi.ptr(s1.hi), _abi.ptr(s1.lo), _abi.ptr(x.hi), _abi.ptr(x.lo), n,
+                                H2, W2, 64, _abi.stream_ptr()))
+        for blk in net[4]:
+            w1, b1 = _fold_bn(blk.conv1.weight, blk.bn1)
+            w2, b2 = _fold_bn(blk.conv2.weight, blk.bn2)
+            h, _ = g.conv([(x, w1, 1, 1)], b1, 64, act="relu")
+            x, _ = g.conv([(h, w2, 1, 1)], b2, 64, act="relu", residual=x)
+        x, _ = g.conv([(x, net[5].weight, 1, 0)], net[5].bias, 128, act="none")
+        x = g.instance_norm(x, pad=1, act="lrelu", slope=0.2, eps=net[6].eps)  # replicate border for net[8]
+        x, _ = g.conv([(x, net[8].weight, 1, 0)], net[8].bias, self.num_ch_out, act="none")
+        return g.instance_norm(x, eps=net[9].eps, f32_pixel_major=True), H4, W4
+
+    @torch.no_grad()
+    def forward(self, input_image):
+        n, _, H, W = input_image.shape
+        sig = tuple(input_image.shape)
+
+        def build():
+            g = Plan(input_image.device)
+            slots = {}
+            feats, H4, W4 = self.plan(g, lambda: slots["img"], n, H, W)
+            return g, slots, feats, H4, W4
+
+        g, slots, feats, H4, W4 = self._get_plan(sig, build)
+        slots["img"] = input_image.contiguous().float()
+        g.run()
+        return feats.view(n, H4, W4, self.num_ch_out).permute(0, 3, 1, 2).contiguous()
+
+
+# ---- binary occupancy MLP -------------------------------------------------------------
+class BinaryMLPNetwork(nn.Module):
+    """modules/networks.py:87-115: per scale Linear(C+extra,128) -> ELU -> Linear(128,128) -> ELU -> Linear(128,1).
+    Inference uses scale 0 only (max_scale_only, bd_model.py:439)."""
+
+    def __init__(self, input_channels, mlp_size=128, use_prior=False):
+        super().__init__()
+        self.scales = list(range(4))
+        self.use_prior = use_prior
+        extra = 2 if use_prior else 1
+        self.mlps = nn.ModuleDict()
+        for scale, c in enumerate(input_channels):
+            self.mlps[f"s{scale}"] = nn.Sequential(nn.Linear(int(c) + extra, mlp_size), nn.ELU(inplace=True),
+                                                   nn.Linear(mlp_size, mlp_size), nn.ELU(inplace=True),
+                                                   nn.Linear(mlp_size, 1))
+
+    def plan_val(self, g: Plan, feat: SplitAct, get_depth, num_planes, get_prior=None):
+        """BDModel.run_mlp_val for every rendered plane (bd_model.py:293-304, 412-442) as 1x1 convs on the
+        tensor cores.  The feature part of layer 1 does not depend on the plane, so W1[:,1:1+C] . feat + b1 is
+        computed once and enters each plane's first layer as a residual; per plane only the depth (+prior)
+        column changes.  get_depth() -> [B, P, H, W] fp32; returns pred [B, P, H, W] fp32 (logits)."""
+        mlp = self.mlps["s0"]
+        B, H, W, C = feat.shape
+        dev = g.device
+        W1 = mlp[0].weight.detach()
+        assert W1.shape[1] == C + (2 if self.use_prior else 1)
+        w_feat = W1[:, 1:1 + C].reshape(128, C, 1, 1)
+        f1, _ = g.conv([(feat, w_feat, 1, 0)], mlp[0].bias, 128, act="none")
+        w_dp = torch.zeros((128, 8, 1, 1), device=dev)
+        w_dp[:, 0, 0, 0] = W1[:, 0]
+        if self.use_prior:
+            w_dp[:, 1, 0, 0] = W1[:, 1 + C]
+        w2 = mlp[2].weight.detach().reshape(128, 128, 1, 1)
+        w3 = torch.zeros((16, 128, 1, 1), device=dev)
+        w3[0, :, 0, 0] = mlp[4].weight.detach()[0]
+        b3 = torch.zeros(16, device=dev)
+        b3[0] = mlp[4].bias.detach()[0]
+        pred = g.empty((B, num_planes, H, W))
+        dp = g.act(B, H, W, 8)
+        h1 = h2 = o32 = None  # scratch shared by all planes
+        for p in range(num_planes):
+            def pack(p=p):
+                d = get_depth()
+                assert tuple(d.shape) == (B, num_planes, H, W) and d.is_contiguous() and d.dtype == torch.float32
+                pr = get_prior() if (self.use_prior and get_prior is not None) else None
+                dptr = d.data_ptr() + 4 * p * H * W
+                pptr = None
+                pstride = 0
+                if pr is not None:
+                    assert pr.is_contiguous() and pr.dtype == torch.float32 and pr.shape[0] == B
+                    pptr = pr.data_ptr() + 4 * (p % pr.shape[1]) * H * W
+                    pstride = pr.shape[1] * H * W
+                _abi.call("b200_pack_depth_prior", ctypes.c_void_p(dptr), num_planes * H * W,
+                          ctypes.c_void_p(pptr) if pptr else None, pstride, _abi.ptr(dp.hi), _abi.ptr(dp.lo), B, H * W,
+                          _abi.stream_ptr())
+
+            g.add(pack)
+            h1, _ = g.conv([(dp, w_dp, 1, 0)], None, 128, act="elu", residual=f1, out=h1)
+            h2, _ = g.conv([(h1, w2, 1, 0)], mlp[2].bias, 128, act="elu", out=h2)
+            _, o32 = g.conv([(h2, w3, 1, 0)], b3, 16, act="none", want_f32=True, want_split=False, out_f32=o32)
+            g.add(lambda p=p, o32=o32: _abi.call("b200_gather_channel", _abi.ptr(o32), 16, 0,
+                                                 ctypes.c_void_p(pred.data_ptr() + 4 * p * H * W),
+                                                 num_planes * H * W, B, H * W, _abi.stream_ptr()))
+        return pred

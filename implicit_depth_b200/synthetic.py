@@ -123,3 +123,35 @@ def make_frame_batch(seed, B, K, image_h, image_w, num_rendered=8, temporal=Fals
         cur["prior_cam_T_world"] = np.linalg.inv(wTc @ T[None])
     cast = lambda d: {k: np.ascontiguousarray(v.astype(dtype)) for k, v in d.items()}
     return cast(cur), cast(src)
+
+
+def init_model_weights(model, seed=0):
+    """Seeded 'random weights' (BASELINE.json configs): torch default init under `seed`, plus non-trivial
+    BatchNorm statistics so that BN folding is exercised.  Returns a float64 checksum of all tensors."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() > 1:
+                fan_in = p[0].numel()
+                p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * (3.0 / fan_in) ** 0.5)
+            else:
+                p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * 0.1)
+        for name, m in model.named_modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.copy_(0.5 + torch.rand(m.weight.shape, generator=g))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+                m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+    return float(sum(v.double().abs().sum() for v in model.state_dict().values() if v.dtype.is_floating_point))
+
+
+def make_net_inputs(seed, B=1, image_h=96, image_w=128, D=16, enc_ch=(24, 48, 64, 160, 256)):
+    """Random image-encoder pyramid + cost volume for the conv-network tests."""
+    rng = np.random.default_rng(seed)
+    enc = [rng.standard_normal((B, c, image_h // 2 ** (i + 1), image_w // 2 ** (i + 1))).astype(np.float32)
+           for i, c in enumerate(enc_ch)]
+    cv = rng.standard_normal((B, D, image_h // 4, image_w // 4)).astype(np.float32)
+    img = rng.standard_normal((B, 3, image_h, image_w)).astype(np.float32)
+    return enc, cv, img

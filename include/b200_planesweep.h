@@ -109,6 +109,38 @@ int b200_conv_create(const b200_conv_desc* desc, void** plan_out);
 int b200_conv_run(void* plan, void* stream);
 int b200_conv_destroy(void* plan);
 
+/* ---- layout / elementwise kernels of the conv path (csrc/elementwise.cu) -------------------- */
+/* fp32 [B,C,H,W] with element strides (NCHW or channels_last) -> NHWC split-bf16 planes. */
+int b200_f32_to_split(const float* in, void* hi, void* lo, int B, int C, int H, int W, long long sB, long long sC,
+                      long long sH, long long sW, void* stream);
+/* NHWC split-bf16 -> dense fp32 NCHW (the layout the reference's modules return). */
+int b200_split_to_nchw(const void* hi, const void* lo, float* out, int B, int C, int H, int W, void* stream);
+/* x2 upsampling, mode 0 bilinear align_corners=False (utils/generic_utils.py:94-103), 1 nearest
+ * (modules/networks_fast.py:42); out is [B,2H,2W,C]. */
+int b200_upsample2x(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int B, int H, int W, int C,
+                    int mode, void* stream);
+/* nn.InstanceNorm2d (affine=False, biased variance; modules/networks.py:277,283) + optional LeakyReLU;
+ * out = split NHWC with a replicated border of `pad` pixels, and/or fp32 pixel-major [B,H*W,C] (pad 0).
+ * Workspaces sized by b200_instance_norm_ws_bytes. Deterministic, batch-invariant reduction. */
+int b200_instance_norm(const void* in_hi, const void* in_lo, double* partial_ws, float* stats_ws, void* out_hi,
+                       void* out_lo, float* out_f32, int B, int H, int W, int C, int pad, int act, float slope,
+                       float eps, void* stream);
+int b200_instance_norm_ws_bytes(int B, int C, long long* partial_bytes, long long* stats_bytes);
+/* Matching-encoder stem conv 7x7/2 (3->64, BatchNorm folded) + ReLU (modules/networks.py:264-266):
+ * img fp32 NCHW [n,3,H,W]; wt [147,64] tap-major (c,dy,dx); out NHWC split [n,H/2,W/2,64]. */
+int b200_stem_conv7(const float* img, const float* wt, const float* bias, void* out_hi, void* out_lo, int n_img,
+                    int H, int W, void* stream);
+/* MaxPool2d(2, stride 1) + BlurPool(4x4 binomial, stride 2, reflect pad) of antialiased-cnns 0.3
+ * (call site modules/networks.py:267); [B,H,W,C] -> [B,H/2,W/2,C]. */
+int b200_maxblurpool(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int B, int H, int W, int C,
+                     void* stream);
+/* Binary-MLP glue (experiment_modules/bd_model.py:412-442): per-plane depth (+prior) as an 8-channel
+ * split tensor; and extraction of one channel of an fp32 NHWC tensor into a strided plane. */
+int b200_pack_depth_prior(const float* depth, long long depth_batch_stride, const float* prior,
+                          long long prior_batch_stride, void* out_hi, void* out_lo, int B, int HW, void* stream);
+int b200_gather_channel(const float* in_nhwc, int C, int ch, float* out, long long out_batch_stride, int B, int HW,
+                        void* stream);
+
 /* Self-test of the tcgen05/TMEM building blocks: D[128,N] = A[128,K] * Bm[N,K]^T on one CTA.
  *   mode 0: bf16 operands from shared memory; 1: A from tensor memory; 2/3: split-bf16 (fp32-grade)
  *   with A from tensor / shared memory.  K in {64,128,192}, N multiple of 16 up to 128. */

@@ -91,5 +91,88 @@ def volume_goldens():
               "fv slow-vs-fast", out.get("fv_slow_vs_fast_maxabs"))
 
 
+def _sd_sub(sd, prefix):
+    return {k[len(prefix) + 1:]: v for k, v in sd.items() if k.startswith(prefix + ".")}
+
+
+def network_goldens():
+    """Reference CVEncoder / BDDecoderPP / SkipDecoder / matching encoder / BinaryMLP with the state dict of
+    the seeded B200 containers (identical key names)."""
+    import options as ref_options  # reference
+    from experiment_modules.bd_model import BDModel  # reference
+    from modules import networks as ref_nets  # reference
+    from modules import networks_fast as ref_fast  # reference
+
+    from implicit_depth_b200.bd_model import B200BDModel, default_options
+
+    out = {}
+    for dec_name in ("unet_pp", "skip"):
+        mine = B200BDModel(default_options(image_width=128, image_height=96, matching_num_depth_bins=16,
+                                           depth_decoder_name=dec_name))
+        out[f"checksum_{dec_name}"] = np.array(synthetic.init_model_weights(mine, seed=0))
+        sd = mine.state_dict()
+        enc, cv, img = synthetic.make_net_inputs(3000)
+        enc_t = [torch.from_numpy(e) for e in enc]
+        if dec_name == "unet_pp":
+            cve = ref_nets.CVEncoder(16, [48, 64, 160, 256], [64, 128, 256, 384])
+            cve.load_state_dict(_sd_sub(sd, "cost_volume_net"))
+            cvf = cve(torch.from_numpy(cv), enc_t[1:])
+            for i, f in enumerate(cvf):
+                out[f"cvenc_{i}"] = f.numpy()
+            dec = ref_nets.BDDecoderPP([24, 64, 128, 256, 384])
+            dec.load_state_dict(_sd_sub(sd, "depth_decoder"))
+            res = dec(enc_t[:1] + cvf)
+            for i in range(4):
+                out[f"unetpp_s{i}"] = res[f"feature_s{i}_b1hw"].numpy()
+            me = ref_nets.ResnetMatchingEncoder(18, 16, pretrained=False)
+            me.load_state_dict(_sd_sub(sd, "matching_model"))
+            me.eval()
+            out["matching"] = me(torch.from_numpy(img)).numpy()
+            bm = ref_nets.BinaryMLPNetwork([64, 64, 128, 256], mlp_size=128, use_prior=False)
+            bm.load_state_dict(_sd_sub(sd, "binary_mlp"))
+            feat = res["feature_s0_b1hw"]
+            depth = torch.full((1, 1, 48, 64), 2.5)
+            x = torch.cat((depth, feat), 1).permute(0, 2, 3, 1)
+            out["binary_pred"] = bm([x], max_scale_only=True)["pred_0"].permute(0, 3, 1, 2).numpy()
+        else:
+            cve = ref_nets.CVEncoder(16, [48, 64, 160, 256], [64, 128, 256, 384])
+            cve.load_state_dict(_sd_sub(sd, "cost_volume_net"))
+            cvf = cve(torch.from_numpy(cv), enc_t[1:])
+            dec = ref_fast.SkipDecoder([24, 64, 128, 256, 384])
+            dec.load_state_dict(_sd_sub(sd, "depth_decoder"))
+            res = dec(enc_t[:1] + cvf)
+            for i in range(4):
+                out[f"skip_s{i}"] = res[f"feature_s{i}_b1hw"].numpy()
+    np.savez_compressed(os.path.join(HERE, "nets_96x128.npz"), **out)
+    print("nets", {k: v.shape for k, v in out.items()})
+
+    # ---- full BDModel.forward, BASELINE config 1 size (256x192), 7 views (hard-wired, SURVEY 0.7), 16 planes ----
+    for fv_type, K in (("mlp_feature_volume", 7), ("simple_cost_volume", 2)):
+        opts = default_options(image_width=256, image_height=192, matching_num_depth_bins=16,
+                               feature_volume_type=fv_type, num_source_views=K)
+        mine = B200BDModel(opts)
+        checksum = synthetic.init_model_weights(mine, seed=0)
+        ro = ref_options.Options()
+        ro.image_width, ro.image_height, ro.matching_num_depth_bins = 256, 192, 16
+        ro.feature_volume_type = fv_type
+        ro.binary_loss_positive_weight = 1.0
+        ro.bd_edge_regularision = False
+        ref = BDModel(ro)
+        sd = dict(mine.state_dict())
+        ref.load_state_dict(sd, strict=True)
+        ref.eval()
+        cur, src = synthetic.make_frame_batch(4000 + K, 1, K, 192, 256)
+        cur_t = {k: torch.from_numpy(v) for k, v in cur.items()}
+        src_t = {k: torch.from_numpy(v) for k, v in src.items()}
+        o = ref("test", cur_t, src_t, unbatched_matching_encoder_forward=True, return_mask=True)
+        g = {"checksum": np.array(checksum), "pred_0": o["pred_0"].numpy(), "lowest_cost_bhw": o["lowest_cost_bhw"].numpy()}
+        if o["overall_mask_bhw"] is not None:
+            g["overall_mask_bhw"] = o["overall_mask_bhw"].numpy()
+        np.savez_compressed(os.path.join(HERE, f"model_256x192_{fv_type}.npz"), **g)
+        print("model", fv_type, {k: v.shape for k, v in g.items()}, "pred range", g["pred_0"].min(), g["pred_0"].max())
+
+
 if __name__ == "__main__":
-    volume_goldens()
+    if "--nets-only" not in sys.argv:
+        volume_goldens()
+    network_goldens()

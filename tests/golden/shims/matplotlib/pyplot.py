@@ -1,2 +1,2 @@
-def get_cmap(name=None):
+def get_cmap(*args, **kwargs):
     return None
