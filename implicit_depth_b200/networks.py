@@ -448,8 +448,8 @@ class ResnetMatchingEncoder(_PlannedModule):
         g.add(stem)
         H4, W4 = (H2 - 2) // 2 + 1, (W2 - 2) // 2 + 1
         x = g.act(n, H4, W4, 64)
-        g.add(lambda: _abi.call("b200_maxblurpool", _abi.ptr(s1.hi), _abi.ptr(s1.lo), _abi.ptr(x.hi), _abi.ptr(x.lo), n,
-                                H2, W2, 64, _abi.stream_ptr()))
+        g.add(lambda o=x: _abi.call("b200_maxblurpool", _abi.ptr(s1.hi), _abi.ptr(s1.lo), _abi.ptr(o.hi),
+                                    _abi.ptr(o.lo), n, H2, W2, 64, _abi.stream_ptr()))  # bind now: x is rebound below
         for blk in net[4]:
             w1, b1 = _fold_bn(blk.conv1.weight, blk.bn1)
             w2, b2 = _fold_bn(blk.conv2.weight, blk.bn2)
