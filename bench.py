@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 plane-sweep hot path (BASELINE.json: frames/sec at 512x384, 7 source views,
+64 depth planes).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one `BDModel.forward("test", ...)` over one batch of synthetic input at BASELINE config 2
+(B=4 frames per GPU, 512x384, K=7, D=64, implicit_depth.yaml = mlp_feature_volume + unet_pp decoder,
+random weights).  N>1 runs one rank per GPU (torchrun) on its own 4 frames (weak scaling, config 3 at N=8)
+followed by the NCCL all_gather of the outputs.  Rank 0 prints ONE JSON line.
+
+`--impl reference` times the reference's algorithm on the host cores (the CPU oracle port under `oracle/`;
+the reference itself is Python under /root/reference and does not exist on the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES_PER_GPU = 4
+IMAGE_H, IMAGE_W, K_SRC, D_PLANES = 384, 512, 7, 64
+METRIC = "frames/sec (512x384, 7 src views, 64 planes)"
+WORKLOAD = "cfg2: B=4 per GPU, 512x384, 7 source views, 64 depth planes, implicit_depth.yaml (mlp_feature_volume, unet_pp), random weights"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                sm.append(float(parts[0]))
+                mx = max(mx, float(parts[1]))
+                for n, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, budget_s=240.0):
+    """The reference's algorithm on the host cores: oracle port, one cfg2 frame per step (bounded sample)."""
+    import torch
+
+    from implicit_depth_b200 import synthetic
+    from implicit_depth_b200.bd_model import B200BDModel, default_options
+    from oracle import networks as ON  # the only place bench.py executes oracle/: the CPU baseline
+
+    torch.set_grad_enabled(False)
+    cores = torch.get_num_threads()
+    opts = default_options(image_width=IMAGE_W, image_height=IMAGE_H, matching_num_depth_bins=D_PLANES)
+    model = B200BDModel(opts)  # parameter container only (CPU); never called
+    synthetic.init_model_weights(model, seed=0)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    enc = model.encoder.eval()
+    cur, src = synthetic.make_frame_batch(2000, 1, K_SRC, IMAGE_H, IMAGE_W)
+    cur = {k: torch.from_numpy(v) for k, v in cur.items()}
+    src = {k: torch.from_numpy(v) for k, v in src.items()}
+    run = lambda: ON.bd_forward(sd, enc, cur, src, opts, torch_volume=True)
+    t0 = time.perf_counter()
+    run()  # first call also serves as warm-up and as the time estimate
+    est = time.perf_counter() - t0
+    n_warm = max(0, min(warmup, int(0.2 * budget_s / max(est, 1e-3))) - 1)
+    for _ in range(n_warm):
+        run()
+    n = max(1, min(steps, int(0.8 * budget_s / max(est, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        run()
+    dt = (time.perf_counter() - t0) / n
+    return {"value": 1.0 / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{n} x 1 frame of cfg2 (512x384, K=7, D=64) through oracle.networks.bd_forward "
+                      f"(torch CPU kernels, {cores} threads), {dt:.2f} s/frame",
+            "steps_timed": n, "s_per_frame": dt}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": r["steps_timed"], "warmup": args.warmup, "ms_per_step": 1000.0 * r["s_per_frame"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU arm: each step is a bounded sample of 1 frame"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from implicit_depth_b200 import _abi, synthetic
+    from implicit_depth_b200.bd_model import B200BDModel, default_options
+    from implicit_depth_b200.cost_volume import B200CostVolumeManager
+    from implicit_depth_b200.parallel import GatherPlan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:  # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _abi.load()
+    torch.set_grad_enabled(False)
+    # strict fp32 for the out-of-scope cuDNN image encoder, like the reference's fp32 test path
+    opts = default_options(image_width=IMAGE_W, image_height=IMAGE_H, matching_num_depth_bins=D_PLANES)
+    model = B200BDModel(opts)
+    synthetic.init_model_weights(model, seed=0)
+    model = model.to(dev).eval()
+    model.use_cuda_graph = not args.no_graph
+    B = FRAMES_PER_GPU
+
+    # three rotating input sets (227 MB) so that no step finds its inputs in the 126 MB L2; plus an explicit
+    # L2 flush (256 MB write) between steps, outside the per-step CUDA-event brackets
+    NSETS = 3
+    host_sets, dev_sets = [], []
+    for i in range(NSETS):
+        cur, src = synthetic.make_frame_batch(2000 + 10 * rank + i, B, K_SRC, IMAGE_H, IMAGE_W)
+        hc = {k: torch.from_numpy(v).pin_memory() for k, v in cur.items()}
+        hs = {k: torch.from_numpy(v).pin_memory() for k, v in src.items()}
+        host_sets.append((hc, hs))
+        dev_sets.append(({k: v.to(dev) for k, v in hc.items()}, {k: v.to(dev) for k, v in hs.items()}))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(i):
+        cur, src = dev_sets[i % NSETS]
+        return model("test", cur, src, unbatched_matching_encoder_forward=False, return_mask=True)
+
+    out = step(0)
+    gplan = GatherPlan(out, world) if world > 1 else None
+
+    def full_step(i):
+        o = step(i)
+        if gplan is not None:
+            gplan.run(o)  # final gather of outputs over NCCL/NVLink
+        return o
+
+    for i in range(max(args.warmup, 3)):
+        full_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    for i in range(args.steps):
+        flush.zero_()
+        evs[i][0].record()
+        full_step(i)
+        evs[i][1].record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    if world > 1:
+        dist.barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    ms_per_step = total_ms / args.steps
+    value = world * B * args.steps / (total_ms / 1000.0)
+
+    # ---- end to end: pinned host inputs -> H2D -> forward -> D2H of the result, all inside the timed region ----
+    def e2e_step(i):
+        hc, hs = host_sets[i % NSETS]
+        cur = {k: v.to(dev, non_blocking=True) for k, v in hc.items()}
+        src = {k: v.to(dev, non_blocking=True) for k, v in hs.items()}
+        o = model("test", cur, src, return_mask=True)
+        if gplan is not None:
+            gplan.run(o)
+        return {k: v.to("cpu", non_blocking=True) for k, v in o.items() if v is not None}
+
+    h2d = sum(v.numel() * v.element_size() for d in host_sets[0] for v in d.values())
+    res = e2e_step(0)
+    torch.cuda.synchronize()
+    d2h = sum(v.numel() * v.element_size() for v in res.values())
+    for i in range(2):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()
+        e_evs[i][0].record()
+        e2e_step(i)
+        e_evs[i][1].record()
+    torch.cuda.synchronize()
+    e_ms = sum(a.elapsed_time(b) for a, b in e_evs)
+    et = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(et.item()) / 1000.0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused warp + metadata MLP), timed live with CUDA events ----
+    hbm_peak, tf_peak, peak_src = load_peaks()
+    st = model._state[(B, K_SRC, IMAGE_H, IMAGE_W, 8)]
+    N = st.h * st.w
+    cur, src = dev_sets[0]
+    ms_ = opts.matching_scale
+    extr = src["cam_T_world_b44"] @ cur["world_T_cam_b44"].unsqueeze(1)
+    poses = cur["cam_T_world_b44"].unsqueeze(1) @ src["world_T_cam_b44"]
+    cur_pm = st.feats_pm[:B]
+    src_pm = st.feats_pm[B:].view(B, K_SRC, N, -1)
+
+    def time_call(fn, n=10):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(n):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return sum(ts) / len(ts)
+
+    fv_ms = time_call(lambda: model.cost_volume.forward_pixel_major(
+        cur_pm, src_pm, extr, poses, src[f"K_s{ms_}_b44"], cur[f"invK_s{ms_}_b44"], model._mn, model._mx, None, True, B,
+        K_SRC, st.h, st.w))
+    fv_flops = 2.0 * D_PLANES * N * (202 * 128 + 128 * 128 + 128) * B
+    dotm = B200CostVolumeManager(st.h, st.w, num_depth_bins=D_PLANES).to(dev)
+    dot_ms = time_call(lambda: dotm.forward_pixel_major(
+        cur_pm, src_pm, extr, poses, src[f"K_s{ms_}_b44"], cur[f"invK_s{ms_}_b44"], model._mn, model._mx, None, False, B,
+        K_SRC, st.h, st.w))
+    dot_bytes = 4.0 * N * (16 * (K_SRC + 1) + D_PLANES) * B  # compulsory HBM bytes
+    roofline = {"kernel": "fv_tc_kernel (fused warp + metadata MLP, tcgen05)", "bound": "tensor",
+                "achieved": fv_flops / (fv_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": fv_flops / (fv_ms * 1e-3) / 1e12 / tf_peak, "traffic": None, "ms_per_launch": fv_ms,
+                "algorithmic_flops_per_launch": fv_flops, "peak_source": peak_src + ", bf16 burst",
+                "note": "algorithmic fp32 FLOPs of the reference MLP; the kernel issues 3 bf16 MMAs per product"}
+    roofline_dot = {"kernel": "cv_dot_kernel (fused warp + dot + view-sum + argmax)", "bound": "hbm",
+                    "achieved": dot_bytes / (dot_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": dot_bytes / (dot_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "ms_per_launch": dot_ms,
+                    "algorithmic_bytes_per_launch": dot_bytes, "peak_source": peak_src,
+                    "secondary_gather_GBps": 4.0 * 16 * 4 * K_SRC * D_PLANES * N * B / (dot_ms * 1e-3) / 1e9}
+
+    # ---- per-stage breakdown (eager launches, CUDA events) ----
+    model.use_cuda_graph = False
+    stage_ms = {}
+    try:
+        cur_image, src_image = cur["image_b3hw"], src["image_b3hw"]
+        stage_ms["image_encoder_cudnn"] = time_call(lambda: model.encoder(cur_image), 5)
+        st.slots["images"] = torch.cat([cur_image, src_image.reshape(B * K_SRC, 3, IMAGE_H, IMAGE_W)], 0).contiguous()
+        stage_ms["matching_encoder"] = time_call(st.pre.run, 5)
+        stage_ms["feature_volume"] = fv_ms
+        stage_ms["cvenc_decoder_binarymlp"] = time_call(st.post.run, 5)
+        stage_ms["full_forward_eager"] = time_call(lambda: step(0), 5)
+    except Exception as e:  # breakdown is informative only
+        stage_ms["error"] = repr(e)
+    model.use_cuda_graph = not args.no_graph
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        try:
+            r = cpu_reference_run(steps=2, warmup=1, budget_s=30.0)
+            cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:
+            cpu_baseline = {"error": repr(e)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (split-bf16 tcgen05 MMAs, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_gpu": B, "global_batch": world * B,
+                   "l2": "3 rotating input sets (227 MB > 126 MB L2) + 256 MB flush write between steps, outside "
+                         "the per-step CUDA-event brackets",
+                   "timing": "sum of per-step CUDA-event durations, max over ranks",
+                   "cuda_graph": not args.no_graph,
+                   "image_encoder": "torchvision EfficientNetV2-S features via cuDNN (out of scope, SURVEY 2 row 20)"},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": args.steps * model.num_kernel_launches(B, K_SRC, IMAGE_H, IMAGE_W, 8),
+        "gpu_launches_per_step": model.num_kernel_launches(B, K_SRC, IMAGE_H, IMAGE_W, 8),
+        "roofline": roofline, "roofline_warp_dot": roofline_dot, "stage_ms": stage_ms, "clocks": clocks,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_b200(a)

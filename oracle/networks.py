@@ -133,7 +133,8 @@ def binary_mlp_val(sd, p, feat, rendered_depth, prior=None):
     return torch.from_numpy(np.concatenate(outs, 1))
 
 
-def bd_forward(sd, encoder, cur, src, opts, feature_volume="mlp_feature_volume", decoder="unet_pp", return_mask=True):
+def bd_forward(sd, encoder, cur, src, opts, feature_volume="mlp_feature_volume", decoder="unet_pp", return_mask=True,
+               torch_volume=False):
     """`BDModel.forward(phase="test")`, bd_model.py:175-311.  cur/src: dicts of CPU float tensors; `encoder`:
     the image-prior module (same instance the product uses, on CPU)."""
     ms = opts.matching_scale
@@ -151,7 +152,21 @@ def bd_forward(sd, encoder, cur, src, opts, feature_volume="mlp_feature_volume",
                                                   opts.matching_num_depth_bins)
         a = (cur_f, src_f, src_cam_T_cur_cam.numpy(), cur_cam_T_src_cam.numpy(), src[f"K_s{ms}_b44"].numpy(),
              cur[f"invK_s{ms}_b44"].numpy())
-        if feature_volume == "mlp_feature_volume":
+        if torch_volume:  # multi-threaded torch-CPU port (the timed CPU baseline)
+            from . import planesweep_torch as PT
+
+            tp = PT.depth_planes(opts.min_matching_depth, opts.max_matching_depth, opts.matching_num_depth_bins)
+            ta = [torch.from_numpy(x) for x in a]
+            if feature_volume == "mlp_feature_volume":
+                W = [(sd[f"cost_volume.mlp.net.{i}.weight"], sd[f"cost_volume.mlp.net.{i}.bias"]) for i in (0, 2, 4)]
+                vol, _, lowest, mask = PT.feature_volume_mlp(ta[0], ta[1], ta[2], ta[3], ta[4], ta[5], tp, W,
+                                                             return_mask)
+                mask = None if mask is None else mask.numpy()
+            else:
+                vol, _, lowest = PT.cost_volume_dot(ta[0], ta[1], ta[2], ta[4], ta[5], tp)
+                mask = None
+            vol, lowest = vol.numpy(), lowest.numpy()
+        elif feature_volume == "mlp_feature_volume":
             W = [(sd[f"cost_volume.mlp.net.{i}.weight"].numpy(), sd[f"cost_volume.mlp.net.{i}.bias"].numpy())
                  for i in (0, 2, 4)]
             vol, _, lowest, mask = planesweep.feature_volume_mlp(a[0], a[1], a[2], a[3], a[4], a[5], planes, W,
