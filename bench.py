@@ -32,7 +32,7 @@ WORKLOAD = "cfg2: B=4 per GPU, 512x384, 7 source views, 64 depth planes, implici
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
@@ -42,43 +42,43 @@ def parse():
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
+    One-shot queries from a thread (the -lms loop mode block-buffers its pipe)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
+        self.index = index
         self.rows = []
-        self.proc = None
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+        self.stop_flag = False
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append(out.splitlines()[0])
+            except Exception:
+                return
+            time.sleep(0.05)
 
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return None
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.rows:
-            if not (t0 - 0.05 <= ts <= t1 + 0.15):
-                continue
+    def stop(self):
+        self.stop_flag = True
+        self.thread.join(timeout=6)
+        sm, mx, power, reasons = [], 0.0, 0.0, set()
+        for line in self.rows:
             parts = [p.strip() for p in line.split(",")]
             try:
                 sm.append(float(parts[0]))
                 mx = max(mx, float(parts[1]))
-                for n, v in zip(names, parts[3:7]):
+                power = max(power, float(parts[2]))
+                for n, v in zip(self.NAMES, parts[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
@@ -86,7 +86,8 @@ class ClockSampler:
         if not sm:
             return None
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "power_w_max": power, "reasons": sorted(reasons),
+                "samples": len(sm)}
 
 
 def load_peaks():
@@ -231,7 +232,7 @@ def main_b200(args):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms = float(tt.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    clocks = sampler.stop() if sampler else None
     ms_per_step = total_ms / args.steps
     value = world * B * args.steps / (total_ms / 1000.0)
 
