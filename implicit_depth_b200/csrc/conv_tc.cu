@@ -15,6 +15,7 @@
 //   issuer, warps 2-5 = epilogue (TMEM -> registers -> bias/activation/residual -> split -> NHWC).
 //   TMEM holds two accumulator tiles so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 #include <cuda_bf16.h>
 
@@ -41,6 +42,10 @@ struct ConvKParams {
   float* out_f32;         // optional NHWC fp32 copy
   int B, OH, OW, Cout, NT, n_ntiles, act, total_chunks, tiles_x, tiles_y, stages;
   float slope;
+  // halo mode (all segments stride 1): one (16+2*?) x (8*sub+2) pixel patch per 64-channel block is loaded
+  // once and every tap reads it through a shifted UMMA descriptor
+  int halo, sub, pw, patch_bytes;  // sub = 8-pixel-wide sub-tiles per item (1|2); pw = patch width in pixels
+  int seg_chunk0[CV_MAX_SEG];      // index of each segment's first chunk in the weight image
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -232,6 +237,216 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
   if (warp == 1) tc::tmem_dealloc(tmem, tmem_cols);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Halo variant for stride-1 convs (3x3 and 1x1 segments).  The plain kernel above re-fetches every input
+// pixel once per tap (9x) and every weight chunk once per 128 pixels: at N = 64 that is ~2 GB through L2
+// for the 192->64 layers, i.e. L2-bandwidth bound (profiles/r01_*).  Here an item is 16 rows x (8*sub)
+// columns of output pixels (M = 128*sub); for each 64-channel block ONE TMA box of 18 x (8*sub+2) pixels
+// lands in shared memory and the 9 taps are 9 UMMA descriptors into it: start address shifted by
+// (dy*pw + dx) rows, 8-row-group stride pw*128 B (one tile row = one 8-row group).  Each weight chunk is
+// used for sub M=128 tiles.  A traffic drops ~6x, B traffic 2x.
+// ------------------------------------------------------------------------------------------------
+#define CVH_ROWS 16
+
+__global__ void __launch_bounds__(CV_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvKParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int NT = prm.NT, SUB = prm.sub, PW = prm.pw;
+  const uint32_t b_bytes = (uint32_t)NT * 256u;
+  const uint32_t b_stage = (b_bytes + 1023u) & ~1023u;
+  const uint32_t patch_plane = (uint32_t)prm.patch_bytes;  // one bf16 plane of a patch, 1024-aligned
+  const int S = prm.stages;
+  uint8_t* patch0 = base;                                   // 2 patch buffers x (hi, lo)
+  uint8_t* bring = base + 4u * patch_plane;                 // S weight stages
+  uint64_t* p_full = reinterpret_cast<uint64_t*>(bring + (size_t)S * b_stage);
+  uint64_t* p_empty = p_full + 2;
+  uint64_t* b_full = p_empty + 2;
+  uint64_t* b_empty = b_full + S;
+  uint64_t* acc_full = b_empty + S;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int items = prm.B * prm.tiles_y * prm.tiles_x * prm.n_ntiles;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * SUB * NT) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < 2 * prm.nseg; ++s) tc::prefetch_tmap(&prm.maps[s]);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&p_full[i], 1);
+      tc::mbar_init(&p_empty[i], 1);
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&acc_empty[i], 128);
+    }
+    for (int s = 0; s < S; ++s) {
+      tc::mbar_init(&b_full[s], 1);
+      tc::mbar_init(&b_empty[s], 1);
+    }
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, tmem_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // =========================== TMA producer ===========================
+      uint32_t pit = 0, bit = 0;  // patch / weight-chunk counters
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int nt = item % prm.n_ntiles;
+        const int mt = item / prm.n_ntiles;
+        const int tx = mt % prm.tiles_x;
+        const int ty = (mt / prm.tiles_x) % prm.tiles_y;
+        const int b = mt / (prm.tiles_x * prm.tiles_y);
+        const uint8_t* wbase = prm.wimage + (size_t)nt * prm.total_chunks * b_bytes;
+        for (int s = 0; s < prm.nseg; ++s) {
+          const int ks = prm.seg_ksize[s], pd = prm.seg_pad[s];
+          const int cblocks = (prm.seg_C[s] + 63) >> 6;
+          // a 1x1 segment reads the centre of the same kind of patch: origin shifted by (1 - pad)
+          const int org = (ks == 3) ? -pd : -(pd + 1);
+          const int x0 = tx * 8 * SUB + org, y0 = ty * CVH_ROWS + org;
+          for (int cb = 0; cb < cblocks; ++cb, ++pit) {
+            const uint32_t pb = pit & 1u, round = pit >> 1;
+            if (round > 0) tc::mbar_wait(&p_empty[pb], (round - 1) & 1u);
+            uint8_t* pa = patch0 + (size_t)pb * 2u * patch_plane;
+            tc::mbar_expect_tx(&p_full[pb], 2u * (uint32_t)(18 * PW * 128));
+            tc::tma_load_4d(pa, &prm.maps[2 * s], cb * 64, x0, y0, b, &p_full[pb]);
+            tc::tma_load_4d(pa + patch_plane, &prm.maps[2 * s + 1], cb * 64, x0, y0, b, &p_full[pb]);
+            for (int tap = 0; tap < ks * ks; ++tap, ++bit) {
+              const uint32_t st = bit % S, r2 = bit / S;
+              if (r2 > 0) tc::mbar_wait(&b_empty[st], (r2 - 1) & 1u);
+              tc::mbar_expect_tx(&b_full[st], b_bytes);
+              tc::bulk_load(bring + (size_t)st * b_stage,
+                            wbase + (size_t)(prm.seg_chunk0[s] + tap * cblocks + cb) * b_bytes, b_bytes, &b_full[st]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // =========================== MMA issuer ===========================
+      const uint32_t idesc = tc::idesc_bf16_f32(128, NT);
+      const uint32_t sbo = (uint32_t)PW * 128u;
+      uint32_t pit = 0, bit = 0, tile_i = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
+        const uint32_t a = tile_i & 1u, use = tile_i >> 1;
+        if (use > 0) tc::mbar_wait(&acc_empty[a], (use - 1) & 1u);
+        tc::fence_after_sync();
+        const uint32_t acc = tmem + a * SUB * NT;
+        uint32_t first = 1;
+        for (int s = 0; s < prm.nseg; ++s) {
+          const int ks = prm.seg_ksize[s], C = prm.seg_C[s];
+          const int cblocks = (C + 63) >> 6;
+          for (int cb = 0; cb < cblocks; ++cb, ++pit) {
+            const uint32_t pb = pit & 1u;
+            tc::mbar_wait(&p_full[pb], (pit >> 1) & 1u);
+            tc::fence_after_sync();
+            const uint32_t pa = tc::smem_u32(patch0 + (size_t)pb * 2u * patch_plane);
+            const int ksteps = (min(64, C - cb * 64) + 15) >> 4;
+            for (int tap = 0; tap < ks * ks; ++tap, ++bit) {
+              const uint32_t st = bit % S;
+              tc::mbar_wait(&b_full[st], (bit / S) & 1u);
+              tc::fence_after_sync();
+              const uint32_t sb = tc::smem_u32(bring + (size_t)st * b_stage);
+              const int dy = (ks == 3) ? tap / 3 : 1, dx = (ks == 3) ? tap % 3 : 1;
+              const uint32_t row0 = (uint32_t)(dy * PW + dx) * 128u;
+              for (int sub = 0; sub < SUB; ++sub) {
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {  // hi*hi, hi*lo, lo*hi
+                  const uint32_t aa = pa + (pass == 2 ? patch_plane : 0u) + row0 + (uint32_t)sub * 1024u;
+                  const uint32_t bb = sb + (pass == 1 ? (uint32_t)NT * 128u : 0u);
+                  for (int k = 0; k < ksteps; ++k)
+                    tc::mma_ss(acc + sub * NT, tc::smem_desc_sw128(aa + k * 32, sbo), tc::smem_desc_sw128(bb + k * 32),
+                               idesc, (first && pass == 0 && k == 0) ? 0u : 1u);  // first MMA of each sub-tile
+                }
+              }
+              first = 0;
+              tc::mma_commit(&b_empty[st]);
+            }
+            tc::mma_commit(&p_empty[pb]);
+          }
+        }
+        tc::mma_commit(&acc_full[a]);
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 2..5) ===========================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    uint32_t tile_i = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
+      const int nt = item % prm.n_ntiles;
+      const int mt = item / prm.n_ntiles;
+      const int tx = mt % prm.tiles_x;
+      const int ty = (mt / prm.tiles_x) % prm.tiles_y;
+      const int b = mt / (prm.tiles_x * prm.tiles_y);
+      const uint32_t a = tile_i & 1u;
+      tc::mbar_wait(&acc_full[a], (tile_i >> 1) & 1u);
+      tc::fence_after_sync();
+      const int n_base = nt * NT;
+      for (int sub = 0; sub < SUB; ++sub) {
+        const int oy = ty * CVH_ROWS + (row >> 3), ox = tx * 8 * SUB + sub * 8 + (row & 7);
+        const bool live = (oy < prm.OH) && (ox < prm.OW);
+        const size_t pix = ((size_t)b * prm.OH + oy) * prm.OW + ox;
+        for (int n0 = 0; n0 < NT; n0 += 16) {
+          uint32_t r[16];
+          tc::tmem_ld16(tmem + lane_base + (a * SUB + sub) * NT + n0, r);
+          tc::wait_ld();
+          if (live) {
+            const int n = n_base + n0;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (prm.bias ? __ldg(prm.bias + n + j) : 0.f);
+            if (prm.res_hi) {
+              const uint4* rh = reinterpret_cast<const uint4*>(prm.res_hi + pix * prm.Cout + n);
+              const uint4* rl = reinterpret_cast<const uint4*>(prm.res_lo + pix * prm.Cout + n);
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const uint4 h4 = __ldg(rh + q), l4 = __ldg(rl + q);
+                const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[8 * q + 2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+                  v[8 * q + 2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], prm.act, prm.slope);
+            if (prm.out_hi) {
+              uint32_t hi[8], lo[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) tc::split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+              uint4* oh = reinterpret_cast<uint4*>(prm.out_hi + pix * prm.Cout + n);
+              uint4* ol = reinterpret_cast<uint4*>(prm.out_lo + pix * prm.Cout + n);
+              oh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              oh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            }
+            if (prm.out_f32) {
+              float4* of = reinterpret_cast<float4*>(prm.out_f32 + pix * prm.Cout + n);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) of[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+          }
+        }
+      }
+      tc::fence_before_sync();
+      tc::mbar_arrive(&acc_empty[a]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem, tmem_cols);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side: plan objects (tensor maps are encoded once, launches are cheap and graph-capturable)
 // ------------------------------------------------------------------------------------------------
@@ -301,6 +516,25 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   memset(&k, 0, sizeof(k));
   k.nseg = d->nseg;
   k.total_chunks = 0;
+  int dev = 0, n_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  k.NT = b200_conv_ntile(d->Cout);
+  k.n_ntiles = (d->Cout + k.NT - 1) / k.NT;
+  // halo mode: every segment stride 1 and either 3x3 (pad 0|1) or 1x1 (pad 0)
+  bool halo = getenv("B200_CONV_NO_HALO") == nullptr;
+  for (int s = 0; s < d->nseg && halo; ++s) {
+    const b200_conv_seg& sg = d->seg[s];
+    halo = sg.stride == 1 && ((sg.ksize == 3 && (sg.pad == 0 || sg.pad == 1)) || (sg.ksize == 1 && sg.pad == 0));
+  }
+  k.halo = halo ? 1 : 0;
+  k.sub = 1;
+  if (halo) {
+    k.sub = (k.NT <= 64) ? 2 : 1;
+    if (k.sub == 2 && d->B * ((d->OW + 15) / 16) * ((d->OH + CVH_ROWS - 1) / CVH_ROWS) * k.n_ntiles < n_sm) k.sub = 1;
+    k.pw = 8 * k.sub + 2;
+    k.patch_bytes = (18 * k.pw * 128 + 1023) & ~1023;
+  }
   for (int s = 0; s < d->nseg; ++s) {
     const b200_conv_seg& sg = d->seg[s];
     if (!(sg.in_hi && sg.in_lo) || sg.C % 8 != 0 || sg.C < 8 || !(sg.ksize == 1 || sg.ksize == 3) ||
@@ -321,10 +555,15 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
     k.seg_ksize[s] = sg.ksize;
     k.seg_stride[s] = sg.stride;
     k.seg_pad[s] = sg.pad;
+    k.seg_chunk0[s] = k.total_chunks;
     k.total_chunks += sg.ksize * sg.ksize * ((sg.C + 63) / 64);
     cuuint64_t gdim[4] = {(cuuint64_t)sg.C, (cuuint64_t)sg.W, (cuuint64_t)sg.H, (cuuint64_t)d->B};
     cuuint64_t gstr[3] = {(cuuint64_t)sg.C * 2, (cuuint64_t)sg.W * sg.C * 2, (cuuint64_t)sg.H * sg.W * sg.C * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)(CV_TW * sg.stride), (cuuint32_t)(CV_TH * sg.stride), 1};
+    if (halo) {
+      box[1] = (cuuint32_t)k.pw;
+      box[2] = 18;
+    }
     cuuint32_t estr[4] = {1, (cuuint32_t)sg.stride, (cuuint32_t)sg.stride, 1};
     for (int part = 0; part < 2; ++part) {
       CUresult r = enc(&k.maps[2 * s + part], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
@@ -350,26 +589,34 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   k.OH = d->OH;
   k.OW = d->OW;
   k.Cout = d->Cout;
-  k.NT = b200_conv_ntile(d->Cout);
-  k.n_ntiles = (d->Cout + k.NT - 1) / k.NT;
   k.act = d->act;
   k.slope = d->slope;
-  k.tiles_x = (d->OW + CV_TW - 1) / CV_TW;
-  k.tiles_y = (d->OH + CV_TH - 1) / CV_TH;
-  const size_t stage_bytes = 32768 + (((size_t)k.NT * 256 + 1023) & ~(size_t)1023);
-  int S = (int)((200 * 1024) / stage_bytes);
-  if (S > 6) S = 6;
-  if (S > k.total_chunks) S = k.total_chunks < 2 ? 2 : k.total_chunks;
-  k.stages = S;
-  p->smem = 1024 + S * stage_bytes + (2 * S + 4) * 8 + 16;
-  int dev = 0, n_sm = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  if (halo) {
+    k.tiles_x = (d->OW + 8 * k.sub - 1) / (8 * k.sub);
+    k.tiles_y = (d->OH + CVH_ROWS - 1) / CVH_ROWS;
+    const size_t b_stage = ((size_t)k.NT * 256 + 1023) & ~(size_t)1023;
+    const size_t fixed = 1024 + 4 * (size_t)k.patch_bytes + 256;
+    int S = (int)((227 * 1024 - fixed) / b_stage);
+    if (S > 6) S = 6;
+    k.stages = S;
+    p->smem = fixed + S * b_stage;
+  } else {
+    k.tiles_x = (d->OW + CV_TW - 1) / CV_TW;
+    k.tiles_y = (d->OH + CV_TH - 1) / CV_TH;
+    const size_t stage_bytes = 32768 + (((size_t)k.NT * 256 + 1023) & ~(size_t)1023);
+    int S = (int)((200 * 1024) / stage_bytes);
+    if (S > 6) S = 6;
+    if (S > k.total_chunks) S = k.total_chunks < 2 ? 2 : k.total_chunks;
+    k.stages = S;
+    p->smem = 1024 + S * stage_bytes + (2 * S + 4) * 8 + 16;
+  }
   const int items = k.B * k.tiles_x * k.tiles_y * k.n_ntiles;
   p->grid = items < n_sm ? items : n_sm;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       delete p;
       b200_set_error("conv_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -384,7 +631,10 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
 extern "C" int b200_conv_run(void* plan, void* stream) {
   B200_CHECK_ARG(plan, "conv_run: null plan");
   ConvPlan* p = (ConvPlan*)plan;
-  conv_tc_kernel<<<p->grid, CV_THREADS, p->smem, (cudaStream_t)stream>>>(p->k);
+  if (p->k.halo)
+    conv_halo_kernel<<<p->grid, CV_THREADS, p->smem, (cudaStream_t)stream>>>(p->k);
+  else
+    conv_tc_kernel<<<p->grid, CV_THREADS, p->smem, (cudaStream_t)stream>>>(p->k);
   B200_CHECK_LAUNCH("conv_run");
   return 0;
 }

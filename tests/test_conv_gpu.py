@@ -67,3 +67,43 @@ def test_conv_matches_fp64(case):
     assert torch.isfinite(got).all()
     assert (got32 - ref).abs().max().item() < 2e-5 * scale
     assert (got - ref).abs().max().item() < 3e-5 * scale  # + split-bf16 storage rounding (2^-17)
+
+
+# mixed-kernel segment lists: (C, ksize, stride, pad) per segment
+MIXED = [
+    (2, 24, 32, [(64, 3, 1, 1), (64, 1, 1, 0), (128, 1, 1, 0)], 64, "lrelu"),   # BasicBlock conv2 + 1x1 shortcut segments
+    (4, 96, 128, [(64, 3, 1, 1), (64, 3, 1, 1), (64, 3, 1, 1)], 64, "lrelu"),   # >= 148 items: M=256 halo tiles
+    (2, 48, 64, [(128, 3, 1, 1), (128, 3, 2, 1)], 128, "lrelu"),                # never: mixed strides give different sizes
+    (3, 26, 34, [(128, 3, 1, 0)], 16, "none"),                                  # valid conv over a pre-padded tensor
+    (1, 48, 64, [(64, 3, 1, 1), (128, 3, 2, 1)], 128, "lrelu"),                 # stride-2 block: conv2 + 3x3/2 shortcut
+]
+
+
+@pytest.mark.parametrize("idx", [0, 1, 3, 4])
+def test_conv_mixed_segments(idx):
+    B, H, W, segs, Cout, act = MIXED[idx]
+    torch.manual_seed(100 + idx)
+    # segment 0 defines the output size; stride-2 segments read a 2x larger input
+    C0, k0, s0, p0 = segs[0]
+    OH = (H + 2 * p0 - k0) // s0 + 1
+    OW = (W + 2 * p0 - k0) // s0 + 1
+    xs, ws = [], []
+    for (C, k, st, p) in segs:
+        h_in = (OH - 1) * st + k - 2 * p
+        w_in = (OW - 1) * st + k - 2 * p
+        if st == 2:  # any size giving the same output works; use the even one
+            h_in, w_in = OH * 2, OW * 2
+        xs.append(torch.randn(B, C, h_in, w_in, device="cuda"))
+        ws.append(torch.randn(Cout, C, k, k, device="cuda") / (C * k * k) ** 0.5)
+    bias = torch.randn(Cout, device="cuda")
+    acts = [SplitAct.from_nchw_torch(x) for x in xs]
+    out = SplitAct(B, OH, OW, Cout, "cuda")
+    wimage = pack_conv_weights(ws, [c for c, _, _, _ in segs], Cout)
+    plan = ConvPlan([(a, k, st, p) for a, (_, k, st, p) in zip(acts, segs)], wimage, bias, out, B, Cout, act=act,
+                    slope=0.2)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = sum(F.conv2d(a.float_nchw().double(), w.double(), None, st, p) for a, w, (_, k, st, p) in zip(acts, ws, segs))
+    ref = act_ref(ref + bias.double().view(1, -1, 1, 1), act, 0.2)
+    got = out.float_nchw().double()
+    assert (got - ref).abs().max().item() < 3e-5 * ref.abs().max().item()
