@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // =========================== TMA producer ===========================
+    {
+      // =========================== TMA producer (whole warp loops, one elected lane issues) ===========
       uint32_t it = 0;  // global chunk counter -> stage ring
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int nt = item % prm.n_ntiles;
@@ -115,10 +115,13 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
               const uint32_t round = it / S;
               if (round > 0) tc::mbar_wait(&empty[stage], (round - 1) & 1u);
               uint8_t* sa = base + (size_t)stage * stage_bytes;
-              tc::mbar_expect_tx(&full[stage], 32768u + b_bytes);
-              tc::tma_load_4d(sa, &prm.maps[2 * s], cb * 64, x0, y0, b, &full[stage]);
-              tc::tma_load_4d(sa + 16384, &prm.maps[2 * s + 1], cb * 64, x0, y0, b, &full[stage]);
-              tc::bulk_load(sa + 32768, wsrc, b_bytes, &full[stage]);
+              if (tc::elect_one()) {
+                tc::mbar_expect_tx(&full[stage], 32768u + b_bytes);
+                tc::tma_load_4d(sa, &prm.maps[2 * s], cb * 64, x0, y0, b, &full[stage]);
+                tc::tma_load_4d(sa + 16384, &prm.maps[2 * s + 1], cb * 64, x0, y0, b, &full[stage]);
+                tc::bulk_load(sa + 32768, wsrc, b_bytes, &full[stage]);
+              }
+              __syncwarp();
               wsrc += b_bytes;
             }
           }
@@ -126,8 +129,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // =========================== MMA issuer ===========================
+    {
+      // =========================== MMA issuer (whole warp loops, one elected lane issues) ============
       const uint32_t idesc = tc::idesc_bf16_f32(128, NT);
       uint32_t it = 0, tile_i = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
@@ -149,21 +152,19 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
               const uint32_t sa = tc::smem_u32(base + (size_t)stage * stage_bytes);
               const uint32_t sb = sa + 32768u;
               const int ksteps = (min(64, C - cb * 64) + 15) >> 4;
-#pragma unroll
-              for (int pass = 0; pass < 3; ++pass) {  // hi*hi, hi*lo, lo*hi
-                const uint32_t aa = sa + (pass == 2 ? 16384u : 0u);
-                const uint32_t bb = sb + (pass == 1 ? (uint32_t)NT * 128u : 0u);
-                for (int k = 0; k < ksteps; ++k) {
-                  tc::mma_ss(acc, tc::smem_desc_sw128(aa + k * 32), tc::smem_desc_sw128(bb + k * 32), idesc,
-                             first ? 0u : 1u);
-                  first = 0;
-                }
+              if (tc::elect_one()) {
+                const uint64_t a_hi = tc::smem_desc_sw128(sa), b_hi = tc::smem_desc_sw128(sb);
+                tc::mma_split_ss_n(ksteps, acc, a_hi, a_hi + (16384u >> 4), b_hi, b_hi + (((uint32_t)NT * 128u) >> 4),
+                                   idesc, first);
+                tc::mma_commit(&empty[stage]);
               }
-              tc::mma_commit(&empty[stage]);
+              __syncwarp();
+              first = 0;
             }
           }
         }
-        tc::mma_commit(&acc_full[a]);
+        if (tc::elect_one()) tc::mma_commit(&acc_full[a]);
+        __syncwarp();
       }
     }
   } else {
@@ -293,8 +294,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_halo_kernel(const __grid_c
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // =========================== TMA producer ===========================
+    {
+      // =========================== TMA producer (whole warp loops, one elected lane issues) ===========
       uint32_t pit = 0, bit = 0;  // patch / weight-chunk counters
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int nt = item % prm.n_ntiles;
@@ -313,23 +314,29 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_halo_kernel(const __grid_c
             const uint32_t pb = pit & 1u, round = pit >> 1;
             if (round > 0) tc::mbar_wait(&p_empty[pb], (round - 1) & 1u);
             uint8_t* pa = patch0 + (size_t)pb * 2u * patch_plane;
-            tc::mbar_expect_tx(&p_full[pb], 2u * (uint32_t)(18 * PW * 128));
-            tc::tma_load_4d(pa, &prm.maps[2 * s], cb * 64, x0, y0, b, &p_full[pb]);
-            tc::tma_load_4d(pa + patch_plane, &prm.maps[2 * s + 1], cb * 64, x0, y0, b, &p_full[pb]);
+            if (tc::elect_one()) {
+              tc::mbar_expect_tx(&p_full[pb], 2u * (uint32_t)(18 * PW * 128));
+              tc::tma_load_4d(pa, &prm.maps[2 * s], cb * 64, x0, y0, b, &p_full[pb]);
+              tc::tma_load_4d(pa + patch_plane, &prm.maps[2 * s + 1], cb * 64, x0, y0, b, &p_full[pb]);
+            }
+            __syncwarp();
             for (int tap = 0; tap < ks * ks; ++tap, ++bit) {
               const uint32_t st = bit % S, r2 = bit / S;
               if (r2 > 0) tc::mbar_wait(&b_empty[st], (r2 - 1) & 1u);
-              tc::mbar_expect_tx(&b_full[st], b_bytes);
-              tc::bulk_load(bring + (size_t)st * b_stage,
-                            wbase + (size_t)(prm.seg_chunk0[s] + tap * cblocks + cb) * b_bytes, b_bytes, &b_full[st]);
+              if (tc::elect_one()) {
+                tc::mbar_expect_tx(&b_full[st], b_bytes);
+                tc::bulk_load(bring + (size_t)st * b_stage,
+                              wbase + (size_t)(prm.seg_chunk0[s] + tap * cblocks + cb) * b_bytes, b_bytes, &b_full[st]);
+              }
+              __syncwarp();
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // =========================== MMA issuer ===========================
+    {
+      // =========================== MMA issuer (whole warp loops, one elected lane issues) ============
       const uint32_t idesc = tc::idesc_bf16_f32(128, NT);
       const uint32_t sbo = (uint32_t)PW * 128u;
       uint32_t pit = 0, bit = 0, tile_i = 0;
@@ -355,23 +362,22 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_halo_kernel(const __grid_c
               const uint32_t sb = tc::smem_u32(bring + (size_t)st * b_stage);
               const int dy = (ks == 3) ? tap / 3 : 1, dx = (ks == 3) ? tap % 3 : 1;
               const uint32_t row0 = (uint32_t)(dy * PW + dx) * 128u;
-              for (int sub = 0; sub < SUB; ++sub) {
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {  // hi*hi, hi*lo, lo*hi
-                  const uint32_t aa = pa + (pass == 2 ? patch_plane : 0u) + row0 + (uint32_t)sub * 1024u;
-                  const uint32_t bb = sb + (pass == 1 ? (uint32_t)NT * 128u : 0u);
-                  for (int k = 0; k < ksteps; ++k)
-                    tc::mma_ss(acc + sub * NT, tc::smem_desc_sw128(aa + k * 32, sbo), tc::smem_desc_sw128(bb + k * 32),
-                               idesc, (first && pass == 0 && k == 0) ? 0u : 1u);  // first MMA of each sub-tile
-                }
+              if (tc::elect_one()) {
+                const uint64_t a_hi = tc::smem_desc_sw128(pa + row0, sbo), b_hi = tc::smem_desc_sw128(sb);
+                const uint64_t a_lo = a_hi + (patch_plane >> 4), b_lo = b_hi + (((uint32_t)NT * 128u) >> 4);
+                for (int sub = 0; sub < SUB; ++sub)  // sub-tile 1 sits 8 pixels = 1024 B to the right
+                  tc::mma_split_ss_n(ksteps, acc + sub * NT, a_hi + sub * 64, a_lo + sub * 64, b_hi, b_lo, idesc, first);
+                tc::mma_commit(&b_empty[st]);
               }
+              __syncwarp();
               first = 0;
-              tc::mma_commit(&b_empty[st]);
             }
-            tc::mma_commit(&p_empty[pb]);
+            if (tc::elect_one()) tc::mma_commit(&p_empty[pb]);
+            __syncwarp();
           }
         }
-        tc::mma_commit(&acc_full[a]);
+        if (tc::elect_one()) tc::mma_commit(&acc_full[a]);
+        __syncwarp();
       }
     }
   } else {

@@ -246,8 +246,8 @@ __global__ void __launch_bounds__(FVT_THREADS, 1) fv_tc_kernel(const FvTcParams 
       if (p_raw < N) prm.vol[((size_t)b * prm.D + d) * N + p] = o + b3v;
       tc::fence_before_sync();  // order this tile's TMEM reads before the next tile's MMAs (via a_full)
     }
-  } else if (lane == 0) {
-    // =============================== MMA issuer ===============================
+  } else {
+    // =============================== MMA issuer (whole warp loops, one elected lane issues) ==========
     constexpr uint32_t IDESC = tc::idesc_bf16_f32(128, 128);
     long long t_cur[2], t_end[2];
     uint32_t nfill[2][2] = {{0, 0}, {0, 0}}, tiles[2] = {0, 0};
@@ -266,34 +266,32 @@ __global__ void __launch_bounds__(FVT_THREADS, 1) fv_tc_kernel(const FvTcParams 
         const uint32_t acc = a_base + 128;
         if (step[g] < Cfg::NCHUNK) {
           const uint32_t slot = step[g] & 1u;
-          if (!tc::mbar_try_wait(&gs->a_full[slot], nfill[g][slot] & 1u)) continue;
+          if (!__all_sync(0xffffffffu, tc::mbar_try_wait(&gs->a_full[slot], nfill[g][slot] & 1u))) continue;
           tc::fence_after_sync();
           const int c = step[g];
-#pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {  // hi*hi, hi*lo, lo*hi
-            const uint32_t a_t = a_base + slot * 64 + (pass == 2 ? 32 : 0);
-            const uint8_t* bs = (pass == 1 ? w1_lo : w1_hi) + c * 16384;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              tc::mma_ts(acc, a_t + ks * 8, tc::smem_desc_sw128(tc::smem_u32(bs) + ks * 32), IDESC,
-                         (c | pass | ks) != 0);
+          if (tc::elect_one()) {
+            const uint64_t b_hi = tc::smem_desc_sw128(tc::smem_u32(w1_hi + c * 16384));
+            const uint64_t b_lo = tc::smem_desc_sw128(tc::smem_u32(w1_lo + c * 16384));
+            tc::mma_split_ts<4>(acc, a_base + slot * 64, a_base + slot * 64 + 32, b_hi, b_lo, IDESC, c == 0);
+            tc::mma_commit(&gs->a_empty[slot]);
+            if (c + 1 == Cfg::NCHUNK) tc::mma_commit(&gs->acc_full);
           }
-          tc::mma_commit(&gs->a_empty[slot]);
+          __syncwarp();
           ++nfill[g][slot];
-          if (++step[g] == Cfg::NCHUNK) tc::mma_commit(&gs->acc_full);
+          ++step[g];
         } else {
-          if (!tc::mbar_try_wait(&gs->h_full, tiles[g] & 1u)) continue;
+          if (!__all_sync(0xffffffffu, tc::mbar_try_wait(&gs->h_full, tiles[g] & 1u))) continue;
           tc::fence_after_sync();
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a_t = a_base + (pass == 2 ? 64 : 0);
-            const uint8_t* bs = (pass == 1 ? w2_lo : w2_hi);
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              tc::mma_ts(acc, a_t + ks * 8, tc::smem_desc_sw128(tc::smem_u32(bs + (ks >> 2) * 16384) + (ks & 3) * 32),
-                         IDESC, (pass | ks) != 0);
+            for (int half = 0; half < 2; ++half) {  // K = 128 = 2 swizzle atoms of 64
+              const uint64_t b_hi = tc::smem_desc_sw128(tc::smem_u32(w2_hi + half * 16384));
+              const uint64_t b_lo = tc::smem_desc_sw128(tc::smem_u32(w2_lo + half * 16384));
+              tc::mma_split_ts<4>(acc, a_base + half * 32, a_base + 64 + half * 32, b_hi, b_lo, IDESC, half == 0);
+            }
+            tc::mma_commit(&gs->acc2_full);
           }
-          tc::mma_commit(&gs->acc2_full);
+          __syncwarp();
           step[g] = 0;
           ++tiles[g];
           ++t_cur[g];

@@ -164,6 +164,46 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// One lane of a converged warp (elect.sync): the role loops are executed by the whole warp so that the
+// compiler keeps descriptors in uniform registers; only the issue itself is predicated.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// Split-bf16 product of one 64-wide K chunk (4 k-steps of 16): D (+)= Ah*Bh + Ah*Bl + Al*Bh.
+// Descriptors advance by 32 bytes (= 2 in the encoded start-address field) per k-step.
+// `fresh` != 0 makes the very first MMA overwrite the accumulator.
+template <int KSTEPS>
+__device__ __forceinline__ void mma_split_ss(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                             uint32_t idesc, uint32_t fresh) {
+#pragma unroll
+  for (int k = 0; k < KSTEPS; ++k) mma_ss(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (k == 0 && fresh) ? 0u : 1u);
+#pragma unroll
+  for (int k = 0; k < KSTEPS; ++k) mma_ss(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+#pragma unroll
+  for (int k = 0; k < KSTEPS; ++k) mma_ss(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+}
+__device__ __forceinline__ void mma_split_ss_n(int ksteps, uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi,
+                                               uint64_t b_lo, uint32_t idesc, uint32_t fresh) {
+  if (ksteps == 4) mma_split_ss<4>(d_tmem, a_hi, a_lo, b_hi, b_lo, idesc, fresh);
+  else if (ksteps == 3) mma_split_ss<3>(d_tmem, a_hi, a_lo, b_hi, b_lo, idesc, fresh);
+  else if (ksteps == 2) mma_split_ss<2>(d_tmem, a_hi, a_lo, b_hi, b_lo, idesc, fresh);
+  else mma_split_ss<1>(d_tmem, a_hi, a_lo, b_hi, b_lo, idesc, fresh);
+}
+// Same with the A operand in tensor memory (8 columns per k-step).
+template <int KSTEPS>
+__device__ __forceinline__ void mma_split_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                             uint32_t idesc, uint32_t fresh) {
+#pragma unroll
+  for (int k = 0; k < KSTEPS; ++k) mma_ts(d_tmem, a_hi + 8 * k, b_hi + 2 * k, idesc, (k == 0 && fresh) ? 0u : 1u);
+#pragma unroll
+  for (int k = 0; k < KSTEPS; ++k) mma_ts(d_tmem, a_hi + 8 * k, b_lo + 2 * k, idesc, 1u);
+#pragma unroll
+  for (int k = 0; k < KSTEPS; ++k) mma_ts(d_tmem, a_lo + 8 * k, b_hi + 2 * k, idesc, 1u);
+}
+
 // ------------------------------------------------------------------ split-bf16 numbers
 // x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits; the product of two such
 // numbers is taken as hi*hi + hi*lo + lo*hi (three bf16 MMAs, fp32 accumulate), dropping only the
