@@ -275,7 +275,7 @@ def main_b200(args):
 
     # ---- roofline of the dominant kernel (fused warp + metadata MLP), timed live with CUDA events ----
     hbm_peak, tf_peak, peak_src = load_peaks()
-    st = model._state[(B, K_SRC, IMAGE_H, IMAGE_W, 8)]
+    st = model._state[(B, K_SRC, IMAGE_H, IMAGE_W, 8, False)]
     N = st.h * st.w
     cur, src = dev_sets[0]
     ms_ = opts.matching_scale

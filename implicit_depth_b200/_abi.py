@@ -37,8 +37,12 @@ SIGNATURES = {
     "b200_instance_norm_ws_bytes": [c_i, c_i, ctypes.c_void_p, ctypes.c_void_p],
     "b200_stem_conv7": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
     "b200_maxblurpool": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, ctypes.c_void_p],
-    "b200_pack_depth_prior": [c_f, c_ll, c_f, c_ll, c_f, c_f, c_i, c_i, ctypes.c_void_p],
-    "b200_gather_channel": [c_f, c_i, c_i, c_f, c_ll, c_i, c_i, ctypes.c_void_p],
+    "b200_sample_prior": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
+    "b200_binary_mlp_create": [ctypes.c_void_p, ctypes.c_void_p],
+    "b200_binary_mlp_planes": [ctypes.c_void_p, c_f, c_i, c_f, c_f, ctypes.c_void_p],
+    "b200_binary_mlp_search": [ctypes.c_void_p, c_f, c_i, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_f, c_f,
+                               ctypes.c_void_p],
+    "b200_binary_mlp_destroy": [ctypes.c_void_p],
     "b200_umma_probe": [c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
 }
 

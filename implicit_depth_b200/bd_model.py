@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from . import _abi
-from .cost_volume import B200CostVolumeManager, B200FeatureVolumeManager
+from .cost_volume import B200CostVolumeManager, B200FeatureVolumeManager, _Eps, _PixGrid
 from .networks import BDDecoderPP, BinaryMLPNetwork, CVEncoder, Plan, ResnetMatchingEncoder, SkipDecoder
 
 
@@ -53,6 +53,27 @@ class EffNetV2SFeatures(nn.Module):
         return outs
 
 
+def fold_batchnorm(module):
+    """Eval-mode copy of `module` with every Conv2d -> BatchNorm2d pair inside an nn.Sequential folded into one
+    conv (the out-of-scope cuDNN image encoder spends a fifth of its launches in stand-alone BN kernels)."""
+    import copy
+
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+
+    def walk(m):
+        for child in m.children():
+            walk(child)
+        if isinstance(m, nn.Sequential):
+            keys = list(m._modules.keys())
+            for a, b in zip(keys, keys[1:]):
+                if isinstance(m._modules[a], nn.Conv2d) and isinstance(m._modules[b], nn.BatchNorm2d):
+                    m._modules[a] = fuse_conv_bn_eval(m._modules[a], m._modules[b])
+                    m._modules[b] = nn.Identity()
+        return m
+
+    return walk(copy.deepcopy(module).eval())
+
+
 class B200BDModel(nn.Module):
     def __init__(self, opts=None, encoder=None):
         super().__init__()
@@ -89,20 +110,46 @@ class B200BDModel(nn.Module):
             raise ValueError("Unrecognized option for matching encoder type!")
         self.matching_model = ResnetMatchingEncoder(18, opts.matching_feature_dims)
         self.binary_mlp = BinaryMLPNetwork(self.depth_decoder.num_ch_dec, mlp_size=128, use_prior=opts.use_prior)
+        if opts.use_prior:
+            # buffers of the reference's BackprojectDepth(192, 256) / Project3D (bd_model.py:136-139), kept so that
+            # temporal checkpoints load strictly; `sample_prior` computes the same grid in-kernel for any size
+            self.backprojector = _PixGrid(192, 256)
+            self.projector = _Eps()
+        self.thresholder = None
         # training-only buffer of the reference (bd_model.py:100-101), kept so its checkpoints load strictly
         self.bce_loss = nn.Module()
         self.bce_loss.register_buffer("pos_weight", torch.ones(1))
         self._state = {}
         self._graphs = {}
         self.use_cuda_graph = False
+        # the image encoder is independent of the matching encoder + plane sweep until the cost-volume encoder:
+        # run it (BatchNorm folded) on a side stream so its many small cuDNN launches overlap our kernels
+        self.overlap_image_encoder = True
+        self._enc_fast = None
+        self._side = None
 
     def _apply(self, fn, *a, **k):
-        self._state, self._graphs = {}, {}
+        self._state, self._graphs, self._enc_fast, self._side = {}, {}, None, None
         return super()._apply(fn, *a, **k)
 
+    def _run_image_encoder(self, cur_image):
+        """Returns (features, join) -- call join() before the features are consumed on the current stream."""
+        if self.training or not self.overlap_image_encoder:
+            return self.encoder(cur_image), (lambda: None)
+        key = tuple((p.data_ptr(), p._version) for p in self.encoder.parameters())
+        if self._enc_fast is None or self._enc_fast[0] != key:
+            self._enc_fast = (key, fold_batchnorm(self.encoder))
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=cur_image.device)
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            feats = self._enc_fast[1](cur_image)
+        return feats, (lambda: main.wait_stream(self._side))
+
     # ------------------------------------------------------------------------------------
-    def _build(self, B, K, H, W, P, dev):
-        """Static launch plans for one input signature."""
+    def _build(self, B, K, H, W, P, dev, search=False):
+        """Static launch plans for one input signature (P rendered planes, or the infer_depth bisection)."""
         ms = self.run_opts.matching_scale
         D = self.run_opts.matching_num_depth_bins
         slots = {}
@@ -116,13 +163,18 @@ class B200BDModel(nn.Module):
         cv_feats = self.cost_volume_net.plan(post, cv, img_feats[ms:])
         dec_in = img_feats[:ms] + cv_feats
         res, _ = self.depth_decoder.plan(post, dec_in, outputs=(0,))
-        pred = self.binary_mlp.plan_val(post, res[0], lambda: slots["rendered_depth"], P,
-                                        get_prior=(lambda: slots.get("prior")))
-        return SimpleNamespace(slots=slots, pre=pre, post=post, feats_pm=feats_pm, h=h, w=w, pred=pred)
+        search_depths = None
+        if search:
+            search_depths, pred = self.binary_mlp.plan_search(post, res[0], get_prior=(lambda: slots.get("prior")))
+        else:
+            pred = self.binary_mlp.plan_val(post, res[0], lambda: slots["rendered_depth"], P,
+                                            get_prior=(lambda: slots.get("prior")))
+        return SimpleNamespace(slots=slots, pre=pre, post=post, feats_pm=feats_pm, h=h, w=w, pred=pred,
+                               search_depths=search_depths)
 
-    def num_kernel_launches(self, B, K, H, W, P):
+    def num_kernel_launches(self, B, K, H, W, P, search=False):
         """Hand-written kernel launches per forward for this signature (matching encoder + volume + nets)."""
-        st = self._state.get((B, K, H, W, P))
+        st = self._state.get((B, K, H, W, P, search))
         if st is None:
             return None
         vol = 4 if isinstance(self.cost_volume, B200FeatureVolumeManager) else 2  # prepare, kernel(, argmax)
@@ -130,19 +182,19 @@ class B200BDModel(nn.Module):
 
     @torch.no_grad()
     def _forward_impl(self, cur_image, src_image, src_K, cur_invK, src_cam_T_world, src_world_T_cam, cur_cam_T_world,
-                      cur_world_T_cam, rendered_depth, prior, return_mask):
+                      cur_world_T_cam, rendered_depth, prior, return_mask, search=False):
         B, K = src_image.shape[:2]
         H, W = cur_image.shape[-2:]
         P = rendered_depth.shape[1]
-        key = (B, K, H, W, P)
+        key = (B, K, H, W, P, search)
         if key not in self._state:
-            self._state = {key: self._build(B, K, H, W, P, cur_image.device)}
+            self._state = {key: self._build(B, K, H, W, P, cur_image.device, search)}
         st = self._state[key]
         # relative poses, bd_model.py:196-204
         src_cam_T_cur_cam = src_cam_T_world @ cur_world_T_cam.unsqueeze(1)
         cur_cam_T_src_cam = cur_cam_T_world.unsqueeze(1) @ src_world_T_cam
-        # image-prior encoder (PyTorch/cuDNN, out of scope)
-        st.slots["enc"] = self.encoder(cur_image)
+        # image-prior encoder (PyTorch/cuDNN, out of scope), on a side stream
+        enc_feats, join_encoder = self._run_image_encoder(cur_image)
         # matching features for the current + source frames in one batch-invariant pass
         st.slots["images"] = torch.cat([cur_image, src_image.reshape(B * K, 3, H, W)], 0).contiguous()
         st.pre.run()
@@ -157,11 +209,28 @@ class B200BDModel(nn.Module):
         cost_volume, lowest_cost, _, overall_mask = self.cost_volume.forward_pixel_major(
             cur_pm, src_pm, src_cam_T_cur_cam, cur_cam_T_src_cam, src_K, cur_invK, mn, mx, None, return_mask, B, K,
             st.h, st.w)
+        join_encoder()
+        st.slots["enc"] = enc_feats
         st.slots["cv"] = cost_volume
         st.slots["rendered_depth"] = rendered_depth
         st.slots["prior"] = prior
         st.post.run()
-        return st.pred, lowest_cost, overall_mask
+        return st.pred, lowest_cost, overall_mask, st.search_depths
+
+    def sample_prior(self, rendered_depth, prior_prediction, cam_to_world, prior_world_to_cam, K, invK):
+        """`BDModel.sample_prior` (bd_model.py:395-410) as one kernel; same argument order as the reference."""
+        B, P, H, W = rendered_depth.shape
+        if P != 1 or tuple(prior_prediction.shape) != (B, 1, H, W):
+            raise ValueError("sample_prior expects one rendered plane and a [B,1,H,W] prior prediction "
+                             "(the reference's back-projection broadcasts only for a single plane)")
+        _abi.require_cuda(rendered_depth, prior_prediction)
+        f = lambda t: (t if t.dtype == torch.float32 else t.float()).contiguous()
+        cur_to_prior = torch.matmul(prior_world_to_cam.float(), cam_to_world.float())
+        Pm = (K.float() @ cur_to_prior)[:, :3, :].contiguous()
+        out = torch.empty((B, 1, H, W), device=rendered_depth.device, dtype=torch.float32)
+        _abi.call("b200_sample_prior", _abi.ptr(f(rendered_depth)), _abi.ptr(f(prior_prediction)), _abi.ptr(Pm),
+                  _abi.ptr(f(invK)), _abi.ptr(out), B, H, W, _abi.stream_ptr())
+        return out
 
     @torch.no_grad()
     def forward(self, phase, cur_data, src_data, unbatched_matching_encoder_forward=False, return_mask=False,
@@ -170,8 +239,8 @@ class B200BDModel(nn.Module):
         irrelevant: the matching-encoder kernels are batch-invariant.  Only the inference branch exists."""
         if phase == "train":
             raise NotImplementedError("B200BDModel implements the inference path only")
-        if infer_depth:
-            raise NotImplementedError("infer_depth (per-pixel binary search) is a next-row item (SURVEY 8f)")
+        if infer_depth and getattr(self, "thresholder", None) is not None:
+            raise NotImplementedError("infer_depth with a depth-dependent Thresholder is not built (threshold 0.5 only)")
         ms = self.run_opts.matching_scale
         cur_image = cur_data["image_b3hw"]
         _abi.require_cuda(cur_image)
@@ -183,19 +252,30 @@ class B200BDModel(nn.Module):
         prior = None
         if self.run_opts.use_prior:
             if cur_data.get("prior_prediction", None) is not None:
-                raise NotImplementedError("temporal prior warp (sample_prior) is not built yet")
-            prior = -torch.ones_like(args[-1][:, :1]).contiguous()  # bd_model.py:433-434
+                # bd_model.py:423-432 (also stores the warped prior back into the inputs, :432)
+                prior = self.sample_prior(args[-1], f(cur_data["prior_prediction"]), f(cur_data["world_T_cam_b44"]),
+                                          f(cur_data["prior_cam_T_world"]), f(cur_data["K_s0_b44"]),
+                                          f(cur_data["invK_s0_b44"]))
+                cur_data["prior_mask"] = prior
+            else:
+                prior = -torch.ones_like(args[-1][:, :1]).contiguous()  # bd_model.py:433-434
         if self.use_cuda_graph:
-            pred, lowest, mask = self._forward_graphed(args, prior, return_mask)
+            pred, lowest, mask, search = self._forward_graphed(args, prior, return_mask, bool(infer_depth))
         else:
-            pred, lowest, mask = self._forward_impl(*args, prior, return_mask)
+            pred, lowest, mask, search = self._forward_impl(*args, prior, return_mask, bool(infer_depth))
             pred = pred.clone()
-        return {"pred_0": pred, "lowest_cost_bhw": lowest, "overall_mask_bhw": mask}
+            search = None if search is None else search.clone()
+        out = {"pred_0": pred}
+        if infer_depth:
+            out["search_depths"] = search  # bd_model.py:292
+        out["lowest_cost_bhw"] = lowest
+        out["overall_mask_bhw"] = mask
+        return out
 
     # ------------------------------------------------------------------------------------
-    def _forward_graphed(self, args, prior, return_mask):
+    def _forward_graphed(self, args, prior, return_mask, search=False):
         """Whole forward captured once per input signature into a CUDA graph and replayed."""
-        key = tuple(tuple(a.shape) for a in args) + (prior is not None, return_mask)
+        key = tuple(tuple(a.shape) for a in args) + (prior is not None, return_mask, search)
         if key not in self._graphs:
             static = [a.clone() for a in args]
             sprior = None if prior is None else prior.clone()
@@ -203,11 +283,11 @@ class B200BDModel(nn.Module):
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 for _ in range(2):  # warm-up: builds plans, packs weights, sets kernel attributes
-                    self._forward_impl(*static, sprior, return_mask)
+                    self._forward_impl(*static, sprior, return_mask, search)
             torch.cuda.current_stream().wait_stream(s)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                outs = self._forward_impl(*static, sprior, return_mask)
+                outs = self._forward_impl(*static, sprior, return_mask, search)
             self._graphs = {key: (graph, static, sprior, outs)}
         graph, static, sprior, outs = self._graphs[key]
         for s_, a in zip(static, args):

@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "tc.cuh"
+#include "tmap.cuh"
 
 #define CV_THREADS 192
 #define CV_TH 8
@@ -46,6 +47,8 @@ struct ConvKParams {
   // once and every tap reads it through a shifted UMMA descriptor
   int halo, sub, pw, patch_bytes;  // sub = 8-pixel-wide sub-tiles per item (1|2); pw = patch width in pixels
   int seg_chunk0[CV_MAX_SEG];      // index of each segment's first chunk in the weight image
+  int debug;                       // dev only (B200_CONV_DEBUG): bit 0 = skip MMAs, bit 1 = skip TMA loads
+  long long* prof;                 // dev only: per-CTA role timings [grid][8] (clock64 ticks) or null
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -116,10 +119,14 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
               if (round > 0) tc::mbar_wait(&empty[stage], (round - 1) & 1u);
               uint8_t* sa = base + (size_t)stage * stage_bytes;
               if (tc::elect_one()) {
-                tc::mbar_expect_tx(&full[stage], 32768u + b_bytes);
-                tc::tma_load_4d(sa, &prm.maps[2 * s], cb * 64, x0, y0, b, &full[stage]);
-                tc::tma_load_4d(sa + 16384, &prm.maps[2 * s + 1], cb * 64, x0, y0, b, &full[stage]);
-                tc::bulk_load(sa + 32768, wsrc, b_bytes, &full[stage]);
+                if (prm.debug & 2) {
+                  tc::mbar_arrive(&full[stage]);
+                } else {
+                  tc::mbar_expect_tx(&full[stage], 32768u + b_bytes);
+                  tc::tma_load_4d(sa, &prm.maps[2 * s], cb * 64, x0, y0, b, &full[stage]);
+                  tc::tma_load_4d(sa + 16384, &prm.maps[2 * s + 1], cb * 64, x0, y0, b, &full[stage]);
+                  tc::bulk_load(sa + 32768, wsrc, b_bytes, &full[stage]);
+                }
               }
               __syncwarp();
               wsrc += b_bytes;
@@ -154,8 +161,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
               const int ksteps = (min(64, C - cb * 64) + 15) >> 4;
               if (tc::elect_one()) {
                 const uint64_t a_hi = tc::smem_desc_sw128(sa), b_hi = tc::smem_desc_sw128(sb);
-                tc::mma_split_ss_n(ksteps, acc, a_hi, a_hi + (16384u >> 4), b_hi, b_hi + (((uint32_t)NT * 128u) >> 4),
-                                   idesc, first);
+                if (!(prm.debug & 1))
+                  tc::mma_split_ss_n(ksteps, acc, a_hi, a_hi + (16384u >> 4), b_hi, b_hi + (((uint32_t)NT * 128u) >> 4),
+                                     idesc, first);
                 tc::mma_commit(&empty[stage]);
               }
               __syncwarp();
@@ -269,6 +277,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_halo_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_t0 = 0;
+  const long long k_t0 = clock64();
+#define PROF_T0 if (prm.prof) prof_t0 = clock64()
+#define PROF_ADD(i) if (prm.prof) prof_acc[i] += clock64() - prof_t0
   const int items = prm.B * prm.tiles_y * prm.tiles_x * prm.n_ntiles;
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * SUB * NT) tmem_cols <<= 1;
@@ -312,21 +324,29 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_halo_kernel(const __grid_c
           const int x0 = tx * 8 * SUB + org, y0 = ty * CVH_ROWS + org;
           for (int cb = 0; cb < cblocks; ++cb, ++pit) {
             const uint32_t pb = pit & 1u, round = pit >> 1;
-            if (round > 0) tc::mbar_wait(&p_empty[pb], (round - 1) & 1u);
+            if (round > 0) { PROF_T0; tc::mbar_wait(&p_empty[pb], (round - 1) & 1u); PROF_ADD(0); }
             uint8_t* pa = patch0 + (size_t)pb * 2u * patch_plane;
             if (tc::elect_one()) {
-              tc::mbar_expect_tx(&p_full[pb], 2u * (uint32_t)(18 * PW * 128));
-              tc::tma_load_4d(pa, &prm.maps[2 * s], cb * 64, x0, y0, b, &p_full[pb]);
-              tc::tma_load_4d(pa + patch_plane, &prm.maps[2 * s + 1], cb * 64, x0, y0, b, &p_full[pb]);
+              if (prm.debug & 2) {
+                tc::mbar_arrive(&p_full[pb]);
+              } else {
+                tc::mbar_expect_tx(&p_full[pb], 2u * (uint32_t)(18 * PW * 128));
+                tc::tma_load_4d(pa, &prm.maps[2 * s], cb * 64, x0, y0, b, &p_full[pb]);
+                tc::tma_load_4d(pa + patch_plane, &prm.maps[2 * s + 1], cb * 64, x0, y0, b, &p_full[pb]);
+              }
             }
             __syncwarp();
             for (int tap = 0; tap < ks * ks; ++tap, ++bit) {
               const uint32_t st = bit % S, r2 = bit / S;
-              if (r2 > 0) tc::mbar_wait(&b_empty[st], (r2 - 1) & 1u);
+              if (r2 > 0) { PROF_T0; tc::mbar_wait(&b_empty[st], (r2 - 1) & 1u); PROF_ADD(1); }
               if (tc::elect_one()) {
-                tc::mbar_expect_tx(&b_full[st], b_bytes);
-                tc::bulk_load(bring + (size_t)st * b_stage,
-                              wbase + (size_t)(prm.seg_chunk0[s] + tap * cblocks + cb) * b_bytes, b_bytes, &b_full[st]);
+                if (prm.debug & 2) {
+                  tc::mbar_arrive(&b_full[st]);
+                } else {
+                  tc::mbar_expect_tx(&b_full[st], b_bytes);
+                  tc::bulk_load(bring + (size_t)st * b_stage,
+                                wbase + (size_t)(prm.seg_chunk0[s] + tap * cblocks + cb) * b_bytes, b_bytes, &b_full[st]);
+                }
               }
               __syncwarp();
             }
@@ -342,7 +362,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_halo_kernel(const __grid_c
       uint32_t pit = 0, bit = 0, tile_i = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
         const uint32_t a = tile_i & 1u, use = tile_i >> 1;
-        if (use > 0) tc::mbar_wait(&acc_empty[a], (use - 1) & 1u);
+        if (use > 0) { PROF_T0; tc::mbar_wait(&acc_empty[a], (use - 1) & 1u); PROF_ADD(2); }
         tc::fence_after_sync();
         const uint32_t acc = tmem + a * SUB * NT;
         uint32_t first = 1;
@@ -351,13 +371,13 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_halo_kernel(const __grid_c
           const int cblocks = (C + 63) >> 6;
           for (int cb = 0; cb < cblocks; ++cb, ++pit) {
             const uint32_t pb = pit & 1u;
-            tc::mbar_wait(&p_full[pb], (pit >> 1) & 1u);
+            { PROF_T0; tc::mbar_wait(&p_full[pb], (pit >> 1) & 1u); PROF_ADD(3); }
             tc::fence_after_sync();
             const uint32_t pa = tc::smem_u32(patch0 + (size_t)pb * 2u * patch_plane);
             const int ksteps = (min(64, C - cb * 64) + 15) >> 4;
             for (int tap = 0; tap < ks * ks; ++tap, ++bit) {
               const uint32_t st = bit % S;
-              tc::mbar_wait(&b_full[st], (bit / S) & 1u);
+              { PROF_T0; tc::mbar_wait(&b_full[st], (bit / S) & 1u); PROF_ADD(4); }
               tc::fence_after_sync();
               const uint32_t sb = tc::smem_u32(bring + (size_t)st * b_stage);
               const int dy = (ks == 3) ? tap / 3 : 1, dx = (ks == 3) ? tap % 3 : 1;
@@ -365,7 +385,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_halo_kernel(const __grid_c
               if (tc::elect_one()) {
                 const uint64_t a_hi = tc::smem_desc_sw128(pa + row0, sbo), b_hi = tc::smem_desc_sw128(sb);
                 const uint64_t a_lo = a_hi + (patch_plane >> 4), b_lo = b_hi + (((uint32_t)NT * 128u) >> 4);
-                for (int sub = 0; sub < SUB; ++sub)  // sub-tile 1 sits 8 pixels = 1024 B to the right
+                for (int sub = 0; sub < SUB && !(prm.debug & 1); ++sub)  // sub-tile 1 sits 8 pixels = 1024 B to the right
                   tc::mma_split_ss_n(ksteps, acc + sub * NT, a_hi + sub * 64, a_lo + sub * 64, b_hi, b_lo, idesc, first);
                 tc::mma_commit(&b_empty[st]);
               }
@@ -393,8 +413,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_halo_kernel(const __grid_c
       const int ty = (mt / prm.tiles_x) % prm.tiles_y;
       const int b = mt / (prm.tiles_x * prm.tiles_y);
       const uint32_t a = tile_i & 1u;
-      tc::mbar_wait(&acc_full[a], (tile_i >> 1) & 1u);
+      { PROF_T0; tc::mbar_wait(&acc_full[a], (tile_i >> 1) & 1u); PROF_ADD(5); }
       tc::fence_after_sync();
+      const long long ep0 = prm.prof ? clock64() : 0;
       const int n_base = nt * NT;
       for (int sub = 0; sub < SUB; ++sub) {
         const int oy = ty * CVH_ROWS + (row >> 3), ox = tx * 8 * SUB + sub * 8 + (row & 7);
@@ -446,7 +467,14 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_halo_kernel(const __grid_c
       }
       tc::fence_before_sync();
       tc::mbar_arrive(&acc_empty[a]);
+      if (prm.prof) prof_acc[6] += clock64() - ep0;
     }
+  }
+  if (prm.prof && lane == 0 && (warp <= 2)) {
+    long long* o = prm.prof + (size_t)blockIdx.x * 8;
+    if (warp == 0) { o[0] = prof_acc[0]; o[1] = prof_acc[1]; }
+    if (warp == 1) { o[2] = prof_acc[2]; o[3] = prof_acc[3]; o[4] = prof_acc[4]; o[7] = clock64() - k_t0; }
+    if (warp == 2) { o[5] = prof_acc[5]; o[6] = prof_acc[6]; }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -456,22 +484,6 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_halo_kernel(const __grid_c
 // ------------------------------------------------------------------------------------------------
 // host side: plan objects (tensor maps are encoded once, launches are cheap and graph-capturable)
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 struct ConvPlan {
   ConvKParams k;
   size_t smem;
@@ -534,6 +546,7 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
     halo = sg.stride == 1 && ((sg.ksize == 3 && (sg.pad == 0 || sg.pad == 1)) || (sg.ksize == 1 && sg.pad == 0));
   }
   k.halo = halo ? 1 : 0;
+  k.debug = getenv("B200_CONV_DEBUG") ? atoi(getenv("B200_CONV_DEBUG")) : 0;
   k.sub = 1;
   if (halo) {
     k.sub = (k.NT <= 64) ? 2 : 1;
@@ -643,6 +656,13 @@ extern "C" int b200_conv_run(void* plan, void* stream) {
     conv_tc_kernel<<<p->grid, CV_THREADS, p->smem, (cudaStream_t)stream>>>(p->k);
   B200_CHECK_LAUNCH("conv_run");
   return 0;
+}
+
+// dev only: attach a [grid][8] int64 buffer for per-CTA role timings (halo kernel); returns the grid size
+extern "C" int b200_conv_set_prof(void* plan, long long* buf) {
+  ConvPlan* p = (ConvPlan*)plan;
+  p->k.prof = buf;
+  return p->grid;
 }
 
 extern "C" int b200_conv_destroy(void* plan) {

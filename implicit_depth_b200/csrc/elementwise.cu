@@ -401,50 +401,54 @@ extern "C" int b200_maxblurpool(const void* in_hi, const void* in_lo, void* out_
 }
 
 // ---------------------------------------------------------------------------------------
-// Binary-occupancy MLP glue (bd_model.py:412-442): the per-plane inputs that change with the
-// rendered depth plane -- depth (channel 0) and the optional temporal prior (channel 1) -- as an
-// 8-channel split NHWC tensor (zero padded) that enters the first layer as a 1x1-conv K-segment,
-// and the extraction of the single logit channel from the padded 16-channel last layer.
+// Temporal prior (BDModel.sample_prior, experiment_modules/bd_model.py:395-410): back-project every pixel of
+// the current frame at its rendered depth (BackprojectDepth, utils/geometry_utils.py:54-63), project it into
+// the previous frame (Project3D, :76-89, z clamped to 1e-5), and fetch the previous prediction with
+// F.grid_sample(mode="nearest", zeros padding, align_corners=False); pixels with rendered depth <= 0 get -1
+// (the z > 0 half of the reference's mask is always true because of the clamp).
+//   P    [B, 12] = (K @ prior_cam_T_world @ world_T_cam)[:3, :4] row-major
+//   invK [B, 16] row-major 4x4 (only the upper 3x3 is read)
 // ---------------------------------------------------------------------------------------
-__global__ void pack_depth_prior_kernel(const float* __restrict__ depth, long long d_sB, const float* __restrict__ prior,
-                                        long long p_sB, __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol,
-                                        int B, int HW) {
+__global__ void sample_prior_kernel(const float* __restrict__ depth, const float* __restrict__ prior,
+                                    const float* __restrict__ P, const float* __restrict__ invK,
+                                    float* __restrict__ out, int B, int H, int W) {
+  const int HW = H * W;
   const size_t total = (size_t)B * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int b = (int)(i / HW), p = (int)(i % HW);
-    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    v[0] = depth[(size_t)b * d_sB + p];
-    if (prior) v[1] = prior[(size_t)b * p_sB + p];
-    store8(oh, ol, i * 8, v);
+    const int b = (int)(i / HW), p = (int)(i - (size_t)b * HW);
+    const int y = p / W, x = p - y * W;
+    const float* Kb = invK + b * 16;
+    const float* Pb = P + b * 12;
+    const float pxc = x + 0.5f, pyc = y + 0.5f;
+    const float d = depth[i];
+    float X[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) X[r] = d * (Kb[4 * r] * pxc + Kb[4 * r + 1] * pyc + Kb[4 * r + 2]);
+    float c[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) c[r] = Pb[4 * r] * X[0] + Pb[4 * r + 1] * X[1] + Pb[4 * r + 2] * X[2] + Pb[4 * r + 3];
+    const float z = fmaxf(c[2], 1e-5f);
+    // normalise exactly like the reference ((p / size - 0.5) * 2), un-normalise like ATen (((g + 1) * size - 1) / 2)
+    const float gx = (__fdiv_rn(__fdiv_rn(c[0], z), (float)W) - 0.5f) * 2.f;
+    const float gy = (__fdiv_rn(__fdiv_rn(c[1], z), (float)H) - 0.5f) * 2.f;
+    const float ix = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)W), -1.f), 0.5f);
+    const float iy = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)H), -1.f), 0.5f);
+    const float rx = nearbyintf(fminf(fmaxf(ix, -2.f), (float)W + 1.f));  // round-half-even like std::nearbyint
+    const float ry = nearbyintf(fminf(fmaxf(iy, -2.f), (float)H + 1.f));
+    float v = 0.f;
+    if (rx >= 0.f && rx < (float)W && ry >= 0.f && ry < (float)H && ix == ix && iy == iy)
+      v = prior[(size_t)b * HW + (int)ry * W + (int)rx];
+    out[i] = d > 0.f ? v : -1.f;
   }
-}
-extern "C" int b200_pack_depth_prior(const float* depth, long long depth_batch_stride, const float* prior,
-                                     long long prior_batch_stride, void* out_hi, void* out_lo, int B, int HW,
-                                     void* stream) {
-  B200_CHECK_ARG(depth && out_hi && out_lo && B > 0 && HW > 0, "pack_depth_prior: bad arguments");
-  int blocks = (int)(((size_t)B * HW + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_depth_prior_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(depth, depth_batch_stride, prior,
-                                                                   prior_batch_stride, (__nv_bfloat16*)out_hi,
-                                                                   (__nv_bfloat16*)out_lo, B, HW);
-  B200_CHECK_LAUNCH("pack_depth_prior");
-  return 0;
 }
 
-__global__ void gather_channel_kernel(const float* __restrict__ in, int C, int ch, float* __restrict__ out,
-                                      long long o_sB, int B, int HW) {
-  const size_t total = (size_t)B * HW;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int b = (int)(i / HW), p = (int)(i % HW);
-    out[(size_t)b * o_sB + p] = in[i * C + ch];
-  }
-}
-extern "C" int b200_gather_channel(const float* in_nhwc, int C, int ch, float* out, long long out_batch_stride, int B,
-                                   int HW, void* stream) {
-  B200_CHECK_ARG(in_nhwc && out && ch >= 0 && ch < C && B > 0 && HW > 0, "gather_channel: bad arguments");
-  int blocks = (int)(((size_t)B * HW + 255) / 256);
+extern "C" int b200_sample_prior(const float* rendered_depth, const float* prior_prediction, const float* P,
+                                 const float* invK, float* out, int B, int H, int W, void* stream) {
+  B200_CHECK_ARG(rendered_depth && prior_prediction && P && invK && out && B > 0 && H > 0 && W > 0,
+                 "sample_prior: bad arguments");
+  int blocks = (int)(((size_t)B * H * W + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gather_channel_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in_nhwc, C, ch, out, out_batch_stride, B, HW);
-  B200_CHECK_LAUNCH("gather_channel");
+  sample_prior_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rendered_depth, prior_prediction, P, invK, out, B, H, W);
+  B200_CHECK_LAUNCH("sample_prior");
   return 0;
 }

@@ -493,51 +493,102 @@ class BinaryMLPNetwork(nn.Module):
                                                    nn.Linear(mlp_size, mlp_size), nn.ELU(inplace=True),
                                                    nn.Linear(mlp_size, 1))
 
-    def plan_val(self, g: Plan, feat: SplitAct, get_depth, num_planes, get_prior=None):
-        """BDModel.run_mlp_val for every rendered plane (bd_model.py:293-304, 412-442) as 1x1 convs on the
-        tensor cores.  The feature part of layer 1 does not depend on the plane, so W1[:,1:1+C] . feat + b1 is
-        computed once and enters each plane's first layer as a residual; per plane only the depth (+prior)
-        column changes.  get_depth() -> [B, P, H, W] fp32; returns pred [B, P, H, W] fp32 (logits)."""
-        mlp = self.mlps["s0"]
-        B, H, W, C = feat.shape
-        dev = g.device
-        W1 = mlp[0].weight.detach()
-        assert W1.shape[1] == C + (2 if self.use_prior else 1)
-        w_feat = W1[:, 1:1 + C].reshape(128, C, 1, 1)
-        f1, _ = g.conv([(feat, w_feat, 1, 0)], mlp[0].bias, 128, act="none")
-        w_dp = torch.zeros((128, 8, 1, 1), device=dev)
-        w_dp[:, 0, 0, 0] = W1[:, 0]
-        if self.use_prior:
-            w_dp[:, 1, 0, 0] = W1[:, 1 + C]
-        w2 = mlp[2].weight.detach().reshape(128, 128, 1, 1)
-        w3 = torch.zeros((16, 128, 1, 1), device=dev)
-        w3[0, :, 0, 0] = mlp[4].weight.detach()[0]
-        b3 = torch.zeros(16, device=dev)
-        b3[0] = mlp[4].bias.detach()[0]
-        pred = g.empty((B, num_planes, H, W))
-        dp = g.act(B, H, W, 8)
-        h1 = h2 = o32 = None  # scratch shared by all planes
-        for p in range(num_planes):
-            def pack(p=p):
-                d = get_depth()
-                assert tuple(d.shape) == (B, num_planes, H, W) and d.is_contiguous() and d.dtype == torch.float32
-                pr = get_prior() if (self.use_prior and get_prior is not None) else None
-                dptr = d.data_ptr() + 4 * p * H * W
-                pptr = None
-                pstride = 0
-                if pr is not None:
-                    assert pr.is_contiguous() and pr.dtype == torch.float32 and pr.shape[0] == B
-                    pptr = pr.data_ptr() + 4 * (p % pr.shape[1]) * H * W
-                    pstride = pr.shape[1] * H * W
-                _abi.call("b200_pack_depth_prior", ctypes.c_void_p(dptr), num_planes * H * W,
-                          ctypes.c_void_p(pptr) if pptr else None, pstride, _abi.ptr(dp.hi), _abi.ptr(dp.lo), B, H * W,
-                          _abi.stream_ptr())
+    def _pack(self, dev):
+        """Shared-memory weight image + fp32 vectors of the fused kernel (csrc/binary_mlp_tc.cu)."""
+        from .cost_volume import sw128_tiles
 
-            g.add(pack)
-            h1, _ = g.conv([(dp, w_dp, 1, 0)], None, 128, act="elu", residual=f1, out=h1)
-            h2, _ = g.conv([(h1, w2, 1, 0)], mlp[2].bias, 128, act="elu", out=h2)
-            _, o32 = g.conv([(h2, w3, 1, 0)], b3, 16, act="none", want_f32=True, want_split=False, out_f32=o32)
-            g.add(lambda p=p, o32=o32: _abi.call("b200_gather_channel", _abi.ptr(o32), 16, 0,
-                                                 ctypes.c_void_p(pred.data_ptr() + 4 * p * H * W),
-                                                 num_planes * H * W, B, H * W, _abi.stream_ptr()))
+        mlp = self.mlps["s0"]
+        W1 = mlp[0].weight.detach().to(dev, torch.float32)
+        C = W1.shape[1] - (2 if self.use_prior else 1)
+        if C != 64 or W1.shape[0] != 128:
+            raise ValueError("the fused binary MLP kernel is built for 64 feature channels and mlp_size 128")
+
+        def split(m):
+            hi = m.to(torch.bfloat16)
+            return hi, (m - hi.float()).to(torch.bfloat16)
+
+        h1, l1 = split(W1[:, 1:1 + C].contiguous())
+        h2, l2 = split(mlp[2].weight.detach().to(dev, torch.float32).contiguous())
+        t2h, t2l = sw128_tiles(h2), sw128_tiles(l2)  # two 16 KB K-chunks each
+        wimage = torch.cat([sw128_tiles(h1), sw128_tiles(l1), t2h[:16384], t2l[:16384], t2h[16384:],
+                            t2l[16384:]]).contiguous()
+        vecs = torch.zeros((6, 128), device=dev, dtype=torch.float32)
+        vecs[0] = mlp[0].bias.detach()
+        vecs[1] = W1[:, 0]
+        if self.use_prior:
+            vecs[2] = W1[:, 1 + C]
+        vecs[3] = mlp[2].bias.detach()
+        vecs[4] = mlp[4].weight.detach()[0]
+        vecs[5, 0] = mlp[4].bias.detach()[0]
+        return wimage, vecs
+
+    def _fused_plan(self, g: Plan, feat: SplitAct):
+        import ctypes as C
+
+        class Desc(C.Structure):
+            _fields_ = [("feat_hi", C.c_void_p), ("feat_lo", C.c_void_p), ("npix", C.c_longlong), ("HW", C.c_int),
+                        ("wimage", C.c_void_p), ("vecs", C.c_void_p), ("use_prior", C.c_int)]
+
+        wimage, vecs = self._pack(g.device)
+        d = Desc(feat.hi.data_ptr(), feat.lo.data_ptr(), feat.B * feat.H * feat.W, feat.H * feat.W, wimage.data_ptr(),
+                 vecs.data_ptr(), 1 if self.use_prior else 0)
+        handle = C.c_void_p()
+        _abi.call("b200_binary_mlp_create", C.byref(d), C.byref(handle))
+        g._keep += [wimage, vecs, feat, _PlanHandle(handle, "b200_binary_mlp_destroy")]
+        return handle
+
+    def plan_val(self, g: Plan, feat: SplitAct, get_depth, num_planes, get_prior=None):
+        """BDModel.run_mlp_val for every rendered plane (bd_model.py:293-304, 412-442) as ONE fused tcgen05 kernel:
+        the 64-channel feature tile of 128 pixels is loaded once and all planes are evaluated from it.
+        get_depth() -> [B, P, H, W] fp32; get_prior() -> [B, 1, H, W] fp32 or None (= -1 everywhere when the model
+        uses a prior); returns pred [B, P, H, W] fp32 (logits)."""
+        B, H, W, _ = feat.shape
+        handle = self._fused_plan(g, feat)
+        pred = g.empty((B, num_planes, H, W))
+
+        def op():
+            d = get_depth()
+            assert tuple(d.shape) == (B, num_planes, H, W) and d.is_contiguous() and d.dtype == torch.float32
+            pr = get_prior() if (self.use_prior and get_prior is not None) else None
+            if pr is not None:
+                assert tuple(pr.shape) == (B, 1, H, W) and pr.is_contiguous() and pr.dtype == torch.float32
+            _abi.require_cuda(d, pr)
+            _abi.call("b200_binary_mlp_planes", handle, _abi.ptr(d), num_planes, _abi.ptr(pr), _abi.ptr(pred),
+                      _abi.stream_ptr())
+
+        g.add(op)
         return pred
+
+    def plan_search(self, g: Plan, feat: SplitAct, get_prior=None, iters=12, min_bound=0.5, max_bound=8.0,
+                    first_depth=7.5 / 2.0):
+        """The `infer_depth` bisection of BDModel.forward (bd_model.py:273-292) in the same fused kernel: per pixel
+        12 evaluations of the MLP at the running query depth, bounds kept in registers.  Returns (search_depths,
+        pred of the last evaluation), both [B, 1, H, W] fp32."""
+        B, H, W, _ = feat.shape
+        handle = self._fused_plan(g, feat)
+        search = g.empty((B, 1, H, W))
+        pred = g.empty((B, 1, H, W))
+
+        def op():
+            pr = get_prior() if (self.use_prior and get_prior is not None) else None
+            if pr is not None:
+                assert tuple(pr.shape) == (B, 1, H, W) and pr.is_contiguous() and pr.dtype == torch.float32
+            _abi.call("b200_binary_mlp_search", handle, _abi.ptr(pr), iters, min_bound, max_bound, first_depth,
+                      _abi.ptr(search), _abi.ptr(pred), _abi.stream_ptr())
+
+        g.add(op)
+        return search, pred
+
+
+class _PlanHandle:
+    """Owns a C-side plan object for the life of a launch plan."""
+
+    def __init__(self, handle, destroy):
+        self.handle, self.destroy = handle, destroy
+
+    def __del__(self):
+        try:
+            if self.handle:
+                getattr(_abi.load(), self.destroy)(self.handle)
+        except Exception:
+            pass

@@ -134,12 +134,32 @@ int b200_stem_conv7(const float* img, const float* wt, const float* bias, void* 
  * (call site modules/networks.py:267); [B,H,W,C] -> [B,H/2,W/2,C]. */
 int b200_maxblurpool(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int B, int H, int W, int C,
                      void* stream);
-/* Binary-MLP glue (experiment_modules/bd_model.py:412-442): per-plane depth (+prior) as an 8-channel
- * split tensor; and extraction of one channel of an fp32 NHWC tensor into a strided plane. */
-int b200_pack_depth_prior(const float* depth, long long depth_batch_stride, const float* prior,
-                          long long prior_batch_stride, void* out_hi, void* out_lo, int B, int HW, void* stream);
-int b200_gather_channel(const float* in_nhwc, int C, int ch, float* out, long long out_batch_stride, int B, int HW,
-                        void* stream);
+/* ---- binary-occupancy MLP (modules/networks.py:87-115 BinaryMLPNetwork scale 0; BDModel.run_mlp_val
+ * experiment_modules/bd_model.py:412-442 looped over rendered planes :293-304; infer_depth bisection :273-292) ----
+ * One fused tcgen05 kernel: a 128-pixel tile of the 64-channel decoder feature (NHWC split-bf16) is TMA-loaded
+ * once and every plane / bisection step is evaluated from it.  The plan owns the TMA descriptors. */
+typedef struct {
+  const void* feat_hi;  /* NHWC bf16 [npix, 64] (feature_s0, hi and lo halves) */
+  const void* feat_lo;
+  long long npix;       /* B * H * W */
+  int HW;               /* H * W */
+  const void* wimage;   /* 96 KB: W1[:,1:65] hi|lo, W2[:, :64] hi|lo, W2[:, 64:] hi|lo as 128x64 bf16 SW128 tiles */
+  const float* vecs;    /* [6][128] fp32: b1, W1[:,0] (depth column), W1[:,65] (prior column) or 0, b2, w3, {b3} */
+  int use_prior;
+} b200_binary_mlp_desc;
+int b200_binary_mlp_create(const b200_binary_mlp_desc* desc, void** plan_out);
+/* depth [B,P,H,W] fp32; prior [B,1,H,W] fp32 or NULL (-1 everywhere if the model uses a prior); pred [B,P,H,W]. */
+int b200_binary_mlp_planes(void* plan, const float* depth, int P, const float* prior, float* pred, void* stream);
+/* per-pixel bisection: `iters` evaluations starting at first_depth inside [min_bound, max_bound];
+ * search_out [B,1,H,W] = final query depth, pred_out [B,1,H,W] = logit of the last evaluation. */
+int b200_binary_mlp_search(void* plan, const float* prior, int iters, float min_bound, float max_bound,
+                           float first_depth, float* search_out, float* pred_out, void* stream);
+int b200_binary_mlp_destroy(void* plan);
+/* BDModel.sample_prior (experiment_modules/bd_model.py:395-410): warp the previous frame's prediction into the
+ * current frame through the rendered depth, nearest sampling, -1 where the rendered depth is not positive.
+ *   P [B,12] = (K_s0 @ prior_cam_T_world @ world_T_cam)[:3,:4]; invK [B,16] = invK_s0; all maps [B,1,H,W]. */
+int b200_sample_prior(const float* rendered_depth, const float* prior_prediction, const float* P, const float* invK,
+                      float* out, int B, int H, int W, void* stream);
 
 /* Self-test of the tcgen05/TMEM building blocks: D[128,N] = A[128,K] * Bm[N,K]^T on one CTA.
  *   mode 0: bf16 operands from shared memory; 1: A from tensor memory; 2/3: split-bf16 (fp32-grade)

@@ -134,7 +134,7 @@ def binary_mlp_val(sd, p, feat, rendered_depth, prior=None):
 
 
 def bd_forward(sd, encoder, cur, src, opts, feature_volume="mlp_feature_volume", decoder="unet_pp", return_mask=True,
-               torch_volume=False):
+               torch_volume=False, infer_depth=False):
     """`BDModel.forward(phase="test")`, bd_model.py:175-311.  cur/src: dicts of CPU float tensors; `encoder`:
     the image-prior module (same instance the product uses, on CPU)."""
     ms = opts.matching_scale
@@ -180,8 +180,21 @@ def bd_forward(sd, encoder, cur, src, opts, feature_volume="mlp_feature_volume",
                                                                                                  feats)
         prior = None
         if getattr(opts, "use_prior", False):
-            prior = -torch.ones_like(cur["rendered_depth"][:, :1])  # :433-434
-        pred = binary_mlp_val(sd, "binary_mlp", dec["feature_s0_b1hw"], cur["rendered_depth"], prior)
-    return {"pred_0": pred, "lowest_cost_bhw": torch.from_numpy(lowest),
+            if cur.get("prior_prediction", None) is not None:  # :423-431
+                prior = torch.from_numpy(planesweep.sample_prior(
+                    cur["rendered_depth"].numpy(), cur["prior_prediction"].numpy(), cur["world_T_cam_b44"].numpy(),
+                    cur["prior_cam_T_world"].numpy(), cur["K_s0_b44"].numpy(), cur["invK_s0_b44"].numpy()))
+            else:
+                prior = -torch.ones_like(cur["rendered_depth"][:, :1])  # :433-434
+        search = None
+        if infer_depth:  # :273-292
+            W = [(sd[f"binary_mlp.mlps.s0.{i}.weight"].numpy(), sd[f"binary_mlp.mlps.s0.{i}.bias"].numpy())
+                 for i in (0, 2, 4)]
+            z, pred = planesweep.binary_search_depth(dec["feature_s0_b1hw"].numpy(), W,
+                                                     None if prior is None else prior.numpy())
+            search, pred = torch.from_numpy(z), torch.from_numpy(pred)
+        else:
+            pred = binary_mlp_val(sd, "binary_mlp", dec["feature_s0_b1hw"], cur["rendered_depth"], prior)
+    return {"pred_0": pred, "search_depths": search, "prior_mask": prior, "lowest_cost_bhw": torch.from_numpy(lowest),
             "overall_mask_bhw": None if mask is None else torch.from_numpy(mask), "cost_volume": torch.from_numpy(vol),
             "feature_s0": dec["feature_s0_b1hw"], "matching_feats": mf}

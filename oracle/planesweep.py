@@ -259,3 +259,52 @@ def binary_mlp(feature_s0, rendered_depth, weights, prior=None):
         if i + 1 < len(weights):
             x = elu(x)
     return x.transpose(0, 3, 1, 2)
+
+
+def sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def binary_search_depth(feature_s0, weights, prior=None, iters=12, min_bound=0.5, max_bound=8.0):
+    """`infer_depth` branch of `BDModel.forward`, `experiment_modules/bd_model.py:273-292` (thresholder None):
+    per-pixel bisection on the occupancy logit.  Returns (search_depths, pred of the last evaluation)."""
+    B, _, H, W = feature_s0.shape
+    dt = feature_s0.dtype
+    lo = np.full((B, 1, H, W), min_bound, dt)
+    hi = np.full((B, 1, H, W), max_bound, dt)
+    z = np.full((B, 1, H, W), 7.5 / 2.0, dt)
+    pred = None
+    for _ in range(iters):
+        pred = binary_mlp(feature_s0, z, weights, prior)
+        visible = sigmoid(pred) < 0.5
+        hi = np.where(visible, z, hi)
+        lo = np.where(visible, lo, z)
+        z = (hi + lo) / dt.type(2)
+    return z, pred
+
+
+def sample_prior(rendered_depth, prior_prediction, cam_to_world, prior_world_to_cam, K, invK):
+    """`BDModel.sample_prior`, `experiment_modules/bd_model.py:395-410`: warp the previous prediction into the
+    current view through the rendered depth; `F.grid_sample(mode="nearest")` (zeros padding,
+    align_corners=False: unnormalise ((g+1)*size-1)/2, round half to even); -1 where rendered depth <= 0
+    (the `z > 0` factor of the mask is always true, z being clamped to 1e-5 by Project3D)."""
+    B, _, H, W = rendered_depth.shape
+    dt = rendered_depth.dtype.type
+    out = np.zeros_like(rendered_depth)
+    pix = pixel_grid(H, W, rendered_depth.dtype.type)
+    for b in range(B):
+        cur_to_prior = prior_world_to_cam[b] @ cam_to_world[b]
+        X = backproject(rendered_depth[b].reshape(1, -1), invK[b], pix)
+        px, py, _ = project(X, K[b], cur_to_prior)
+        gx = (px / dt(W) - dt(0.5)) * dt(2)
+        gy = (py / dt(H) - dt(0.5)) * dt(2)
+        ix = ((gx + dt(1)) * dt(W) - dt(1)) / dt(2)
+        iy = ((gy + dt(1)) * dt(H) - dt(1)) / dt(2)
+        rx = np.rint(np.clip(ix, -2, W + 1)).astype(np.int64)
+        ry = np.rint(np.clip(iy, -2, H + 1)).astype(np.int64)
+        ok = (rx >= 0) & (rx < W) & (ry >= 0) & (ry < H)
+        flat = prior_prediction[b].reshape(-1)
+        v = np.where(ok, flat[np.where(ok, ry * W + rx, 0)], dt(0))
+        v = np.where(rendered_depth[b].reshape(-1) > 0, v, dt(-1))
+        out[b, 0] = v.reshape(H, W)
+    return out

@@ -172,7 +172,74 @@ def network_goldens():
         print("model", fv_type, {k: v.shape for k, v in g.items()}, "pred range", g["pred_0"].min(), g["pred_0"].max())
 
 
+def temporal_goldens():
+    """use_prior model (implicit_depth_temporal.yaml): prior warp + 66-input binary MLP; and the infer_depth
+    bisection of the plain model.  256x192, 7 views, 16 planes, one rendered plane."""
+    import options as ref_options  # reference
+    from experiment_modules.bd_model import BDModel  # reference
+    from utils.geometry_utils import BackprojectDepth  # reference
+
+    from implicit_depth_b200.bd_model import B200BDModel, default_options
+
+    real_cuda = torch.nn.Module.cuda
+    torch.nn.Module.cuda = lambda self, *a, **k: self  # BDModel.__init__ calls .cuda() when use_prior (bd_model.py:138)
+    try:
+        g = {}
+        for use_prior in (True, False):
+            opts = default_options(image_width=256, image_height=192, matching_num_depth_bins=16, use_prior=use_prior)
+            mine = B200BDModel(opts)
+            checksum = synthetic.init_model_weights(mine, seed=0)
+            ro = ref_options.Options()
+            ro.image_width, ro.image_height, ro.matching_num_depth_bins = 256, 192, 16
+            ro.use_prior = use_prior
+            ro.binary_loss_positive_weight = 1.0
+            ro.bd_edge_regularision = False
+            ref = BDModel(ro)
+            ref.load_state_dict(dict(mine.state_dict()), strict=True)
+            ref.eval()
+            if use_prior:
+                ref.backprojector = BackprojectDepth(96, 128)  # the reference hard-codes 192x256 (bd_model.py:138)
+            cur, src = synthetic.make_frame_batch(5000, 1, 7, 192, 256, num_rendered=1, temporal=True)
+            cur_t = {k: torch.from_numpy(v) for k, v in cur.items()}
+            src_t = {k: torch.from_numpy(v) for k, v in src.items()}
+            if use_prior:
+                g["checksum_prior"] = np.array(checksum)
+                o = ref("test", dict(cur_t), src_t, unbatched_matching_encoder_forward=True, return_mask=True)
+                g["prior_pred_0"] = o["pred_0"].numpy()
+                g["prior_mask"] = ref.sample_prior(cur_t["rendered_depth"], cur_t["prior_prediction"],
+                                                   cur_t["world_T_cam_b44"], cur_t["prior_cam_T_world"],
+                                                   cur_t["K_s0_b44"], cur_t["invK_s0_b44"]).numpy()
+                no_prior = {k: v for k, v in cur_t.items() if not k.startswith("prior_")}
+                o = ref("test", no_prior, src_t, unbatched_matching_encoder_forward=True, return_mask=True)
+                g["noprior_pred_0"] = o["pred_0"].numpy()  # first frame of a sequence: prior = -1 (bd_model.py:434)
+                # sample_prior alone at the cfg4 size (240x320) with a rendered-depth map that has holes
+                ref.backprojector = BackprojectDepth(240, 320)
+                c4, _ = synthetic.make_frame_batch(5001, 2, 1, 480, 640, num_rendered=1, temporal=True)
+                rng = np.random.default_rng(7)
+                rd = rng.uniform(0.5, 4.0, size=c4["rendered_depth"].shape).astype(np.float32)
+                rd[rng.uniform(size=rd.shape) < 0.05] = 0.0
+                g["cfg4_rendered_depth"] = rd
+                t4 = {k: torch.from_numpy(v) for k, v in c4.items()}
+                g["cfg4_prior_mask"] = ref.sample_prior(torch.from_numpy(rd), t4["prior_prediction"],
+                                                        t4["world_T_cam_b44"], t4["prior_cam_T_world"], t4["K_s0_b44"],
+                                                        t4["invK_s0_b44"]).numpy()
+            else:
+                g["checksum_search"] = np.array(checksum)
+                o = ref("test", cur_t, src_t, unbatched_matching_encoder_forward=True, return_mask=True,
+                        infer_depth=True)
+                g["search_depths"] = o["search_depths"].numpy()
+                g["search_pred_0"] = o["pred_0"].numpy()
+        np.savez_compressed(os.path.join(HERE, "temporal_256x192.npz"), **g)
+        print("temporal", {k: v.shape for k, v in g.items()})
+    finally:
+        torch.nn.Module.cuda = real_cuda
+
+
 if __name__ == "__main__":
+    if "--temporal-only" in sys.argv:
+        temporal_goldens()
+        sys.exit(0)
     if "--nets-only" not in sys.argv:
         volume_goldens()
     network_goldens()
+    temporal_goldens()

@@ -130,3 +130,78 @@ def _strict_fp32_library_convs():
     torch.backends.cuda.matmul.allow_tf32 = False
     yield
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("use_prior", [False, True])
+def test_fused_binary_mlp_kernel_vs_oracle(use_prior):
+    """csrc/binary_mlp_tc.cu against the numpy restatement of run_mlp_val on a ragged map (pixel count not a
+    multiple of the 128-row tile), several planes, with and without the prior column."""
+    from implicit_depth_b200.conv import SplitAct
+    from implicit_depth_b200.networks import BinaryMLPNetwork, Plan
+
+    rng = np.random.default_rng(11)
+    B, H, W, P = 2, 37, 53, 3
+    feat = rng.standard_normal((B, 64, H, W)).astype(np.float32)
+    depth = rng.uniform(0.5, 6.0, size=(B, P, H, W)).astype(np.float32)
+    prior = rng.uniform(-1, 1, size=(B, 1, H, W)).astype(np.float32) if use_prior else None
+    torch.manual_seed(3)
+    net = BinaryMLPNetwork([64, 64, 128, 256], mlp_size=128, use_prior=use_prior).cuda()
+    Wt = [(net.mlps["s0"][i].weight.detach().cpu().numpy(), net.mlps["s0"][i].bias.detach().cpu().numpy())
+          for i in (0, 2, 4)]
+    g = Plan("cuda")
+    fa = SplitAct.from_nchw_torch(torch.from_numpy(feat).cuda())
+    d_c = torch.from_numpy(depth).cuda()
+    p_c = None if prior is None else torch.from_numpy(prior).cuda()
+    pred = net.plan_val(g, fa, lambda: d_c, P, get_prior=(lambda: p_c))
+    g.run()
+    torch.cuda.synchronize()
+    ref = np.concatenate([O.binary_mlp(feat, depth[:, p:p + 1], Wt, prior) for p in range(P)], 1)
+    assert rel_err(pred.cpu().numpy(), ref) < 1e-4
+    # bisection mode against the numpy loop
+    g2 = Plan("cuda")
+    search, last = net.plan_search(g2, fa, get_prior=(lambda: p_c))
+    g2.run()
+    torch.cuda.synchronize()
+    z_ref, pred_ref = O.binary_search_depth(feat, Wt, prior)
+    assert np.abs(search.cpu().numpy() - z_ref).max() <= 2 * 7.5 / 2**12 + 1e-6
+    assert (search.cpu().numpy() != z_ref).mean() < 1e-2
+
+
+def test_sample_prior_kernel_vs_reference_golden():
+    g = np.load(f"{GOLDEN}/temporal_256x192.npz")
+    m, _, _ = seeded(image_width=256, image_height=192, matching_num_depth_bins=16, use_prior=True)
+    c4, _ = synthetic.make_frame_batch(5001, 2, 1, 480, 640, num_rendered=1, temporal=True)
+    t = {k: torch.from_numpy(v).cuda() for k, v in c4.items()}
+    rd = torch.from_numpy(g["cfg4_rendered_depth"]).cuda()
+    got = m.sample_prior(rd, t["prior_prediction"], t["world_T_cam_b44"], t["prior_cam_T_world"], t["K_s0_b44"],
+                         t["invK_s0_b44"]).cpu().numpy()
+    assert got.shape == g["cfg4_prior_mask"].shape
+    assert (got != g["cfg4_prior_mask"]).mean() < 1e-3  # nearest sampling: rounding-boundary pixels may flip
+    ref = O.sample_prior(g["cfg4_rendered_depth"], c4["prior_prediction"], c4["world_T_cam_b44"],
+                         c4["prior_cam_T_world"], c4["K_s0_b44"], c4["invK_s0_b44"])
+    assert (got != ref).mean() < 1e-3
+    assert ((got == -1) >= (g["cfg4_rendered_depth"] <= 0)).all()
+
+
+@pytest.mark.parametrize("mode", ["prior", "noprior", "search"])
+def test_temporal_and_infer_depth_forward_vs_reference_golden(mode):
+    """implicit_depth_temporal.yaml path (use_prior: prior warp + 66-input MLP) and the
+    infer_depth bisection through B200BDModel.forward, against the reference goldens."""
+    g = np.load(f"{GOLDEN}/temporal_256x192.npz")
+    use_prior = mode != "search"
+    m, checksum, sd = seeded(image_width=256, image_height=192, matching_num_depth_bins=16, use_prior=use_prior)
+    cur, src = synthetic.make_frame_batch(5000, 1, 7, 192, 256, num_rendered=1, temporal=True)
+    cur_c = {k: torch.from_numpy(v).cuda() for k, v in cur.items() if mode == "prior" or not k.startswith("prior_")}
+    src_c = {k: torch.from_numpy(v).cuda() for k, v in src.items()}
+    for graph in (False, True):
+        m.use_cuda_graph = graph
+        out = m("test", dict(cur_c), src_c, return_mask=True, infer_depth=(mode == "search"))
+        if abs(checksum - float(g["checksum_prior" if use_prior else "checksum_search"])) > 1e-6 * checksum:
+            pytest.skip("seeded weights differ from the ones the goldens were generated with")
+        if mode == "search":
+            assert set(out) == {"pred_0", "search_depths", "lowest_cost_bhw", "overall_mask_bhw"}
+            sd_got = out["search_depths"].cpu().numpy()
+            assert np.abs(sd_got - g["search_depths"]).max() <= 4 * 7.5 / 2**12
+            assert (np.abs(sd_got - g["search_depths"]) > 1e-6).mean() < 2e-2
+        else:
+            assert rel_err(out["pred_0"].cpu().numpy(), g[f"{mode}_pred_0"]) < TOL
