@@ -67,34 +67,50 @@ def _swizzle_last(t):
     return torch.gather(v, -2, idx).reshape(t.shape)
 
 
-def pack_conv_weights(weights, seg_channels, cout):
-    """weights: list (one per segment) of [Cout, C_s, k, k] fp32 tensors.  Returns the uint8 image
-    [n_ntiles][chunk][hi NT x 64 | lo NT x 64] in the producer's chunk order (segment, tap, 64-channel block)."""
+def _swizzle64_last(t):
+    """[..., R, 32] bf16 with R % 8 == 0 -> same shape, 16-byte chunk j of row r moved to chunk j ^ ((r >> 1) & 3)
+    (the 64-byte swizzle of a dense tile whose rows are 64 B apart)."""
+    R = t.shape[-2]
+    v = t.reshape(*t.shape[:-1], 4, 8)
+    r = torch.arange(R, device=t.device).view(R, 1, 1)
+    j = torch.arange(4, device=t.device).view(1, 4, 1)
+    idx = (j ^ ((r >> 1) & 3)).expand(R, 4, 8).expand(v.shape)
+    return torch.gather(v, -2, idx).reshape(t.shape)
+
+
+def pack_conv_weights(weights, seg_channels, cout, halo=False):
+    """weights: list (one per segment) of [Cout, C_s, k, k] fp32 tensors.  Returns the uint8 weight image in the
+    producer's chunk order (segment, tap, channel block):
+      plain kernel  [n_ntiles][chunk][hi NT x 64 | lo NT x 64]  64-channel chunks, 128-byte swizzle
+      halo kernel   [n_ntiles][chunk][hi NT x 32 | lo NT x 32]  32-channel chunks, 64-byte swizzle; hi and lo are
+                    adjacent rows of ONE tile so that A_hi x [B_hi | B_lo] is a single N = 2*NT MMA."""
     NT = ntile(cout)
     n_nt = (cout + NT - 1) // NT
+    cw = 32 if halo else 64
     chunks = []
     for w, C in zip(weights, seg_channels):
         k = w.shape[-1]
         assert w.shape[0] == cout and w.shape[1] == C and w.shape[2] == k
-        Cp = (C + 63) // 64 * 64
+        Cp = (C + cw - 1) // cw * cw
         wp = torch.zeros((cout, Cp, k, k), device=w.device, dtype=torch.float32)
         wp[:, :C] = w.detach().float()
-        # [Cout, Cp/64, 64, k, k] -> [k, k, Cp/64, Cout, 64] -> [chunks, Cout, 64]
-        chunks.append(wp.view(cout, Cp // 64, 64, k, k).permute(3, 4, 1, 0, 2).reshape(-1, cout, 64))
-    allw = torch.cat(chunks, 0)  # [Q, Cout, 64]
+        # [Cout, Cp/cw, cw, k, k] -> [k, k, Cp/cw, Cout, cw] -> [chunks, Cout, cw]
+        chunks.append(wp.view(cout, Cp // cw, cw, k, k).permute(3, 4, 1, 0, 2).reshape(-1, cout, cw))
+    allw = torch.cat(chunks, 0)  # [Q, Cout, cw]
     Q = allw.shape[0]
     hi = allw.to(torch.bfloat16)
     lo = (allw - hi.float()).to(torch.bfloat16)
-    both = torch.stack([hi, lo], 1).view(Q, 2, n_nt, NT, 64)  # [Q, part, nt, NT, 64]
-    both = _swizzle_last(both).permute(2, 0, 1, 3, 4).contiguous()  # [nt, Q, part, NT, 64]
-    return both.view(torch.uint8).reshape(-1)
+    both = torch.stack([hi, lo], 1).view(Q, 2, n_nt, NT, cw)  # [Q, part, nt, NT, cw]
+    both = (_swizzle64_last(both) if halo else _swizzle_last(both)).permute(2, 0, 1, 3, 4).contiguous()
+    return both.view(torch.uint8).reshape(-1)  # [nt, Q, part, NT, cw]
 
 
 class ConvPlan:
     """One convolution launch with everything (tensor maps, weight image, buffers) fixed at plan time."""
 
-    def __init__(self, segs, wimage, bias, out, B, cout, act="none", slope=0.2, residual=None, out_f32=None):
-        """segs: list of (SplitAct, ksize, stride, pad); out: SplitAct or None; residual: SplitAct or None."""
+    def __init__(self, segs, weights, bias, out, B, cout, act="none", slope=0.2, residual=None, out_f32=None):
+        """segs: list of (SplitAct, ksize, stride, pad); weights: one [Cout, C, k, k] fp32 tensor per segment;
+        out: SplitAct or None; residual: SplitAct or None."""
         d = _Desc()
         d.nseg = len(segs)
         for i, (a, k, s, p) in enumerate(segs):
@@ -105,7 +121,6 @@ class ConvPlan:
         a0, k0, s0, p0 = segs[0]
         OH = (a0.H + 2 * p0 - k0) // s0 + 1
         OW = (a0.W + 2 * p0 - k0) // s0 + 1
-        d.wimage = wimage.data_ptr()
         d.bias = bias.data_ptr() if bias is not None else None
         d.res_hi = residual.hi.data_ptr() if residual is not None else None
         d.res_lo = residual.lo.data_ptr() if residual is not None else None
@@ -115,9 +130,12 @@ class ConvPlan:
         d.B, d.OH, d.OW, d.Cout = B, OH, OW, cout
         d.act = ACT[act]
         d.slope = slope
+        lib = _abi.load()
+        self.halo = bool(lib.b200_conv_uses_halo(ctypes.byref(d)))  # decides the weight-image layout
+        wimage = pack_conv_weights(weights, [a.C for a, _, _, _ in segs], cout, halo=self.halo)
+        d.wimage = wimage.data_ptr()
         self._keep = (segs, wimage, bias, out, residual, out_f32)  # keep buffers alive
         self.handle = ctypes.c_void_p()
-        lib = _abi.load()
         rc = lib.b200_conv_create(ctypes.byref(d), ctypes.byref(self.handle))
         if rc != 0:
             raise _abi.B200Error(f"b200_conv_create failed ({rc}): {lib.b200_last_error().decode()}")

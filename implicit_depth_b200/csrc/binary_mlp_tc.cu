@@ -39,8 +39,6 @@ struct BmSync {
   uint64_t feat_full, feat_empty, acc1_full, h_full, acc2_full, acc_free;
 };
 
-__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
-
 template <bool SEARCH>
 __global__ void __launch_bounds__(BM_THREADS, 1) binary_mlp_tc_kernel(const __grid_constant__ BmParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -56,7 +54,7 @@ __global__ void __launch_bounds__(BM_THREADS, 1) binary_mlp_tc_kernel(const __gr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long n_tiles = (prm.npix + BM_ROWS - 1) / BM_ROWS;
   const int G = 2 * gridDim.x;
-  const int steps = SEARCH ? prm.P : prm.P;  // evaluations per tile (planes, or bisection iterations)
+  const int steps = prm.P;  // evaluations per tile (rendered planes, or bisection iterations)
 
   for (int i = tid; i < 98304 / 16; i += BM_THREADS)
     reinterpret_cast<uint4*>(base)[i] = __ldg(reinterpret_cast<const uint4*>(prm.wimage) + i);

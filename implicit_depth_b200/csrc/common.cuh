@@ -54,6 +54,10 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 
 __device__ __forceinline__ float leaky(float x, float slope) { return x >= 0.f ? x : x * slope; }
 
+// ELU(alpha = 1).  exp through the SFU (ex2.approx, 2^-22 relative) minus one: absolute error < 3e-7 on values of
+// order one, far inside the 1e-3 parity budget, at 3 instructions instead of expm1f's ~50.
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
+
 // Projection of the pixel-centre ray through plane depth zd into one source view.
 // Mp = M @ (x+.5, y+.5, 1); returns source pixel coords and clamped depth
 // (geometry_utils.py:84-89: z = max(c_z, 1e-5), xy / z).

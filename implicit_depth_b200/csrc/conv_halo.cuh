@@ -1,0 +1,301 @@
+// Halo-patch implicit-GEMM convolution for stride-1 3x3 / 1x1 segments (included by conv_tc.cu).
+//
+// An item is 16 rows x (8*SUB) columns of output pixels (SUB M=128 sub-tiles of 16x8) for one N tile.
+// * A operand: for each 32-channel block of each K-segment ONE TMA box of 18 x (8*SUB+2) pixel records of
+//   64 B lands in shared memory (64-byte swizzle); the 9 taps are 9 UMMA descriptors into that patch (start
+//   shifted by (dy*PW+dx) records, 8-row-group stride PW*64 B) -- each input pixel is fetched once per item
+//   instead of once per tap, and the 32-channel granularity keeps the double-buffered hi+lo patches at 86 KB.
+// * B operand: per (tap, 32-channel block) one 1-D bulk copy of the pre-swizzled tile [hi NT rows | lo NT rows];
+//   hi and lo sit back to back so that  A_hi x [B_hi | B_lo]  is ONE MMA with N = 2*NT (columns [0,NT) collect
+//   hi*hi, columns [NT,2NT) hi*lo) followed by  A_lo x B_hi  with N = NT into columns [0,NT).  M=128 MMAs with
+//   N = 64 cost ~53 clocks instead of 32 (measured, scripts/mma_rate.py), so merging the first two passes of
+//   the split-bf16 product into an N = 128 instruction removes most of that penalty for the 64-channel layers.
+// * Epilogue: 8 warps; TMEM -> registers (main + cross columns) -> bias / residual / activation -> hi/lo split ->
+//   128-byte-swizzled staging tiles in shared memory -> TMA tensor stores (full 128-byte lines, clipping at the
+//   image border done by the TMA unit).  The residual tile is TMA-loaded into the same staging buffer while the
+//   main loop of the item is still running.  The bias vector lives in shared memory.
+#pragma once
+
+#define CVH_THREADS 320
+#define CVH_ROWS 16
+#define CVH_EPI_THREADS 256
+
+template <int SUB, int NTC /* NT / 64: 1 or 2 */>
+__global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvKParams prm) {
+  constexpr int NT = 64 * NTC;
+  constexpr int PW = 8 * SUB + 2;
+  constexpr uint32_t PATCH_PLANE = (18u * PW * 64u + 1023u) & ~1023u;  // one bf16 plane of a 32-channel patch
+  constexpr uint32_t B_BYTES = NT * 128u;                              // [hi NT x 32 | lo NT x 32] bf16
+  constexpr uint32_t STAGE_BLK = 16384u;                               // 128 px x 64 ch bf16 (one store box)
+  constexpr uint32_t STAGING = 2u * NTC * STAGE_BLK;                   // hi + lo of one sub-tile
+  constexpr uint32_t ACC_COLS = SUB * 2 * NT;                          // TMEM columns of one accumulator set
+  static_assert(2 * ACC_COLS <= 512, "TMEM overflow");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = prm.stages;
+  uint8_t* patch0 = base;                                   // 2 patch slots x (hi, lo)
+  uint8_t* staging = base + 4u * PATCH_PLANE;               // SUB staging buffers
+  uint8_t* bring = staging + SUB * STAGING;                 // S weight stages
+  float* bias_s = reinterpret_cast<float*>(bring + (size_t)S * B_BYTES);  // [n_ntiles * NT]
+  uint64_t* p_full = reinterpret_cast<uint64_t*>(bias_s + prm.n_ntiles * NT);
+  uint64_t* p_empty = p_full + 2;
+  uint64_t* acc_full = p_empty + 2;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* res_full = acc_empty + 2;  // [SUB]
+  uint64_t* b_full = res_full + 2;
+  uint64_t* b_empty = b_full + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + S);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_t0 = 0;
+  const long long k_t0 = clock64();
+#define PROF_T0 if (prm.prof) prof_t0 = clock64()
+#define PROF_ADD(i) if (prm.prof) prof_acc[i] += clock64() - prof_t0
+  const int items = prm.B * prm.tiles_y * prm.tiles_x * prm.n_ntiles;
+
+  for (int i = tid; i < prm.n_ntiles * NT; i += CVH_THREADS)
+    bias_s[i] = (prm.bias != nullptr && i < prm.Cout) ? prm.bias[i] : 0.f;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < 2 * prm.nseg; ++s) tc::prefetch_tmap(&prm.maps[s]);
+    tc::prefetch_tmap(&prm.out_maps[0]);
+    tc::prefetch_tmap(&prm.out_maps[1]);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&p_full[i], 1);
+      tc::mbar_init(&p_empty[i], 1);
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&acc_empty[i], CVH_EPI_THREADS);
+      tc::mbar_init(&res_full[i], 1);
+    }
+    for (int s = 0; s < S; ++s) {
+      tc::mbar_init(&b_full[s], 1);
+      tc::mbar_init(&b_empty[s], 1);
+    }
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer (whole warp loops, one elected lane issues) ===========
+    uint32_t pit = 0, bit = 0;  // patch / weight-chunk counters
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int nt = item % prm.n_ntiles;
+      const int mt = item / prm.n_ntiles;
+      const int tx = mt % prm.tiles_x;
+      const int ty = (mt / prm.tiles_x) % prm.tiles_y;
+      const int b = mt / (prm.tiles_x * prm.tiles_y);
+      const uint8_t* wbase = prm.wimage + (size_t)nt * prm.total_chunks * B_BYTES;
+      for (int s = 0; s < prm.nseg; ++s) {
+        const int ks = prm.seg_ksize[s], pd = prm.seg_pad[s];
+        const int cblocks = (prm.seg_C[s] + 31) >> 5;
+        // a 1x1 segment reads the centre of the same kind of patch: origin shifted by (1 - pad)
+        const int org = (ks == 3) ? -pd : -(pd + 1);
+        const int x0 = tx * 8 * SUB + org, y0 = ty * CVH_ROWS + org;
+        for (int cb = 0; cb < cblocks; ++cb, ++pit) {
+          const uint32_t pb = pit & 1u, round = pit >> 1;
+          if (round > 0) { PROF_T0; tc::mbar_wait(&p_empty[pb], (round - 1) & 1u); PROF_ADD(0); }
+          uint8_t* pa = patch0 + (size_t)pb * 2u * PATCH_PLANE;
+          if (tc::elect_one()) {
+            tc::mbar_expect_tx(&p_full[pb], 2u * (uint32_t)(18 * PW * 64));
+            tc::tma_load_4d(pa, &prm.maps[2 * s], cb * 32, x0, y0, b, &p_full[pb]);
+            tc::tma_load_4d(pa + PATCH_PLANE, &prm.maps[2 * s + 1], cb * 32, x0, y0, b, &p_full[pb]);
+          }
+          __syncwarp();
+          for (int tap = 0; tap < ks * ks; ++tap, ++bit) {
+            const uint32_t st = bit % S, r2 = bit / S;
+            if (r2 > 0) { PROF_T0; tc::mbar_wait(&b_empty[st], (r2 - 1) & 1u); PROF_ADD(1); }
+            if (tc::elect_one()) {
+              tc::mbar_expect_tx(&b_full[st], B_BYTES);
+              tc::bulk_load(bring + (size_t)st * B_BYTES,
+                            wbase + (size_t)(prm.seg_chunk0[s] + tap * cblocks + cb) * B_BYTES, B_BYTES, &b_full[st]);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (whole warp loops, one elected lane issues) ============
+    constexpr uint32_t IDESC_MERGED = tc::idesc_bf16_f32(128, 2 * NT);
+    constexpr uint32_t IDESC_HI = tc::idesc_bf16_f32(128, NT);
+    constexpr uint32_t SBO = PW * 64u;
+    uint32_t pit = 0, bit = 0, tile_i = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
+      const uint32_t a = tile_i & 1u, use = tile_i >> 1;
+      if (use > 0) { PROF_T0; tc::mbar_wait(&acc_empty[a], (use - 1) & 1u); PROF_ADD(2); }
+      tc::fence_after_sync();
+      const uint32_t acc = tmem + a * ACC_COLS;
+      uint32_t first = 1;
+      for (int s = 0; s < prm.nseg; ++s) {
+        const int ks = prm.seg_ksize[s], C = prm.seg_C[s];
+        const int cblocks = (C + 31) >> 5;
+        for (int cb = 0; cb < cblocks; ++cb, ++pit) {
+          const uint32_t pb = pit & 1u;
+          { PROF_T0; tc::mbar_wait(&p_full[pb], (pit >> 1) & 1u); PROF_ADD(3); }
+          tc::fence_after_sync();
+          const uint32_t pa = tc::smem_u32(patch0 + (size_t)pb * 2u * PATCH_PLANE);
+          const int ksteps = (min(32, C - cb * 32) + 15) >> 4;
+          for (int tap = 0; tap < ks * ks; ++tap, ++bit) {
+            const uint32_t st = bit % S;
+            { PROF_T0; tc::mbar_wait(&b_full[st], (bit / S) & 1u); PROF_ADD(4); }
+            tc::fence_after_sync();
+            const uint32_t sb = tc::smem_u32(bring + (size_t)st * B_BYTES);
+            const int dy = (ks == 3) ? tap / 3 : 1, dx = (ks == 3) ? tap % 3 : 1;
+            const uint32_t row0 = (uint32_t)(dy * PW + dx) * 64u;
+            if (tc::elect_one()) {
+              const uint64_t b_m = tc::smem_desc_sw64(sb);
+#pragma unroll
+              for (int sub = 0; sub < SUB; ++sub) {  // sub-tile 1 sits 8 pixel records = 512 B to the right
+                const uint64_t a_hi = tc::smem_desc_sw64(pa + row0 + sub * 512u, SBO);
+                const uint64_t a_lo = a_hi + (PATCH_PLANE >> 4);
+                const uint32_t d = acc + sub * 2 * NT;
+                // hi*hi -> columns [0,NT), hi*lo -> columns [NT,2NT): one N = 2*NT instruction per k-step
+                tc::mma_ss(d, a_hi, b_m, IDESC_MERGED, first ? 0u : 1u);
+                if (ksteps > 1) tc::mma_ss(d, a_hi + 2, b_m + 2, IDESC_MERGED, 1u);
+                // lo*hi -> columns [0,NT)
+                tc::mma_ss(d, a_lo, b_m, IDESC_HI, 1u);
+                if (ksteps > 1) tc::mma_ss(d, a_lo + 2, b_m + 2, IDESC_HI, 1u);
+              }
+              tc::mma_commit(&b_empty[st]);
+            }
+            __syncwarp();
+            first = 0;
+          }
+          if (tc::elect_one()) tc::mma_commit(&p_empty[pb]);
+          __syncwarp();
+        }
+      }
+      if (tc::elect_one()) tc::mma_commit(&acc_full[a]);
+      __syncwarp();
+    }
+  } else {
+    // =========================== epilogue (warps 2..9) ===========================
+    const int et = tid - 64;                  // 0..255
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may touch
+    const int half = (warp - 2) >> 2;         // column half handled by this warp
+    const int row = quarter * 32 + lane;      // row of the M=128 sub-tile = TMEM lane
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const bool leader = (et == 0);
+    const bool has_res = prm.has_res != 0;
+    constexpr int COLS = NT / 2;              // columns per thread: 32 (NT = 64) or 64 (NT = 128)
+    const uint32_t swz = (uint32_t)(row & 7);
+    uint32_t tile_i = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
+      const int nt = item % prm.n_ntiles;
+      const int mt = item / prm.n_ntiles;
+      const int tx = mt % prm.tiles_x;
+      const int ty = (mt / prm.tiles_x) % prm.tiles_y;
+      const int b = mt / (prm.tiles_x * prm.tiles_y);
+      const uint32_t a = tile_i & 1u;
+      // ---- staging buffers free again?  then fetch the residual tiles while the main loop still runs ----
+      if (leader) {
+        tc::tma_store_wait_read<0>();
+        if (has_res) {
+#pragma unroll
+          for (int sub = 0; sub < SUB; ++sub) {
+            tc::mbar_expect_tx(&res_full[sub], STAGING);
+            uint8_t* sg = staging + sub * STAGING;
+#pragma unroll
+            for (int part = 0; part < 2; ++part)
+#pragma unroll
+              for (int blk = 0; blk < NTC; ++blk)
+                tc::tma_load_4d(sg + (part * NTC + blk) * STAGE_BLK, &prm.res_maps[part], nt * NT + blk * 64,
+                                tx * 8 * SUB + sub * 8, ty * CVH_ROWS, b, &res_full[sub]);
+          }
+        }
+      }
+      tc::named_sync(1, CVH_EPI_THREADS);
+      { PROF_T0; tc::mbar_wait(&acc_full[a], (tile_i >> 1) & 1u); PROF_ADD(5); }
+      tc::fence_after_sync();
+      const long long ep0 = prm.prof ? clock64() : 0;
+      const float* bias_t = bias_s + nt * NT + half * COLS;
+#pragma unroll
+      for (int sub = 0; sub < SUB; ++sub) {
+        uint8_t* sg = staging + sub * STAGING;
+        if (has_res) tc::mbar_wait(&res_full[sub], tile_i & 1u);
+        const uint32_t t_main = tmem + lane_base + a * ACC_COLS + sub * 2 * NT + half * COLS;
+#pragma unroll
+        for (int c0 = 0; c0 < COLS; c0 += 32) {
+          uint32_t rm[32], rc[32];
+          tc::tmem_ld32(t_main + c0, rm);
+          tc::tmem_ld32(t_main + NT + c0, rc);
+          tc::wait_ld();
+          // this thread's 32 channels = 4 chunks of 16 B in the row's 128-byte record of column block `blk`
+          const int col = half * COLS + c0;  // first channel within the N tile
+          const int blk = col >> 6;
+          const int chunk0 = (col & 63) >> 3;
+          uint8_t* row_hi = sg + blk * STAGE_BLK + row * 128;
+          uint8_t* row_lo = sg + (NTC + blk) * STAGE_BLK + row * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t off = ((uint32_t)(chunk0 + q) ^ swz) << 4;
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_t + c0 + 8 * q);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_t + c0 + 8 * q + 4);
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              v[j] = (__uint_as_float(rm[8 * q + j]) + __uint_as_float(rc[8 * q + j])) + bv[j];
+            if (has_res) {
+              const uint4 h4 = *reinterpret_cast<const uint4*>(row_hi + off);
+              const uint4 l4 = *reinterpret_cast<const uint4*>(row_lo + off);
+              const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+                v[2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+              }
+            }
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              tc::split2(apply_act(v[2 * e], prm.act, prm.slope), apply_act(v[2 * e + 1], prm.act, prm.slope), hi[e],
+                         lo[e]);
+            *reinterpret_cast<uint4*>(row_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(row_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+      }
+      // accumulator drained: hand it back to the MMA warp; staging written: publish to the async proxy
+      tc::fence_before_sync();
+      tc::mbar_arrive(&acc_empty[a]);
+      tc::fence_async_smem();
+      tc::named_sync(1, CVH_EPI_THREADS);
+      if (leader) {
+#pragma unroll
+        for (int sub = 0; sub < SUB; ++sub)
+#pragma unroll
+          for (int part = 0; part < 2; ++part)
+#pragma unroll
+            for (int blk = 0; blk < NTC; ++blk)
+              tc::tma_store_4d(&prm.out_maps[part], staging + sub * STAGING + (part * NTC + blk) * STAGE_BLK,
+                               nt * NT + blk * 64, tx * 8 * SUB + sub * 8, ty * CVH_ROWS, b);
+        tc::tma_store_commit();
+      }
+      if (prm.prof) prof_acc[6] += clock64() - ep0;
+    }
+    if (leader) tc::tma_store_wait_all<0>();
+  }
+  if (prm.prof && lane == 0 && (warp <= 2)) {
+    long long* o = prm.prof + (size_t)blockIdx.x * 8;
+    if (warp == 0) { o[0] = prof_acc[0]; o[1] = prof_acc[1]; }
+    if (warp == 1) { o[2] = prof_acc[2]; o[3] = prof_acc[3]; o[4] = prof_acc[4]; o[7] = clock64() - k_t0; }
+    if (warp == 2) { o[5] = prof_acc[5]; o[6] = prof_acc[6]; }
+  }
+#undef PROF_T0
+#undef PROF_ADD
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+// shared-memory footprint of the halo kernel for (SUB, NT, stages, n_ntiles)
+static inline size_t conv_halo_smem(int sub, int NT, int stages, int n_ntiles) {
+  const size_t patch_plane = ((size_t)18 * (8 * sub + 2) * 64 + 1023) & ~(size_t)1023;
+  const size_t staging = (size_t)sub * 2 * (NT / 64) * 16384;
+  return 1024 + 4 * patch_plane + staging + (size_t)stages * NT * 128 + (size_t)n_ntiles * NT * 4 +
+         (10 + 2 * stages) * 8 + 16;
+}

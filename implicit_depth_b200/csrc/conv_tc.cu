@@ -7,13 +7,15 @@
 //   networks_fast.py:42-43) and the BasicBlock shortcut conv (layers.py:64-71, 89-92) are just extra
 //   segments accumulating into the same TMEM tile -- nothing is concatenated or added in memory.
 // * Activations are stored as two bf16 planes (hi, lo) with x = hi + lo (16 mantissa bits, same bytes as
-//   fp32); weights are pre-split the same way.  Each 64-channel K-chunk issues hi*hi, hi*lo, lo*hi MMAs
-//   into one fp32 accumulator: fp32-grade results (the CPU-oracle parity bar) at bf16 MMA rates.
-// * Warp-specialised, persistent: warp 0 = TMA producer (4-D tiled loads of a 8x16-pixel x 64-channel
-//   box per tap: zero padding and channel tails come from TMA out-of-bounds fill, stride-2 from the
-//   tensor map's element strides; weights by 1-D bulk copies of pre-swizzled tiles), warp 1 = MMA
-//   issuer, warps 2-5 = epilogue (TMEM -> registers -> bias/activation/residual -> split -> NHWC).
-//   TMEM holds two accumulator tiles so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   fp32); weights are pre-split the same way.  Each K-chunk issues hi*hi, hi*lo, lo*hi MMAs into fp32
+//   accumulators: fp32-grade results (the CPU-oracle parity bar) at bf16 MMA rates.
+// * Two kernels behind one plan API:
+//     conv_halo_kernel (conv_halo.cuh)  stride-1 convs with Cout % 64 == 0 -- 141 of the 147 conv launches of a
+//                                        forward: halo patches, merged-N MMAs, TMA-store epilogue;
+//     conv_tc_kernel (below)            everything else (stride 2, Cout = 16): one TMA box per tap, 64-channel
+//                                        chunks, 128-byte swizzle, direct-store epilogue.
+//   Both are warp-specialised and persistent: warp 0 = TMA producer, warp 1 = MMA issuer, remaining warps =
+//   epilogue; two TMEM accumulator sets so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -32,29 +34,28 @@ enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_ELU = 2, ACT_RELU = 3 };
 
 struct ConvKParams {
   CUtensorMap maps[2 * CV_MAX_SEG];  // [2s] = hi plane, [2s+1] = lo plane of segment s
+  CUtensorMap out_maps[2];           // halo kernel: output hi / lo (TMA stores)
+  CUtensorMap res_maps[2];           // halo kernel: residual hi / lo (TMA loads into the staging tiles)
   int seg_C[CV_MAX_SEG], seg_ksize[CV_MAX_SEG], seg_stride[CV_MAX_SEG], seg_pad[CV_MAX_SEG];
   int nseg;
-  const uint8_t* wimage;  // [n_ntiles][total_chunks][hi NT x 64 | lo NT x 64] bf16, SW128 tiles
+  const uint8_t* wimage;  // packed weights, layout depends on the kernel (see b200_conv_uses_halo)
   const float* bias;      // [Cout] or null
   const __nv_bfloat16* res_hi;  // optional residual, NHWC [B,OH,OW,Cout]
   const __nv_bfloat16* res_lo;
   __nv_bfloat16* out_hi;  // NHWC [B,OH,OW,Cout] (may be null if only out_f32 is wanted)
   __nv_bfloat16* out_lo;
-  float* out_f32;         // optional NHWC fp32 copy
+  float* out_f32;         // optional NHWC fp32 copy (plain kernel only)
   int B, OH, OW, Cout, NT, n_ntiles, act, total_chunks, tiles_x, tiles_y, stages;
   float slope;
-  // halo mode (all segments stride 1): one (16+2*?) x (8*sub+2) pixel patch per 64-channel block is loaded
-  // once and every tap reads it through a shifted UMMA descriptor
-  int halo, sub, pw, patch_bytes;  // sub = 8-pixel-wide sub-tiles per item (1|2); pw = patch width in pixels
-  int seg_chunk0[CV_MAX_SEG];      // index of each segment's first chunk in the weight image
-  int debug;                       // dev only (B200_CONV_DEBUG): bit 0 = skip MMAs, bit 1 = skip TMA loads
-  long long* prof;                 // dev only: per-CTA role timings [grid][8] (clock64 ticks) or null
+  int halo, sub, has_res;
+  int seg_chunk0[CV_MAX_SEG];  // index of each segment's first chunk in the weight image
+  long long* prof;             // dev only: per-CTA role timings [grid][8] (clock64 ticks) or null
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   if (act == ACT_LRELU) return v >= 0.f ? v : v * slope;
   if (act == ACT_RELU) return fmaxf(v, 0.f);
-  if (act == ACT_ELU) return v > 0.f ? v : expm1f(v);
+  if (act == ACT_ELU) return elu1(v);
   return v;
 }
 
@@ -119,14 +120,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
               if (round > 0) tc::mbar_wait(&empty[stage], (round - 1) & 1u);
               uint8_t* sa = base + (size_t)stage * stage_bytes;
               if (tc::elect_one()) {
-                if (prm.debug & 2) {
-                  tc::mbar_arrive(&full[stage]);
-                } else {
-                  tc::mbar_expect_tx(&full[stage], 32768u + b_bytes);
-                  tc::tma_load_4d(sa, &prm.maps[2 * s], cb * 64, x0, y0, b, &full[stage]);
-                  tc::tma_load_4d(sa + 16384, &prm.maps[2 * s + 1], cb * 64, x0, y0, b, &full[stage]);
-                  tc::bulk_load(sa + 32768, wsrc, b_bytes, &full[stage]);
-                }
+                tc::mbar_expect_tx(&full[stage], 32768u + b_bytes);
+                tc::tma_load_4d(sa, &prm.maps[2 * s], cb * 64, x0, y0, b, &full[stage]);
+                tc::tma_load_4d(sa + 16384, &prm.maps[2 * s + 1], cb * 64, x0, y0, b, &full[stage]);
+                tc::bulk_load(sa + 32768, wsrc, b_bytes, &full[stage]);
               }
               __syncwarp();
               wsrc += b_bytes;
@@ -161,9 +158,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
               const int ksteps = (min(64, C - cb * 64) + 15) >> 4;
               if (tc::elect_one()) {
                 const uint64_t a_hi = tc::smem_desc_sw128(sa), b_hi = tc::smem_desc_sw128(sb);
-                if (!(prm.debug & 1))
-                  tc::mma_split_ss_n(ksteps, acc, a_hi, a_hi + (16384u >> 4), b_hi, b_hi + (((uint32_t)NT * 128u) >> 4),
-                                     idesc, first);
+                tc::mma_split_ss_n(ksteps, acc, a_hi, a_hi + (16384u >> 4), b_hi, b_hi + (((uint32_t)NT * 128u) >> 4),
+                                   idesc, first);
                 tc::mma_commit(&empty[stage]);
               }
               __syncwarp();
@@ -247,239 +243,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// Halo variant for stride-1 convs (3x3 and 1x1 segments).  The plain kernel above re-fetches every input
-// pixel once per tap (9x) and every weight chunk once per 128 pixels: at N = 64 that is ~2 GB through L2
-// for the 192->64 layers, i.e. L2-bandwidth bound (profiles/r01_*).  Here an item is 16 rows x (8*sub)
-// columns of output pixels (M = 128*sub); for each 64-channel block ONE TMA box of 18 x (8*sub+2) pixels
-// lands in shared memory and the 9 taps are 9 UMMA descriptors into it: start address shifted by
-// (dy*pw + dx) rows, 8-row-group stride pw*128 B (one tile row = one 8-row group).  Each weight chunk is
-// used for sub M=128 tiles.  A traffic drops ~6x, B traffic 2x.
-// ------------------------------------------------------------------------------------------------
-#define CVH_ROWS 16
 
-__global__ void __launch_bounds__(CV_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvKParams prm) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int NT = prm.NT, SUB = prm.sub, PW = prm.pw;
-  const uint32_t b_bytes = (uint32_t)NT * 256u;
-  const uint32_t b_stage = (b_bytes + 1023u) & ~1023u;
-  const uint32_t patch_plane = (uint32_t)prm.patch_bytes;  // one bf16 plane of a patch, 1024-aligned
-  const int S = prm.stages;
-  uint8_t* patch0 = base;                                   // 2 patch buffers x (hi, lo)
-  uint8_t* bring = base + 4u * patch_plane;                 // S weight stages
-  uint64_t* p_full = reinterpret_cast<uint64_t*>(bring + (size_t)S * b_stage);
-  uint64_t* p_empty = p_full + 2;
-  uint64_t* b_full = p_empty + 2;
-  uint64_t* b_empty = b_full + S;
-  uint64_t* acc_full = b_empty + S;
-  uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_t0 = 0;
-  const long long k_t0 = clock64();
-#define PROF_T0 if (prm.prof) prof_t0 = clock64()
-#define PROF_ADD(i) if (prm.prof) prof_acc[i] += clock64() - prof_t0
-  const int items = prm.B * prm.tiles_y * prm.tiles_x * prm.n_ntiles;
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * SUB * NT) tmem_cols <<= 1;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < 2 * prm.nseg; ++s) tc::prefetch_tmap(&prm.maps[s]);
-    for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&p_full[i], 1);
-      tc::mbar_init(&p_empty[i], 1);
-      tc::mbar_init(&acc_full[i], 1);
-      tc::mbar_init(&acc_empty[i], 128);
-    }
-    for (int s = 0; s < S; ++s) {
-      tc::mbar_init(&b_full[s], 1);
-      tc::mbar_init(&b_empty[s], 1);
-    }
-    tc::mbar_fence_init();
-  }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, tmem_cols);
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 0) {
-    {
-      // =========================== TMA producer (whole warp loops, one elected lane issues) ===========
-      uint32_t pit = 0, bit = 0;  // patch / weight-chunk counters
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int nt = item % prm.n_ntiles;
-        const int mt = item / prm.n_ntiles;
-        const int tx = mt % prm.tiles_x;
-        const int ty = (mt / prm.tiles_x) % prm.tiles_y;
-        const int b = mt / (prm.tiles_x * prm.tiles_y);
-        const uint8_t* wbase = prm.wimage + (size_t)nt * prm.total_chunks * b_bytes;
-        for (int s = 0; s < prm.nseg; ++s) {
-          const int ks = prm.seg_ksize[s], pd = prm.seg_pad[s];
-          const int cblocks = (prm.seg_C[s] + 63) >> 6;
-          // a 1x1 segment reads the centre of the same kind of patch: origin shifted by (1 - pad)
-          const int org = (ks == 3) ? -pd : -(pd + 1);
-          const int x0 = tx * 8 * SUB + org, y0 = ty * CVH_ROWS + org;
-          for (int cb = 0; cb < cblocks; ++cb, ++pit) {
-            const uint32_t pb = pit & 1u, round = pit >> 1;
-            if (round > 0) { PROF_T0; tc::mbar_wait(&p_empty[pb], (round - 1) & 1u); PROF_ADD(0); }
-            uint8_t* pa = patch0 + (size_t)pb * 2u * patch_plane;
-            if (tc::elect_one()) {
-              if (prm.debug & 2) {
-                tc::mbar_arrive(&p_full[pb]);
-              } else {
-                tc::mbar_expect_tx(&p_full[pb], 2u * (uint32_t)(18 * PW * 128));
-                tc::tma_load_4d(pa, &prm.maps[2 * s], cb * 64, x0, y0, b, &p_full[pb]);
-                tc::tma_load_4d(pa + patch_plane, &prm.maps[2 * s + 1], cb * 64, x0, y0, b, &p_full[pb]);
-              }
-            }
-            __syncwarp();
-            for (int tap = 0; tap < ks * ks; ++tap, ++bit) {
-              const uint32_t st = bit % S, r2 = bit / S;
-              if (r2 > 0) { PROF_T0; tc::mbar_wait(&b_empty[st], (r2 - 1) & 1u); PROF_ADD(1); }
-              if (tc::elect_one()) {
-                if (prm.debug & 2) {
-                  tc::mbar_arrive(&b_full[st]);
-                } else {
-                  tc::mbar_expect_tx(&b_full[st], b_bytes);
-                  tc::bulk_load(bring + (size_t)st * b_stage,
-                                wbase + (size_t)(prm.seg_chunk0[s] + tap * cblocks + cb) * b_bytes, b_bytes, &b_full[st]);
-                }
-              }
-              __syncwarp();
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    {
-      // =========================== MMA issuer (whole warp loops, one elected lane issues) ============
-      const uint32_t idesc = tc::idesc_bf16_f32(128, NT);
-      const uint32_t sbo = (uint32_t)PW * 128u;
-      uint32_t pit = 0, bit = 0, tile_i = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
-        const uint32_t a = tile_i & 1u, use = tile_i >> 1;
-        if (use > 0) { PROF_T0; tc::mbar_wait(&acc_empty[a], (use - 1) & 1u); PROF_ADD(2); }
-        tc::fence_after_sync();
-        const uint32_t acc = tmem + a * SUB * NT;
-        uint32_t first = 1;
-        for (int s = 0; s < prm.nseg; ++s) {
-          const int ks = prm.seg_ksize[s], C = prm.seg_C[s];
-          const int cblocks = (C + 63) >> 6;
-          for (int cb = 0; cb < cblocks; ++cb, ++pit) {
-            const uint32_t pb = pit & 1u;
-            { PROF_T0; tc::mbar_wait(&p_full[pb], (pit >> 1) & 1u); PROF_ADD(3); }
-            tc::fence_after_sync();
-            const uint32_t pa = tc::smem_u32(patch0 + (size_t)pb * 2u * patch_plane);
-            const int ksteps = (min(64, C - cb * 64) + 15) >> 4;
-            for (int tap = 0; tap < ks * ks; ++tap, ++bit) {
-              const uint32_t st = bit % S;
-              { PROF_T0; tc::mbar_wait(&b_full[st], (bit / S) & 1u); PROF_ADD(4); }
-              tc::fence_after_sync();
-              const uint32_t sb = tc::smem_u32(bring + (size_t)st * b_stage);
-              const int dy = (ks == 3) ? tap / 3 : 1, dx = (ks == 3) ? tap % 3 : 1;
-              const uint32_t row0 = (uint32_t)(dy * PW + dx) * 128u;
-              if (tc::elect_one()) {
-                const uint64_t a_hi = tc::smem_desc_sw128(pa + row0, sbo), b_hi = tc::smem_desc_sw128(sb);
-                const uint64_t a_lo = a_hi + (patch_plane >> 4), b_lo = b_hi + (((uint32_t)NT * 128u) >> 4);
-                for (int sub = 0; sub < SUB && !(prm.debug & 1); ++sub)  // sub-tile 1 sits 8 pixels = 1024 B to the right
-                  tc::mma_split_ss_n(ksteps, acc + sub * NT, a_hi + sub * 64, a_lo + sub * 64, b_hi, b_lo, idesc, first);
-                tc::mma_commit(&b_empty[st]);
-              }
-              __syncwarp();
-              first = 0;
-            }
-            if (tc::elect_one()) tc::mma_commit(&p_empty[pb]);
-            __syncwarp();
-          }
-        }
-        if (tc::elect_one()) tc::mma_commit(&acc_full[a]);
-        __syncwarp();
-      }
-    }
-  } else {
-    // =========================== epilogue (warps 2..5) ===========================
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    uint32_t tile_i = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
-      const int nt = item % prm.n_ntiles;
-      const int mt = item / prm.n_ntiles;
-      const int tx = mt % prm.tiles_x;
-      const int ty = (mt / prm.tiles_x) % prm.tiles_y;
-      const int b = mt / (prm.tiles_x * prm.tiles_y);
-      const uint32_t a = tile_i & 1u;
-      { PROF_T0; tc::mbar_wait(&acc_full[a], (tile_i >> 1) & 1u); PROF_ADD(5); }
-      tc::fence_after_sync();
-      const long long ep0 = prm.prof ? clock64() : 0;
-      const int n_base = nt * NT;
-      for (int sub = 0; sub < SUB; ++sub) {
-        const int oy = ty * CVH_ROWS + (row >> 3), ox = tx * 8 * SUB + sub * 8 + (row & 7);
-        const bool live = (oy < prm.OH) && (ox < prm.OW);
-        const size_t pix = ((size_t)b * prm.OH + oy) * prm.OW + ox;
-        for (int n0 = 0; n0 < NT; n0 += 16) {
-          uint32_t r[16];
-          tc::tmem_ld16(tmem + lane_base + (a * SUB + sub) * NT + n0, r);
-          tc::wait_ld();
-          if (live) {
-            const int n = n_base + n0;
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (prm.bias ? __ldg(prm.bias + n + j) : 0.f);
-            if (prm.res_hi) {
-              const uint4* rh = reinterpret_cast<const uint4*>(prm.res_hi + pix * prm.Cout + n);
-              const uint4* rl = reinterpret_cast<const uint4*>(prm.res_lo + pix * prm.Cout + n);
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const uint4 h4 = __ldg(rh + q), l4 = __ldg(rl + q);
-                const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  v[8 * q + 2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
-                  v[8 * q + 2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], prm.act, prm.slope);
-            if (prm.out_hi) {
-              uint32_t hi[8], lo[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) tc::split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-              uint4* oh = reinterpret_cast<uint4*>(prm.out_hi + pix * prm.Cout + n);
-              uint4* ol = reinterpret_cast<uint4*>(prm.out_lo + pix * prm.Cout + n);
-              oh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              oh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-              ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-            }
-            if (prm.out_f32) {
-              float4* of = reinterpret_cast<float4*>(prm.out_f32 + pix * prm.Cout + n);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) of[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
-          }
-        }
-      }
-      tc::fence_before_sync();
-      tc::mbar_arrive(&acc_empty[a]);
-      if (prm.prof) prof_acc[6] += clock64() - ep0;
-    }
-  }
-  if (prm.prof && lane == 0 && (warp <= 2)) {
-    long long* o = prm.prof + (size_t)blockIdx.x * 8;
-    if (warp == 0) { o[0] = prof_acc[0]; o[1] = prof_acc[1]; }
-    if (warp == 1) { o[2] = prof_acc[2]; o[3] = prof_acc[3]; o[4] = prof_acc[4]; o[7] = clock64() - k_t0; }
-    if (warp == 2) { o[5] = prof_acc[5]; o[6] = prof_acc[6]; }
-  }
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem, tmem_cols);
-}
+#include "conv_halo.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side: plan objects (tensor maps are encoded once, launches are cheap and graph-capturable)
@@ -512,11 +277,35 @@ struct b200_conv_desc {
 
 extern "C" int b200_conv_ntile(int Cout) { return Cout <= 128 ? Cout : 128; }
 
-extern "C" long long b200_conv_wimage_bytes(const int* seg_C, const int* seg_ksize, int nseg, int Cout) {
+// 1 if this conv runs on the halo kernel (weight image in 32-channel chunks, 64-byte swizzle, [hi | lo] per
+// chunk), 0 for the plain kernel (64-channel chunks, 128-byte swizzle).  Pure function of the geometry.
+extern "C" int b200_conv_uses_halo(const b200_conv_desc* d) {
+  if (!d || getenv("B200_CONV_NO_HALO") != nullptr) return 0;
+  if (d->Cout % 64 != 0 || d->out_f32 != nullptr || d->out_hi == nullptr) return 0;
+  for (int s = 0; s < d->nseg; ++s) {
+    const b200_conv_seg& sg = d->seg[s];
+    const bool ok = sg.stride == 1 && ((sg.ksize == 3 && (sg.pad == 0 || sg.pad == 1)) || (sg.ksize == 1 && sg.pad == 0));
+    if (!ok) return 0;
+  }
+  return 1;
+}
+
+extern "C" long long b200_conv_wimage_bytes(const int* seg_C, const int* seg_ksize, int nseg, int Cout, int halo) {
   long long chunks = 0;
-  for (int s = 0; s < nseg; ++s) chunks += (long long)seg_ksize[s] * seg_ksize[s] * ((seg_C[s] + 63) / 64);
+  const int cw = halo ? 32 : 64;
+  for (int s = 0; s < nseg; ++s) chunks += (long long)seg_ksize[s] * seg_ksize[s] * ((seg_C[s] + cw - 1) / cw);
   const int NT = b200_conv_ntile(Cout);
-  return chunks * ((Cout + NT - 1) / NT) * NT * 256;
+  return chunks * ((Cout + NT - 1) / NT) * NT * (halo ? 128 : 256);
+}
+
+static int encode_nhwc(EncodeTiledFn enc, CUtensorMap* map, const void* ptr, int C, int W, int H, int B,
+                       const cuuint32_t box[4], int estride, CUtensorMapSwizzle swz) {
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+  return (int)enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
 extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
@@ -527,6 +316,7 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
                  d->Cout);
   B200_CHECK_ARG(d->wimage && (d->out_hi || d->out_f32), "conv_create: missing weights or output");
   B200_CHECK_ARG((d->out_hi == nullptr) == (d->out_lo == nullptr), "conv_create: out_hi/out_lo must come together");
+  B200_CHECK_ARG((d->res_hi == nullptr) == (d->res_lo == nullptr), "conv_create: res_hi/res_lo must come together");
   EncodeTiledFn enc = get_encode();
   B200_CHECK_ARG(enc != nullptr, "conv_create: cuTensorMapEncodeTiled not available from the driver");
   ConvPlan* p = new ConvPlan();
@@ -539,21 +329,15 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   k.NT = b200_conv_ntile(d->Cout);
   k.n_ntiles = (d->Cout + k.NT - 1) / k.NT;
-  // halo mode: every segment stride 1 and either 3x3 (pad 0|1) or 1x1 (pad 0)
-  bool halo = getenv("B200_CONV_NO_HALO") == nullptr;
-  for (int s = 0; s < d->nseg && halo; ++s) {
-    const b200_conv_seg& sg = d->seg[s];
-    halo = sg.stride == 1 && ((sg.ksize == 3 && (sg.pad == 0 || sg.pad == 1)) || (sg.ksize == 1 && sg.pad == 0));
-  }
+  const bool halo = b200_conv_uses_halo(d) != 0;
   k.halo = halo ? 1 : 0;
-  k.debug = getenv("B200_CONV_DEBUG") ? atoi(getenv("B200_CONV_DEBUG")) : 0;
   k.sub = 1;
   if (halo) {
-    k.sub = (k.NT <= 64) ? 2 : 1;
+    // two M=128 sub-tiles per item share every weight chunk when the N tile is 64 wide and there is enough work
+    k.sub = (k.NT == 64) ? 2 : 1;
     if (k.sub == 2 && d->B * ((d->OW + 15) / 16) * ((d->OH + CVH_ROWS - 1) / CVH_ROWS) * k.n_ntiles < n_sm) k.sub = 1;
-    k.pw = 8 * k.sub + 2;
-    k.patch_bytes = (18 * k.pw * 128 + 1023) & ~1023;
   }
+  const int cw = halo ? 32 : 64;  // channels per K chunk
   for (int s = 0; s < d->nseg; ++s) {
     const b200_conv_seg& sg = d->seg[s];
     if (!(sg.in_hi && sg.in_lo) || sg.C % 8 != 0 || sg.C < 8 || !(sg.ksize == 1 || sg.ksize == 3) ||
@@ -575,24 +359,35 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
     k.seg_stride[s] = sg.stride;
     k.seg_pad[s] = sg.pad;
     k.seg_chunk0[s] = k.total_chunks;
-    k.total_chunks += sg.ksize * sg.ksize * ((sg.C + 63) / 64);
-    cuuint64_t gdim[4] = {(cuuint64_t)sg.C, (cuuint64_t)sg.W, (cuuint64_t)sg.H, (cuuint64_t)d->B};
-    cuuint64_t gstr[3] = {(cuuint64_t)sg.C * 2, (cuuint64_t)sg.W * sg.C * 2, (cuuint64_t)sg.H * sg.W * sg.C * 2};
+    k.total_chunks += sg.ksize * sg.ksize * ((sg.C + cw - 1) / cw);
     cuuint32_t box[4] = {64, (cuuint32_t)(CV_TW * sg.stride), (cuuint32_t)(CV_TH * sg.stride), 1};
     if (halo) {
-      box[1] = (cuuint32_t)k.pw;
+      box[0] = 32;
+      box[1] = (cuuint32_t)(8 * k.sub + 2);
       box[2] = 18;
     }
-    cuuint32_t estr[4] = {1, (cuuint32_t)sg.stride, (cuuint32_t)sg.stride, 1};
     for (int part = 0; part < 2; ++part) {
-      CUresult r = enc(&k.maps[2 * s + part], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
-                       const_cast<void*>(part ? sg.in_lo : sg.in_hi), gdim, gstr, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) {
+      const int r = encode_nhwc(enc, &k.maps[2 * s + part], part ? sg.in_lo : sg.in_hi, sg.C, sg.W, sg.H, d->B, box,
+                                sg.stride, halo ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+      if (r != 0) {
         delete p;
-        b200_set_error("conv_create: cuTensorMapEncodeTiled failed (%d) for segment %d (C=%d H=%d W=%d stride=%d)",
-                       (int)r, s, sg.C, sg.H, sg.W, sg.stride);
+        b200_set_error("conv_create: cuTensorMapEncodeTiled failed (%d) for segment %d (C=%d H=%d W=%d stride=%d)", r, s,
+                       sg.C, sg.H, sg.W, sg.stride);
+        return -2;
+      }
+    }
+  }
+  if (halo) {
+    const cuuint32_t obox[4] = {64, 8, CVH_ROWS, 1};
+    for (int part = 0; part < 2; ++part) {
+      int r = encode_nhwc(enc, &k.out_maps[part], part ? d->out_lo : d->out_hi, d->Cout, d->OW, d->OH, d->B, obox, 1,
+                          CU_TENSOR_MAP_SWIZZLE_128B);
+      if (r == 0 && d->res_hi)
+        r = encode_nhwc(enc, &k.res_maps[part], part ? d->res_lo : d->res_hi, d->Cout, d->OW, d->OH, d->B, obox, 1,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+      if (r != 0) {
+        delete p;
+        b200_set_error("conv_create: cuTensorMapEncodeTiled failed (%d) for the output / residual map", r);
         return -2;
       }
     }
@@ -601,6 +396,7 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   k.bias = d->bias;
   k.res_hi = (const __nv_bfloat16*)d->res_hi;
   k.res_lo = (const __nv_bfloat16*)d->res_lo;
+  k.has_res = d->res_hi != nullptr;
   k.out_hi = (__nv_bfloat16*)d->out_hi;
   k.out_lo = (__nv_bfloat16*)d->out_lo;
   k.out_f32 = d->out_f32;
@@ -613,12 +409,10 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   if (halo) {
     k.tiles_x = (d->OW + 8 * k.sub - 1) / (8 * k.sub);
     k.tiles_y = (d->OH + CVH_ROWS - 1) / CVH_ROWS;
-    const size_t b_stage = ((size_t)k.NT * 256 + 1023) & ~(size_t)1023;
-    const size_t fixed = 1024 + 4 * (size_t)k.patch_bytes + 256;
-    int S = (int)((227 * 1024 - fixed) / b_stage);
-    if (S > 6) S = 6;
+    int S = 12;
+    while (S > 2 && conv_halo_smem(k.sub, k.NT, S, k.n_ntiles) > 227 * 1024) --S;
     k.stages = S;
-    p->smem = fixed + S * b_stage;
+    p->smem = conv_halo_smem(k.sub, k.NT, S, k.n_ntiles);
   } else {
     k.tiles_x = (d->OW + CV_TW - 1) / CV_TW;
     k.tiles_y = (d->OH + CV_TH - 1) / CV_TH;
@@ -635,7 +429,11 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(conv_halo_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_halo_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_halo_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       delete p;
       b200_set_error("conv_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -650,10 +448,15 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
 extern "C" int b200_conv_run(void* plan, void* stream) {
   B200_CHECK_ARG(plan, "conv_run: null plan");
   ConvPlan* p = (ConvPlan*)plan;
-  if (p->k.halo)
-    conv_halo_kernel<<<p->grid, CV_THREADS, p->smem, (cudaStream_t)stream>>>(p->k);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!p->k.halo)
+    conv_tc_kernel<<<p->grid, CV_THREADS, p->smem, st>>>(p->k);
+  else if (p->k.NT == 128)
+    conv_halo_kernel<1, 2><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
+  else if (p->k.sub == 2)
+    conv_halo_kernel<2, 1><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
   else
-    conv_tc_kernel<<<p->grid, CV_THREADS, p->smem, (cudaStream_t)stream>>>(p->k);
+    conv_halo_kernel<1, 1><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
   B200_CHECK_LAUNCH("conv_run");
   return 0;
 }

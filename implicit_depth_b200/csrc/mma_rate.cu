@@ -32,15 +32,31 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(long long* out, int N, in
       const uint64_t a_hi = tc::smem_desc_sw128(a), a_lo = tc::smem_desc_sw128(a + 16384u);
       const uint64_t b_hi = tc::smem_desc_sw128(b0), b_lo = tc::smem_desc_sw128(b0 + N * 128u);
       const uint32_t acc = tmem + ((mode & 4) ? (it & 1) * 256u : 0u);
-      if ((mode & 3) == 0) {
+      if ((mode & 24) == 0 && (mode & 3) == 0) {
         tc::mma_split_ss<4>(acc, a_hi, a_lo, b_hi, b_lo, idesc, it == 0);
-      } else if ((mode & 3) == 1) {  // A from TMEM columns 256.. (hi 32 cols | lo 32 cols)
+      } else if ((mode & 24) == 0 && (mode & 3) == 1) {  // A from TMEM columns 256.. (hi 32 cols | lo 32 cols)
         tc::mma_split_ts<4>(acc, tmem + 256 + 128, tmem + 256 + 160, b_hi, b_lo, idesc, it == 0);
-      } else if ((mode & 3) == 2) {  // SS, plain bf16: 12 k-steps hi*hi only over 3 chunks (no operand reuse)
+      } else if ((mode & 24) == 0 && (mode & 3) == 2) {  // SS, plain bf16: 12 k-steps hi*hi only over 3 chunks (no operand reuse)
 #pragma unroll
         for (int k = 0; k < 12; ++k)
           tc::mma_ss(acc, tc::smem_desc_sw128(a0 + ((it + k / 4) & 3) * 32768u) + 2 * (k & 3), b_hi + 2 * (k & 3), idesc,
                      (it == 0 && k == 0) ? 0u : 1u);
+      } else if (mode & 8) {  // SS, 64-byte swizzle, conv-halo pattern: per k-step A_hi x [B_hi|B_lo] (N) + A_lo x B_hi (N/2)
+        const uint32_t idh = tc::idesc_bf16_f32(128, N / 2);
+        const uint64_t a64 = tc::smem_desc_sw64(a + 11 * 64, 1152), a64l = tc::smem_desc_sw64(a + 16384u + 11 * 64, 1152);
+        const uint64_t b64 = tc::smem_desc_sw64(b0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          tc::mma_ss(acc, a64 + 2 * (k & 1), b64 + 2 * (k & 1), idesc, (it == 0 && k == 0) ? 0u : 1u);
+          tc::mma_ss(acc, a64l + 2 * (k & 1), b64 + 2 * (k & 1), idh, 1u);
+        }
+      } else if (mode & 16) {  // SS, 128-byte swizzle, same instruction mix as mode 8
+        const uint32_t idh = tc::idesc_bf16_f32(128, N / 2);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          tc::mma_ss(acc, a_hi + 2 * (k & 3), b_hi + 2 * (k & 3), idesc, (it == 0 && k == 0) ? 0u : 1u);
+          tc::mma_ss(acc, a_lo + 2 * (k & 3), b_hi + 2 * (k & 3), idh, 1u);
+        }
       } else {  // SS, the same A and B k-slice every time (best-case operand locality)
 #pragma unroll
         for (int k = 0; k < 12; ++k) tc::mma_ss(acc, a_hi, b_hi, idesc, (it == 0 && k == 0) ? 0u : 1u);

@@ -157,6 +157,16 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
 }
+// Same for the 64-byte-swizzled layout: rows are 64 B (32 bf16) apart, 8-row groups `sbo_bytes` apart (512 when
+// dense); the 16-byte chunk index of a row is XORed with address bits 7..8 (= (row >> 1) & 3 for a 512-aligned tile).
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t smem_addr, uint32_t sbo_bytes = 512) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
+         (4ull << 61);
+}
+// Byte offset of element (row, k) of a [rows x 32] bf16 K-major SW64 tile.
+__device__ __forceinline__ uint32_t sw64_offset(uint32_t row, uint32_t k) {
+  return row * 64u + ((((k >> 3) ^ ((row >> 1) & 3u)) << 4) | ((k & 7u) << 1));
+}
 // Byte offset of element (row, k) of a [rows x 64] bf16 K-major SW128 tile.
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t k) {
   return row * 128u + ((((k >> 3) ^ (row & 7u)) << 4) | ((k & 7u) << 1));

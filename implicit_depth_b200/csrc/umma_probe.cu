@@ -7,6 +7,9 @@
 //   mode 4: bf16 SS with the A rows taken from inside a larger swizzled "halo patch": M-tile row r lives
 //           at patch row (r/8)*10 + (r%8) + 11, i.e. descriptor start shifted by a non-multiple of 8 rows
 //           and an 8-row-group stride of 1280 B -- the addressing an implicit-GEMM conv tap needs
+//   mode 5: bf16 SS, 64-byte swizzle, K = 32: A rows inside a halo patch of 64-byte pixel records (patch row
+//           (r/8)*10 + (r%8) + 11, 8-row-group stride 640 B), B as a dense [N x 32] SW64 tile -- the layout of
+//           the 32-channel-block conv kernel
 // The GPU tests compare D against a host matmul, so a layout mistake shows up as a numeric error
 // in a 30-line kernel instead of inside the fused ones.
 #include "common.cuh"
@@ -33,6 +36,7 @@ umma_probe_kernel(const float* __restrict__ A, const float* __restrict__ Bm, flo
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool split = (mode == 2 || mode == 3);
   const bool halo = (mode == 4);
+
   const bool a_in_tmem = (mode == 1 || mode == 2);
 
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
@@ -45,6 +49,47 @@ umma_probe_kernel(const float* __restrict__ A, const float* __restrict__ Bm, flo
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  if (mode == 5) {
+    // ---- 64-byte-swizzle variant, self-contained ----
+    uint8_t* a64 = base;           // patch: up to 171 pixel rows x 64 B
+    uint8_t* b64 = base + 16384;   // [N x 32] bf16 SW64
+    for (int i = tid; i < 16384 / 4; i += 128) reinterpret_cast<uint32_t*>(a64)[i] = 0u;
+    __syncthreads();
+    for (int i = tid; i < N * 16; i += 128) {
+      const int n = i / 16, k = (i % 16) * 2;
+      __nv_bfloat162 v = __floats2bfloat162_rn(Bm[n * K + k], Bm[n * K + k + 1]);
+      *reinterpret_cast<__nv_bfloat162*>(b64 + tc::sw64_offset(n, k)) = v;
+    }
+    for (int k = 0; k < 32; k += 2) {
+      const int srow = (tid / 8) * 10 + (tid % 8) + 11;
+      __nv_bfloat162 v = __floats2bfloat162_rn(A[tid * K + k], A[tid * K + k + 1]);
+      *reinterpret_cast<__nv_bfloat162*>(a64 + tc::sw64_offset(srow, k)) = v;
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      const uint32_t idesc = tc::idesc_bf16_f32(128, N);
+      for (int ks = 0; ks < 2; ++ks)
+        tc::mma_ss(tmem, tc::smem_desc_sw64(tc::smem_u32(a64) + 11 * 64 + ks * 32, 640),
+                   tc::smem_desc_sw64(tc::smem_u32(b64) + ks * 32), idesc, ks);
+      tc::mma_commit(bar);
+    }
+    tc::mbar_wait(bar, 0);
+    tc::fence_after_sync();
+    for (int n0 = 0; n0 < N; n0 += 16) {
+      uint32_t r[16];
+      tc::tmem_ld16(tmem + lane_base + n0, r);
+      tc::wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) D[tid * N + n0 + j] = __uint_as_float(r[j]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+    return;
+  }
 
   // B tiles (all threads), pairs of k
   for (int i = tid; i < N * K / 2; i += 128) {
@@ -123,11 +168,12 @@ umma_probe_kernel(const float* __restrict__ A, const float* __restrict__ Bm, flo
 
 extern "C" int b200_umma_probe(const float* A, const float* Bm, float* D, int K, int N, int mode, void* stream) {
   B200_CHECK_ARG(A && Bm && D, "umma_probe: null pointer");
-  B200_CHECK_ARG(K % 64 == 0 && K >= 64 && K <= PROBE_MAX_K, "umma_probe: K must be 64, 128 or 192");
+  B200_CHECK_ARG(mode == 5 ? K == 32 : (K % 64 == 0 && K >= 64 && K <= PROBE_MAX_K),
+                 "umma_probe: K must be 64, 128 or 192 (32 for mode 5)");
   B200_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= PROBE_MAX_N, "umma_probe: N must be a multiple of 16 up to 128");
-  B200_CHECK_ARG(mode >= 0 && mode <= 4, "umma_probe: mode 0..4");
+  B200_CHECK_ARG(mode >= 0 && mode <= 5, "umma_probe: mode 0..5");
   B200_CHECK_ARG(mode != 4 || K == 64, "umma_probe: mode 4 needs K == 64");
-  const int nchunk = K / 64;
+  const int nchunk = K >= 64 ? K / 64 : 1;
   size_t smem = 1024 + (size_t)nchunk * (2 * 16384 + 2 * N * 128) + 64;
   B200_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, Bm, D, K, N, mode);

@@ -21,7 +21,7 @@ import torch
 from torch import nn
 
 from . import _abi
-from .conv import ConvPlan, SplitAct, pack_conv_weights
+from .conv import ConvPlan, SplitAct
 
 LRELU = 0.2  # nn.LeakyReLU(0.2) of BasicBlock (layers.py:60) and the matching head (networks.py:278)
 
@@ -68,9 +68,8 @@ class Plan:
             out = self.act(B, OH, OW, cout)
         if out_f32 is None and want_f32:
             out_f32 = self.empty((B, OH, OW, cout))
-        wimage = pack_conv_weights([w for _, w, _, _ in segs], [a.C for a, _, _, _ in segs], cout)
         b = None if bias is None else bias.detach().to(self.device, torch.float32).contiguous()
-        plan = ConvPlan([(a, w.shape[-1], s, p) for a, w, s, p in segs], wimage, b, out, B, cout, act=act,
+        plan = ConvPlan([(a, w.shape[-1], s, p) for a, w, s, p in segs], [w for _, w, _, _ in segs], b, out, B, cout, act=act,
                         slope=slope, residual=residual, out_f32=out_f32)
         self.add(plan.run)
         return out, out_f32

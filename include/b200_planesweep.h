@@ -92,8 +92,10 @@ typedef struct {
 typedef struct {
   b200_conv_seg seg[4]; /* K-segments: concatenated inputs and/or the shortcut conv of a BasicBlock */
   int nseg;
-  const void* wimage;   /* packed weights, b200_conv_wimage_bytes() bytes: [n-tile][chunk][hi|lo] SW128 tiles,
-                           chunks ordered (segment, tap row-major, 64-channel block), zero-padded channel tails */
+  const void* wimage;   /* packed weights, b200_conv_wimage_bytes() bytes: [n-tile][chunk][hi NT rows | lo NT rows],
+                           chunks ordered (segment, tap row-major, channel block), zero-padded channel tails;
+                           b200_conv_uses_halo(desc) == 1: 32-channel blocks, 64-byte-swizzled K-major tiles,
+                           == 0: 64-channel blocks, 128-byte swizzle */
   const float* bias;    /* [Cout] or NULL */
   const void* res_hi;   /* optional identity residual NHWC [B,OH,OW,Cout] (layers.py:92) */
   const void* res_lo;
@@ -104,7 +106,10 @@ typedef struct {
   float slope;
 } b200_conv_desc;
 int b200_conv_ntile(int Cout);
-long long b200_conv_wimage_bytes(const int* seg_C, const int* seg_ksize, int nseg, int Cout);
+/* which kernel (and weight-image layout) a conv gets: 1 = halo-patch kernel (all segments stride 1, Cout % 64 == 0,
+ * no fp32 copy), 0 = per-tap kernel.  Depends only on the geometry fields of the descriptor. */
+int b200_conv_uses_halo(const b200_conv_desc* desc);
+long long b200_conv_wimage_bytes(const int* seg_C, const int* seg_ksize, int nseg, int Cout, int halo);
 int b200_conv_create(const b200_conv_desc* desc, void** plan_out);
 int b200_conv_run(void* plan, void* stream);
 int b200_conv_destroy(void* plan);

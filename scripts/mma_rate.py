@@ -6,10 +6,11 @@ from implicit_depth_b200 import _abi
 lib = _abi.load()
 lib.b200_mma_rate.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
 names = {0: "SS split (hi/lo pattern)", 1: "TS split (A in TMEM)", 2: "SS plain, 3 A chunks", 3: "SS same slice",
-         4: "SS split, 2 accumulators", 5: "TS split, 2 accumulators"}
-for grid in (1, 148):
+         4: "SS split, 2 accumulators", 5: "TS split, 2 accumulators", 8: "SW64 halo: merged N + lo N/2 (avg)",
+         16: "SW128 merged N + lo N/2 (avg)"}
+for grid in (148,):
     for N in (64, 128, 256):
-        for mode in (0, 1, 2, 3, 4, 5):
+        for mode in (0, 3, 8, 16):
             if N == 256 and (mode & 4):
                 continue
             out = torch.zeros(grid, dtype=torch.int64, device="cuda")

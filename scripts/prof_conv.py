@@ -3,7 +3,7 @@ import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from implicit_depth_b200 import _abi
-from implicit_depth_b200.conv import ConvPlan, SplitAct, pack_conv_weights
+from implicit_depth_b200.conv import ConvPlan, SplitAct
 lib = _abi.load()
 lib.b200_conv_set_prof.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 NAMES = ["prod:wait p_empty", "prod:wait b_empty", "mma:wait acc_empty", "mma:wait p_full", "mma:wait b_full",
@@ -12,7 +12,7 @@ def run(B, H, W, segC, Cout, k=3):
     acts = [SplitAct.from_nchw_torch(torch.randn(B, C, H, W, device="cuda")) for C in segC]
     ws = [torch.randn(Cout, C, k, k, device="cuda") * 0.05 for C in segC]
     out = SplitAct(B, H, W, Cout, "cuda")
-    plan = ConvPlan([(a, k, 1, k // 2) for a in acts], pack_conv_weights(ws, segC, Cout), torch.zeros(Cout, device="cuda"), out, B, Cout, act="lrelu")
+    plan = ConvPlan([(a, k, 1, k // 2) for a in acts], ws, torch.zeros(Cout, device="cuda"), out, B, Cout, act="lrelu")
     buf = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
     grid = lib.b200_conv_set_prof(plan.handle, buf.data_ptr())
     for _ in range(3): plan.run()

@@ -2,13 +2,13 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from implicit_depth_b200.conv import ConvPlan, SplitAct, pack_conv_weights
+from implicit_depth_b200.conv import ConvPlan, SplitAct
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 def run(B, H, W, segC, Cout, k=3):
     acts = [SplitAct.from_nchw_torch(torch.randn(B, C, H, W, device="cuda")) for C in segC]
     ws = [torch.randn(Cout, C, k, k, device="cuda") * 0.05 for C in segC]
     out = SplitAct(B, H, W, Cout, "cuda")
-    plan = ConvPlan([(a, k, 1, k // 2) for a in acts], pack_conv_weights(ws, segC, Cout), torch.zeros(Cout, device="cuda"), out, B, Cout, act="lrelu")
+    plan = ConvPlan([(a, k, 1, k // 2) for a in acts], ws, torch.zeros(Cout, device="cuda"), out, B, Cout, act="lrelu")
     for _ in range(3): plan.run()
     ts = []
     for _ in range(10):

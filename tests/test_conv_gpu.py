@@ -3,7 +3,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from implicit_depth_b200.conv import ConvPlan, SplitAct, pack_conv_weights
+from implicit_depth_b200.conv import ConvPlan, SplitAct
 
 pytestmark = pytest.mark.gpu
 
@@ -33,8 +33,9 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("with_f32", [False, True])  # an fp32 copy forces the per-tap kernel, else halo if eligible
 @pytest.mark.parametrize("case", CASES)
-def test_conv_matches_fp64(case):
+def test_conv_matches_fp64(case, with_f32):
     B, H, W, segC, Cout, k, stride, act, use_res = case
     torch.manual_seed(sum(segC) + Cout + k + stride)
     xs = [torch.randn(B, C, H, W, device="cuda") for C in segC]
@@ -46,15 +47,16 @@ def test_conv_matches_fp64(case):
     OW = (W + 2 * pad - k) // stride + 1
     out = SplitAct(B, OH, OW, Cout, "cuda")
     out.hi.fill_(float("nan")); out.lo.fill_(float("nan"))
-    out_f32 = torch.full((B, OH, OW, Cout), float("nan"), device="cuda")
+    out_f32 = torch.full((B, OH, OW, Cout), float("nan"), device="cuda") if with_f32 else None
     res = None
     if use_res:
         rx = torch.randn(B, Cout, OH, OW, device="cuda")
         res = SplitAct.from_nchw_torch(rx)
-    wimage = pack_conv_weights(ws, segC, Cout)
-    plan = ConvPlan([(a, k, stride, pad) for a in acts], wimage, bias, out, B, Cout, act=act, slope=0.2,
+    plan = ConvPlan([(a, k, stride, pad) for a in acts], ws, bias, out, B, Cout, act=act, slope=0.2,
                     residual=res, out_f32=out_f32)
+    assert plan.halo == (not with_f32 and stride == 1 and Cout % 64 == 0)
     plan.run()
+    plan.run()  # a second launch must give the same answer (persistent state fully re-initialised)
     torch.cuda.synchronize()
     ref = sum(F.conv2d(a.float_nchw().double(), w.double(), None, stride, pad) for a, w in zip(acts, ws))
     ref = ref + bias.double().view(1, -1, 1, 1)
@@ -62,10 +64,10 @@ def test_conv_matches_fp64(case):
         ref = ref + res.float_nchw().double()
     ref = act_ref(ref, act, 0.2)
     got = out.float_nchw().double()
-    got32 = out_f32.permute(0, 3, 1, 2).double()
     scale = ref.abs().max().item()
     assert torch.isfinite(got).all()
-    assert (got32 - ref).abs().max().item() < 2e-5 * scale
+    if with_f32:
+        assert (out_f32.permute(0, 3, 1, 2).double() - ref).abs().max().item() < 2e-5 * scale
     assert (got - ref).abs().max().item() < 3e-5 * scale  # + split-bf16 storage rounding (2^-17)
 
 
@@ -98,8 +100,7 @@ def test_conv_mixed_segments(idx):
     bias = torch.randn(Cout, device="cuda")
     acts = [SplitAct.from_nchw_torch(x) for x in xs]
     out = SplitAct(B, OH, OW, Cout, "cuda")
-    wimage = pack_conv_weights(ws, [c for c, _, _, _ in segs], Cout)
-    plan = ConvPlan([(a, k, st, p) for a, (_, k, st, p) in zip(acts, segs)], wimage, bias, out, B, Cout, act=act,
+    plan = ConvPlan([(a, k, st, p) for a, (_, k, st, p) in zip(acts, segs)], ws, bias, out, B, Cout, act=act,
                     slope=0.2)
     plan.run()
     torch.cuda.synchronize()

@@ -48,3 +48,16 @@ def test_halo_patch_descriptor():
     ref = (A.bfloat16().double() @ Bm.bfloat16().double().t()).float()
     err = (D - ref).abs().max().item()
     assert err < 1e-3 * ref.abs().max().item(), f"halo descriptor: max err {err}"
+
+
+@pytest.mark.parametrize("N", [128, 64, 32])
+def test_sw64_halo_patch_descriptor(N):
+    """64-byte swizzle, 32-channel K chunk, A rows inside a halo patch (start shifted by 11 pixel records of
+    64 B, 640-byte group stride): the operand addressing of the 32-channel-block conv kernel."""
+    torch.manual_seed(9 + N)
+    A = torch.randn(128, 32, device="cuda")
+    Bm = torch.randn(N, 32, device="cuda")
+    D = run_probe(A, Bm, 5)
+    ref = (A.bfloat16().double() @ Bm.bfloat16().double().t()).float()
+    err = (D - ref).abs().max().item()
+    assert err < 1e-3 * ref.abs().max().item(), f"sw64 halo descriptor: max err {err}"
