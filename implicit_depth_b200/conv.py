@@ -80,7 +80,7 @@ def _swizzle64_last(t):
 
 def pack_conv_weights(weights, seg_channels, cout, halo=False):
     """weights: list (one per segment) of [Cout, C_s, k, k] fp32 tensors.  Returns the uint8 weight image in the
-    producer's chunk order (segment, tap, channel block):
+    producer's chunk order (plain: segment, tap, channel block; halo: segment, channel block, tap):
       plain kernel  [n_ntiles][chunk][hi NT x 64 | lo NT x 64]  64-channel chunks, 128-byte swizzle
       halo kernel   [n_ntiles][chunk][hi NT x 32 | lo NT x 32]  32-channel chunks, 64-byte swizzle; hi and lo are
                     adjacent rows of ONE tile so that A_hi x [B_hi | B_lo] is a single N = 2*NT MMA."""
@@ -94,8 +94,11 @@ def pack_conv_weights(weights, seg_channels, cout, halo=False):
         Cp = (C + cw - 1) // cw * cw
         wp = torch.zeros((cout, Cp, k, k), device=w.device, dtype=torch.float32)
         wp[:, :C] = w.detach().float()
-        # [Cout, Cp/cw, cw, k, k] -> [k, k, Cp/cw, Cout, cw] -> [chunks, Cout, cw]
-        chunks.append(wp.view(cout, Cp // cw, cw, k, k).permute(3, 4, 1, 0, 2).reshape(-1, cout, cw))
+        v = wp.view(cout, Cp // cw, cw, k, k)
+        if halo:  # chunk order (channel block, tap): the 9 taps of a block are contiguous (one bulk copy per row)
+            chunks.append(v.permute(1, 3, 4, 0, 2).reshape(-1, cout, cw))
+        else:     # chunk order (tap, channel block)
+            chunks.append(v.permute(3, 4, 1, 0, 2).reshape(-1, cout, cw))
     allw = torch.cat(chunks, 0)  # [Q, Cout, cw]
     Q = allw.shape[0]
     hi = allw.to(torch.bfloat16)

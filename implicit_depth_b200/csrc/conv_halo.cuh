@@ -20,7 +20,7 @@
 #define CVH_ROWS 16
 #define CVH_EPI_THREADS 256
 
-template <int SUB, int NTC /* NT / 64: 1 or 2 */>
+template <int SUB, int NTC /* NT / 64: 1 or 2 */, bool PROF /* dev: per-role clock64 accounting */>
 __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvKParams prm) {
   constexpr int NT = 64 * NTC;
   constexpr int PW = 8 * SUB + 2;
@@ -33,10 +33,11 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = prm.stages;
+  const int TPS = prm.tps;  // taps per weight stage (1 or 3)
   uint8_t* patch0 = base;                                   // 2 patch slots x (hi, lo)
   uint8_t* staging = base + 4u * PATCH_PLANE;               // SUB staging buffers
   uint8_t* bring = staging + SUB * STAGING;                 // S weight stages
-  float* bias_s = reinterpret_cast<float*>(bring + (size_t)S * B_BYTES);  // [n_ntiles * NT]
+  float* bias_s = reinterpret_cast<float*>(bring + (size_t)S * TPS * B_BYTES);  // [n_ntiles * NT]
   uint64_t* p_full = reinterpret_cast<uint64_t*>(bias_s + prm.n_ntiles * NT);
   uint64_t* p_empty = p_full + 2;
   uint64_t* acc_full = p_empty + 2;
@@ -49,8 +50,8 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_t0 = 0;
   const long long k_t0 = clock64();
-#define PROF_T0 if (prm.prof) prof_t0 = clock64()
-#define PROF_ADD(i) if (prm.prof) prof_acc[i] += clock64() - prof_t0
+#define PROF_T0 if (PROF) prof_t0 = clock64()
+#define PROF_ADD(i) if (PROF) prof_acc[i] += clock64() - prof_t0
   const int items = prm.B * prm.tiles_y * prm.tiles_x * prm.n_ntiles;
 
   for (int i = tid; i < prm.n_ntiles * NT; i += CVH_THREADS)
@@ -80,7 +81,8 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
 
   if (warp == 0) {
     // =========================== TMA producer (whole warp loops, one elected lane issues) ===========
-    uint32_t pit = 0, bit = 0;  // patch / weight-chunk counters
+    uint32_t pit = 0;                 // patch counter
+    uint32_t bst = 0, bround = 0;     // weight-stage ring position / wrap count
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int nt = item % prm.n_ntiles;
       const int mt = item / prm.n_ntiles;
@@ -99,18 +101,31 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
           if (round > 0) { PROF_T0; tc::mbar_wait(&p_empty[pb], (round - 1) & 1u); PROF_ADD(0); }
           uint8_t* pa = patch0 + (size_t)pb * 2u * PATCH_PLANE;
           if (tc::elect_one()) {
-            tc::mbar_expect_tx(&p_full[pb], 2u * (uint32_t)(18 * PW * 64));
-            tc::tma_load_4d(pa, &prm.maps[2 * s], cb * 32, x0, y0, b, &p_full[pb]);
-            tc::tma_load_4d(pa + PATCH_PLANE, &prm.maps[2 * s + 1], cb * 32, x0, y0, b, &p_full[pb]);
+            if (prm.debug & 2) {
+              tc::mbar_arrive(&p_full[pb]);
+            } else {
+              tc::mbar_expect_tx(&p_full[pb], 2u * (uint32_t)(18 * PW * 64));
+              tc::tma_load_4d(pa, &prm.maps[2 * s], cb * 32, x0, y0, b, &p_full[pb]);
+              tc::tma_load_4d(pa + PATCH_PLANE, &prm.maps[2 * s + 1], cb * 32, x0, y0, b, &p_full[pb]);
+            }
           }
           __syncwarp();
-          for (int tap = 0; tap < ks * ks; ++tap, ++bit) {
-            const uint32_t st = bit % S, r2 = bit / S;
+          // weights: TPS taps per stage (a kernel row of a 3x3 segment when TPS = 3), chunks ordered (seg, cb, tap)
+          const int ntaps = ks * ks;
+          for (int tap = 0; tap < ntaps; tap += TPS) {
+            const int nt_g = min(TPS, ntaps - tap);
+            const uint32_t st = bst, r2 = bround;
+            if (++bst == (uint32_t)S) { bst = 0; ++bround; }
             if (r2 > 0) { PROF_T0; tc::mbar_wait(&b_empty[st], (r2 - 1) & 1u); PROF_ADD(1); }
             if (tc::elect_one()) {
-              tc::mbar_expect_tx(&b_full[st], B_BYTES);
-              tc::bulk_load(bring + (size_t)st * B_BYTES,
-                            wbase + (size_t)(prm.seg_chunk0[s] + tap * cblocks + cb) * B_BYTES, B_BYTES, &b_full[st]);
+              if (prm.debug & 2) {
+                tc::mbar_arrive(&b_full[st]);
+              } else {
+                tc::mbar_expect_tx(&b_full[st], nt_g * B_BYTES);
+                tc::bulk_load(bring + (size_t)st * (TPS * B_BYTES),
+                              wbase + (size_t)(prm.seg_chunk0[s] + cb * ntaps + tap) * B_BYTES, nt_g * B_BYTES,
+                              &b_full[st]);
+              }
             }
             __syncwarp();
           }
@@ -122,7 +137,8 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
     constexpr uint32_t IDESC_MERGED = tc::idesc_bf16_f32(128, 2 * NT);
     constexpr uint32_t IDESC_HI = tc::idesc_bf16_f32(128, NT);
     constexpr uint32_t SBO = PW * 64u;
-    uint32_t pit = 0, bit = 0, tile_i = 0;
+    uint32_t pit = 0, tile_i = 0;
+    uint32_t bst = 0, bround = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
       const uint32_t a = tile_i & 1u, use = tile_i >> 1;
       if (use > 0) { PROF_T0; tc::mbar_wait(&acc_empty[a], (use - 1) & 1u); PROF_ADD(2); }
@@ -138,31 +154,39 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
           tc::fence_after_sync();
           const uint32_t pa = tc::smem_u32(patch0 + (size_t)pb * 2u * PATCH_PLANE);
           const int ksteps = (min(32, C - cb * 32) + 15) >> 4;
-          for (int tap = 0; tap < ks * ks; ++tap, ++bit) {
-            const uint32_t st = bit % S;
-            { PROF_T0; tc::mbar_wait(&b_full[st], (bit / S) & 1u); PROF_ADD(4); }
+          const int ntaps = ks * ks;
+          int dy = (ks == 3) ? 0 : 1, dx = (ks == 3) ? 0 : 1;
+          for (int tap = 0; tap < ntaps; tap += TPS) {
+            const int nt_g = min(TPS, ntaps - tap);
+            const uint32_t st = bst;
+            { PROF_T0; tc::mbar_wait(&b_full[st], bround & 1u); PROF_ADD(4); }
+            if (++bst == (uint32_t)S) { bst = 0; ++bround; }
             tc::fence_after_sync();
-            const uint32_t sb = tc::smem_u32(bring + (size_t)st * B_BYTES);
-            const int dy = (ks == 3) ? tap / 3 : 1, dx = (ks == 3) ? tap % 3 : 1;
-            const uint32_t row0 = (uint32_t)(dy * PW + dx) * 64u;
+            const uint32_t sb = tc::smem_u32(bring) + st * (TPS * B_BYTES);
             if (tc::elect_one()) {
-              const uint64_t b_m = tc::smem_desc_sw64(sb);
+              for (int t = 0; t < nt_g; ++t) {
+                const uint64_t b_m = tc::smem_desc_sw64(sb + t * B_BYTES);
+                const uint32_t row0 = (uint32_t)(dy * PW + dx + t) * 64u;  // a group never crosses a kernel row
 #pragma unroll
-              for (int sub = 0; sub < SUB; ++sub) {  // sub-tile 1 sits 8 pixel records = 512 B to the right
-                const uint64_t a_hi = tc::smem_desc_sw64(pa + row0 + sub * 512u, SBO);
-                const uint64_t a_lo = a_hi + (PATCH_PLANE >> 4);
-                const uint32_t d = acc + sub * 2 * NT;
-                // hi*hi -> columns [0,NT), hi*lo -> columns [NT,2NT): one N = 2*NT instruction per k-step
-                tc::mma_ss(d, a_hi, b_m, IDESC_MERGED, first ? 0u : 1u);
-                if (ksteps > 1) tc::mma_ss(d, a_hi + 2, b_m + 2, IDESC_MERGED, 1u);
-                // lo*hi -> columns [0,NT)
-                tc::mma_ss(d, a_lo, b_m, IDESC_HI, 1u);
-                if (ksteps > 1) tc::mma_ss(d, a_lo + 2, b_m + 2, IDESC_HI, 1u);
+                for (int sub = 0; sub < SUB; ++sub) {  // sub-tile 1 sits 8 pixel records = 512 B to the right
+                  const uint64_t a_hi = tc::smem_desc_sw64(pa + row0 + sub * 512u, SBO);
+                  const uint64_t a_lo = a_hi + (PATCH_PLANE >> 4);
+                  const uint32_t d = acc + sub * 2 * NT;
+                  if (prm.debug & 4) continue;  // dev: no MMAs
+                  // hi*hi -> columns [0,NT), hi*lo -> columns [NT,2NT): one N = 2*NT instruction per k-step
+                  tc::mma_ss(d, a_hi, b_m, IDESC_MERGED, (first && t == 0) ? 0u : 1u);
+                  if (ksteps > 1) tc::mma_ss(d, a_hi + 2, b_m + 2, IDESC_MERGED, 1u);
+                  // lo*hi -> columns [0,NT)
+                  tc::mma_ss(d, a_lo, b_m, IDESC_HI, 1u);
+                  if (ksteps > 1) tc::mma_ss(d, a_lo + 2, b_m + 2, IDESC_HI, 1u);
+                }
               }
               tc::mma_commit(&b_empty[st]);
             }
             __syncwarp();
             first = 0;
+            dx += nt_g;
+            if (dx >= 3) { dx = 0; ++dy; }
           }
           if (tc::elect_one()) tc::mma_commit(&p_empty[pb]);
           __syncwarp();
@@ -210,12 +234,13 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
       tc::named_sync(1, CVH_EPI_THREADS);
       { PROF_T0; tc::mbar_wait(&acc_full[a], (tile_i >> 1) & 1u); PROF_ADD(5); }
       tc::fence_after_sync();
-      const long long ep0 = prm.prof ? clock64() : 0;
+      const long long ep0 = PROF ? clock64() : 0;
       const float* bias_t = bias_s + nt * NT + half * COLS;
 #pragma unroll
       for (int sub = 0; sub < SUB; ++sub) {
         uint8_t* sg = staging + sub * STAGING;
         if (has_res) tc::mbar_wait(&res_full[sub], tile_i & 1u);
+        if (prm.debug & 1) continue;  // dev: skip the TMEM drain / staging writes
         const uint32_t t_main = tmem + lane_base + a * ACC_COLS + sub * 2 * NT + half * COLS;
 #pragma unroll
         for (int c0 = 0; c0 < COLS; c0 += 32) {
@@ -264,7 +289,7 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
       tc::mbar_arrive(&acc_empty[a]);
       tc::fence_async_smem();
       tc::named_sync(1, CVH_EPI_THREADS);
-      if (leader) {
+      if (leader && !(prm.debug & 1)) {
 #pragma unroll
         for (int sub = 0; sub < SUB; ++sub)
 #pragma unroll
@@ -275,11 +300,11 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
                                nt * NT + blk * 64, tx * 8 * SUB + sub * 8, ty * CVH_ROWS, b);
         tc::tma_store_commit();
       }
-      if (prm.prof) prof_acc[6] += clock64() - ep0;
+      if (PROF) prof_acc[6] += clock64() - ep0;
     }
     if (leader) tc::tma_store_wait_all<0>();
   }
-  if (prm.prof && lane == 0 && (warp <= 2)) {
+  if (PROF && prm.prof && lane == 0 && (warp <= 2)) {
     long long* o = prm.prof + (size_t)blockIdx.x * 8;
     if (warp == 0) { o[0] = prof_acc[0]; o[1] = prof_acc[1]; }
     if (warp == 1) { o[2] = prof_acc[2]; o[3] = prof_acc[3]; o[4] = prof_acc[4]; o[7] = clock64() - k_t0; }
@@ -293,9 +318,9 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
 }
 
 // shared-memory footprint of the halo kernel for (SUB, NT, stages, n_ntiles)
-static inline size_t conv_halo_smem(int sub, int NT, int stages, int n_ntiles) {
+static inline size_t conv_halo_smem(int sub, int NT, int stages, int tps, int n_ntiles) {
   const size_t patch_plane = ((size_t)18 * (8 * sub + 2) * 64 + 1023) & ~(size_t)1023;
   const size_t staging = (size_t)sub * 2 * (NT / 64) * 16384;
-  return 1024 + 4 * patch_plane + staging + (size_t)stages * NT * 128 + (size_t)n_ntiles * NT * 4 +
+  return 1024 + 4 * patch_plane + staging + (size_t)stages * tps * NT * 128 + (size_t)n_ntiles * NT * 4 +
          (10 + 2 * stages) * 8 + 16;
 }

@@ -47,9 +47,10 @@ struct ConvKParams {
   float* out_f32;         // optional NHWC fp32 copy (plain kernel only)
   int B, OH, OW, Cout, NT, n_ntiles, act, total_chunks, tiles_x, tiles_y, stages;
   float slope;
-  int halo, sub, has_res;
+  int halo, sub, has_res, tps;
   int seg_chunk0[CV_MAX_SEG];  // index of each segment's first chunk in the weight image
   long long* prof;             // dev only: per-CTA role timings [grid][8] (clock64 ticks) or null
+  int debug;                   // dev only (B200_CONV_DEBUG): 1 = no epilogue body, 2 = no TMA loads, 4 = no MMAs
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -331,6 +332,7 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   k.n_ntiles = (d->Cout + k.NT - 1) / k.NT;
   const bool halo = b200_conv_uses_halo(d) != 0;
   k.halo = halo ? 1 : 0;
+  k.debug = getenv("B200_CONV_DEBUG") ? atoi(getenv("B200_CONV_DEBUG")) : 0;
   k.sub = 1;
   if (halo) {
     // two M=128 sub-tiles per item share every weight chunk when the N tile is 64 wide and there is enough work
@@ -409,10 +411,13 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   if (halo) {
     k.tiles_x = (d->OW + 8 * k.sub - 1) / (8 * k.sub);
     k.tiles_y = (d->OH + CVH_ROWS - 1) / CVH_ROWS;
-    int S = 12;
-    while (S > 2 && conv_halo_smem(k.sub, k.NT, S, k.n_ntiles) > 227 * 1024) --S;
+    // weight stages: a whole kernel row (3 taps) per barrier round for the 64-wide N tile (halves the issue-loop
+    // overhead per MMA); single taps for the 128-wide tile whose stages would otherwise be 48 KB
+    k.tps = (k.NT == 64) ? 3 : 1;
+    int S = 12 / k.tps;
+    while (S > 2 && conv_halo_smem(k.sub, k.NT, S, k.tps, k.n_ntiles) > 227 * 1024) --S;
     k.stages = S;
-    p->smem = conv_halo_smem(k.sub, k.NT, S, k.n_ntiles);
+    p->smem = conv_halo_smem(k.sub, k.NT, S, k.tps, k.n_ntiles);
   } else {
     k.tiles_x = (d->OW + CV_TW - 1) / CV_TW;
     k.tiles_y = (d->OH + CV_TH - 1) / CV_TH;
@@ -429,11 +434,17 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_halo_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(conv_halo_kernel<2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_halo_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(conv_halo_kernel<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_halo_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(conv_halo_kernel<1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_halo_kernel<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_halo_kernel<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_halo_kernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       delete p;
       b200_set_error("conv_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -451,12 +462,15 @@ extern "C" int b200_conv_run(void* plan, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!p->k.halo)
     conv_tc_kernel<<<p->grid, CV_THREADS, p->smem, st>>>(p->k);
-  else if (p->k.NT == 128)
-    conv_halo_kernel<1, 2><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
-  else if (p->k.sub == 2)
-    conv_halo_kernel<2, 1><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
-  else
-    conv_halo_kernel<1, 1><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
+  else if (p->k.prof == nullptr) {
+    if (p->k.NT == 128) conv_halo_kernel<1, 2, false><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
+    else if (p->k.sub == 2) conv_halo_kernel<2, 1, false><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
+    else conv_halo_kernel<1, 1, false><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
+  } else {
+    if (p->k.NT == 128) conv_halo_kernel<1, 2, true><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
+    else if (p->k.sub == 2) conv_halo_kernel<2, 1, true><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
+    else conv_halo_kernel<1, 1, true><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
+  }
   B200_CHECK_LAUNCH("conv_run");
   return 0;
 }

@@ -41,6 +41,7 @@ __device__ __forceinline__ void named_sync(uint32_t id, uint32_t nthreads) {
 }
 // Bounded wait: a protocol bug traps (launch error the host sees) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 26); ++it)
     if (mbar_try_wait(bar, parity)) return;
   __trap();
