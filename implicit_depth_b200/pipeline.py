@@ -1,0 +1,96 @@
+"""Host <-> device streaming around `B200BDModel.forward`.
+
+`FramePipeline` keeps two device-side input slots and two pinned host-side output slots and runs three CUDA
+streams: while batch i is in the forward (compute stream), batch i+1 is uploaded (copy-in stream) and the outputs
+of batch i-1 are downloaded (copy-out stream).  Ordering is by CUDA events only; the host blocks once per batch,
+on the event of the batch whose results it hands back.  This is the path `bench.py` times as `e2e`.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class FramePipeline:
+    def __init__(self, model, device, gather=None, **forward_kwargs):
+        """model: B200BDModel (or anything with the reference's forward signature); gather: optional callable
+        applied to the output dict on the compute stream (e.g. `parallel.GatherPlan.run`)."""
+        self.model, self.device, self.gather, self.kw = model, torch.device(device), gather, forward_kwargs
+        self.s_in = torch.cuda.Stream(device=self.device)
+        self.s_out = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]          # device input dictionaries
+        self.host_out = [None, None]       # pinned output dictionaries
+        self.ev_free = [None, None]        # forward that last read input slot s has finished
+        self.ev_out_free = [None, None]    # host has consumed host_out[s] (host-side: implicit, see run())
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _upload(self, slot, cur, src):
+        """Enqueue the H2D copies of one batch on the copy-in stream; returns the event that marks their end."""
+        if self.slots[slot] is None:
+            mk = lambda d: {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in d.items()}
+            self.slots[slot] = (mk(cur), mk(src))
+        dcur, dsrc = self.slots[slot]
+        with torch.cuda.stream(self.s_in):
+            if self.ev_free[slot] is not None:
+                self.s_in.wait_event(self.ev_free[slot])
+            n = 0
+            for dst, srcd in ((dcur, cur), (dsrc, src)):
+                for k, v in srcd.items():
+                    dst[k].copy_(v, non_blocking=True)
+                    n += v.numel() * v.element_size()
+            self.h2d_bytes = n
+            ev = torch.cuda.Event()
+            ev.record(self.s_in)
+        return ev
+
+    def _forward(self, slot, ev_in):
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(ev_in)
+        dcur, dsrc = self.slots[slot]
+        out = self.model("test", dict(dcur), dsrc, **self.kw)
+        if self.gather is not None:
+            g = self.gather(out)
+            out = {k: (g[k] if k in g else v) for k, v in out.items()}
+        self.ev_free[slot] = torch.cuda.Event()
+        self.ev_free[slot].record(main)
+        return out, self.ev_free[slot]
+
+    def _download(self, slot, out, ev_fwd):
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(ev_fwd)
+            if self.host_out[slot] is None:
+                self.host_out[slot] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()
+                                       if v is not None}
+            n = 0
+            for k, h in self.host_out[slot].items():
+                h.copy_(out[k], non_blocking=True)
+                out[k].record_stream(self.s_out)
+                n += h.numel() * h.element_size()
+            self.d2h_bytes = n
+            ev = torch.cuda.Event()
+            ev.record(self.s_out)
+        return ev
+
+    def run(self, host_batches):
+        """host_batches: iterable of (cur_data, src_data) dictionaries of PINNED host tensors.  Yields one dictionary
+        of pinned host tensors per batch (valid until two more batches have been yielded)."""
+        pending = None  # (slot, event of the D2H copy)
+        it = iter(host_batches)
+        nxt = next(it, None)
+        i = 0
+        ev_in = self._upload(0, *nxt) if nxt is not None else None
+        while nxt is not None:
+            slot = i & 1
+            following = next(it, None)
+            ev_next = self._upload(slot ^ 1, *following) if following is not None else None
+            out, ev_fwd = self._forward(slot, ev_in)
+            ev_done = self._download(slot, out, ev_fwd)
+            if pending is not None:
+                pending[1].synchronize()
+                yield self.host_out[pending[0]]
+            pending = (slot, ev_done)
+            nxt, ev_in = following, ev_next
+            i += 1
+        if pending is not None:
+            pending[1].synchronize()
+            yield self.host_out[pending[0]]

@@ -205,3 +205,27 @@ def test_temporal_and_infer_depth_forward_vs_reference_golden(mode):
             assert (np.abs(sd_got - g["search_depths"]) > 1e-6).mean() < 2e-2
         else:
             assert rel_err(out["pred_0"].cpu().numpy(), g[f"{mode}_pred_0"]) < TOL
+
+
+def test_frame_pipeline_matches_direct_forward():
+    """The streaming API (H2D / forward / D2H on three streams) returns, batch by batch, what direct calls return."""
+    from implicit_depth_b200.pipeline import FramePipeline
+
+    m, _, _ = seeded(image_width=256, image_height=192, matching_num_depth_bins=16)
+    m.use_cuda_graph = True
+    batches = []
+    for i in range(4):
+        cur, src = synthetic.make_frame_batch(6000 + i, 1, 7, 192, 256)
+        batches.append(({k: torch.from_numpy(v).pin_memory() for k, v in cur.items()},
+                        {k: torch.from_numpy(v).pin_memory() for k, v in src.items()}))
+    direct = []
+    for cur, src in batches:
+        o = m("test", {k: v.cuda() for k, v in cur.items()}, {k: v.cuda() for k, v in src.items()}, return_mask=True)
+        direct.append({k: v.cpu().clone() for k, v in o.items()})
+    pipe = FramePipeline(m, "cuda", return_mask=True)
+    got = [{k: v.clone() for k, v in res.items()} for res in pipe.run(iter(batches))]
+    assert len(got) == len(direct)
+    for g_, d_ in zip(got, direct):
+        for k in d_:
+            assert torch.equal(g_[k], d_[k]), k
+    assert pipe.h2d_bytes > 0 and pipe.d2h_bytes > 0
