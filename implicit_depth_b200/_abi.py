@@ -37,6 +37,7 @@ SIGNATURES = {
     "b200_instance_norm": [c_f] * 7 + [c_i] * 6 + [ctypes.c_float, ctypes.c_float, ctypes.c_void_p],
     "b200_instance_norm_ws_bytes": [c_i, c_i, ctypes.c_void_p, ctypes.c_void_p],
     "b200_stem_conv7": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
+    "b200_stem_conv7_tc": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
     "b200_maxblurpool": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, ctypes.c_void_p],
     "b200_sample_prior": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
     "b200_binary_mlp_create": [ctypes.c_void_p, ctypes.c_void_p],

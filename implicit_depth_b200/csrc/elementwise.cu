@@ -360,25 +360,49 @@ __global__ void maxblurpool_kernel(const __nv_bfloat16* __restrict__ ih, const _
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int a = 0; a < 4; ++a) {
-      int my = 2 * oy + a - 1;  // index into the reflect-padded max-pooled map (pad top 1)
-      my = my < 0 ? -my : (my >= MH ? 2 * (MH - 1) - my : my);
-      for (int q = 0; q < 4; ++q) {
-        int mx = 2 * ox + q - 1;
-        mx = mx < 0 ? -mx : (mx >= MW ? 2 * (MW - 1) - mx : mx);
-        float m[8], t[8];
-        const size_t base = ((size_t)b * H + my) * W + mx;
-        load8(ih, il, base * C + c8 * 8, m);
-        load8(ih, il, (base + 1) * C + c8 * 8, t);
+    if (oy >= 1 && 2 * oy + 2 < MH && ox >= 1 && 2 * ox + 2 < MW) {
+      // interior: the 4x4 max-pooled window needs a 5x5 window of inputs; load each once, slide row by row
+      const size_t base = (((size_t)b * H + 2 * oy - 1) * W + 2 * ox - 1) * C + c8 * 8;
+      float prev[5][8], cur[5][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], t[e]);
-        load8(ih, il, (base + W) * C + c8 * 8, t);
+      for (int q = 0; q < 5; ++q) load8(ih, il, base + (size_t)q * C, prev[q]);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], t[e]);
-        load8(ih, il, (base + W + 1) * C + c8 * 8, t);
-        const float wgt = f[a] * f[q] * (1.f / 64.f);
+      for (int a = 0; a < 4; ++a) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, fmaxf(m[e], t[e]), acc[e]);
+        for (int q = 0; q < 5; ++q) load8(ih, il, base + ((size_t)(a + 1) * W + q) * C, cur[q]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float wgt = f[a] * f[q] * (1.f / 64.f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            acc[e] = fmaf(wgt, fmaxf(fmaxf(prev[q][e], prev[q + 1][e]), fmaxf(cur[q][e], cur[q + 1][e])), acc[e]);
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) prev[q][e] = cur[q][e];
+      }
+    } else {
+      for (int a = 0; a < 4; ++a) {
+        int my = 2 * oy + a - 1;  // index into the reflect-padded max-pooled map (pad top 1)
+        my = my < 0 ? -my : (my >= MH ? 2 * (MH - 1) - my : my);
+        for (int q = 0; q < 4; ++q) {
+          int mx = 2 * ox + q - 1;
+          mx = mx < 0 ? -mx : (mx >= MW ? 2 * (MW - 1) - mx : mx);
+          float m[8], t[8];
+          const size_t base = ((size_t)b * H + my) * W + mx;
+          load8(ih, il, base * C + c8 * 8, m);
+          load8(ih, il, (base + 1) * C + c8 * 8, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], t[e]);
+          load8(ih, il, (base + W) * C + c8 * 8, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], t[e]);
+          load8(ih, il, (base + W + 1) * C + c8 * 8, t);
+          const float wgt = f[a] * f[q] * (1.f / 64.f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, fmaxf(m[e], t[e]), acc[e]);
+        }
       }
     }
     store8(oh, ol, (((size_t)b * OH + oy) * OW + ox) * C + c8 * 8, acc);

@@ -433,16 +433,26 @@ class ResnetMatchingEncoder(_PlannedModule):
         net = self.net
         dev = g.device
         w7, b7 = _fold_bn(net[0].weight, net[1])
-        wt = w7.permute(1, 2, 3, 0).reshape(147, 64).to(dev, torch.float32).contiguous()
+        # K index of the tensor-core stem kernel (csrc/stem_tc.cu): k = (c*7 + dy)*8 + dx, dx = 7 is a zero column
+        wk = torch.zeros((64, 3, 7, 8), dtype=torch.float32)
+        wk[..., :7] = w7.detach().float().cpu()
+        wk = torch.cat([wk.reshape(64, 168), torch.zeros(64, 24)], 1).to(dev)  # [64, 192]
+        hi = wk.to(torch.bfloat16)
+        lo = (wk - hi.float()).to(torch.bfloat16)
+        tiles = torch.cat([hi, lo], 0).view(128, 3, 64).permute(1, 0, 2).contiguous()  # [chunk, 128 rows, 64 k]
+        from .conv import _swizzle_last
+
+        wimage = _swizzle_last(tiles).contiguous().view(torch.uint8).reshape(-1)
         b7 = b7.to(dev, torch.float32).contiguous()
         H2, W2 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
         s1 = g.act(n, H2, W2, 64)
+        g._keep += [wimage, b7]
 
         def stem():
             img = get_images()
             assert tuple(img.shape) == (n, 3, H, W) and img.is_contiguous() and img.dtype == torch.float32
-            _abi.call("b200_stem_conv7", _abi.ptr(img), _abi.ptr(wt), _abi.ptr(b7), _abi.ptr(s1.hi), _abi.ptr(s1.lo), n,
-                      H, W, _abi.stream_ptr())
+            _abi.call("b200_stem_conv7_tc", _abi.ptr(img), _abi.ptr(wimage), _abi.ptr(b7), _abi.ptr(s1.hi),
+                      _abi.ptr(s1.lo), n, H, W, _abi.stream_ptr())
 
         g.add(stem)
         H4, W4 = (H2 - 2) // 2 + 1, (W2 - 2) // 2 + 1

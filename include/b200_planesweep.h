@@ -135,6 +135,11 @@ int b200_instance_norm_ws_bytes(int B, int C, long long* partial_bytes, long lon
  * img fp32 NCHW [n,3,H,W]; wt [147,64] tap-major (c,dy,dx); out NHWC split [n,H/2,W/2,64]. */
 int b200_stem_conv7(const float* img, const float* wt, const float* bias, void* out_hi, void* out_lo, int n_img,
                     int H, int W, void* stream);
+/* Same layer on the tensor cores (csrc/stem_tc.cu): implicit GEMM with K = (c*7 + dy)*8 + dx built row by row into
+ * tensor memory.  wimage: 48 KB = 3 K-chunks x [W_hi 64x64 | W_lo 64x64] bf16 in the 128-byte-swizzled K-major
+ * layout (BatchNorm folded, k >= 168 and dx == 7 zero). */
+int b200_stem_conv7_tc(const float* img, const void* wimage, const float* bias, void* out_hi, void* out_lo,
+                       int n_img, int H, int W, void* stream);
 /* MaxPool2d(2, stride 1) + BlurPool(4x4 binomial, stride 2, reflect pad) of antialiased-cnns 0.3
  * (call site modules/networks.py:267); [B,H,W,C] -> [B,H/2,W/2,C]. */
 int b200_maxblurpool(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int B, int H, int W, int C,

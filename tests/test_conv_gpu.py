@@ -108,3 +108,36 @@ def test_conv_mixed_segments(idx):
     ref = act_ref(ref + bias.double().view(1, -1, 1, 1), act, 0.2)
     got = out.float_nchw().double()
     assert (got - ref).abs().max().item() < 3e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("shape", [(2, 50, 70), (1, 96, 128), (3, 33, 47)])
+def test_stem_conv7_tensor_core_matches_fp64(shape):
+    """csrc/stem_tc.cu (7x7/2 stem as an implicit GEMM built row by row in tensor memory) vs torch fp64, incl. ragged
+    sizes whose last tiles are clipped by the TMA store."""
+    from implicit_depth_b200 import _abi
+    from implicit_depth_b200.networks import Plan, ResnetMatchingEncoder
+
+    n, H, W = shape
+    torch.manual_seed(n * H + W)
+    enc = ResnetMatchingEncoder(18, 16).cuda().eval()
+    with torch.no_grad():
+        enc.net[1].running_mean.normal_(0, 0.1)
+        enc.net[1].running_var.uniform_(0.5, 1.5)
+        enc.net[1].weight.uniform_(0.5, 1.5)
+        enc.net[1].bias.normal_(0, 0.1)
+    img = torch.randn(n, 3, H, W, device="cuda")
+    # run only the first op of the plan (the stem) and read its output buffer back
+    g = Plan("cuda")
+    enc.plan(g, lambda: img, n, H, W)
+    g.ops[0]()
+    torch.cuda.synchronize()
+    s1 = [t for t in (getattr(o, "__closure__", None) and [c.cell_contents for c in o.__closure__] for o in g.ops[:1])][0]
+    act = [c for c in s1 if isinstance(c, SplitAct)][0]
+    got = act.float_nchw().double()
+    bn = enc.net[1]
+    ref = F.conv2d(img.double(), enc.net[0].weight.double(), None, 2, 3)
+    ref = F.batch_norm(ref, bn.running_mean.double(), bn.running_var.double(), bn.weight.double(), bn.bias.double(),
+                       False, 0.0, bn.eps)
+    ref = F.relu(ref)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() < 3e-5 * ref.abs().max().item()
