@@ -229,3 +229,35 @@ def test_frame_pipeline_matches_direct_forward():
         for k in d_:
             assert torch.equal(g_[k], d_[k]), k
     assert pipe.h2d_bytes > 0 and pipe.d2h_bytes > 0
+
+
+def test_cfg4_temporal_model_640x480_96_planes_vs_oracle():
+    """BASELINE config 4: implicit_depth_temporal.yaml shape (use_prior, 640x480 -> 120x160 matching, 96 planes,
+    7 views, one rendered plane, previous prediction warped in): B200BDModel.forward against the CPU oracle run on
+    the same inputs and weights, two consecutive frames carrying the prediction forward like test_bd.py:178-214."""
+    m, _, sd = seeded(image_width=640, image_height=480, matching_num_depth_bins=96, use_prior=True)
+    cpu = B200BDModel(m.run_opts)
+    cpu.load_state_dict(sd)
+    enc_cpu = cpu.encoder.eval()
+    prev_pred = prev_pose = None
+    prev_pred_ref = None
+    for frame in range(2):
+        cur, src = synthetic.make_frame_batch(7000 + frame, 1, 7, 480, 640, num_rendered=1, temporal=True)
+        cur_t = {k: torch.from_numpy(v) for k, v in cur.items() if not k.startswith("prior_")}
+        src_t = {k: torch.from_numpy(v) for k, v in src.items()}
+        cur_c = {k: v.cuda() for k, v in cur_t.items()}
+        src_c = {k: v.cuda() for k, v in src_t.items()}
+        if prev_pred is not None:
+            cur_c["prior_prediction"], cur_c["prior_cam_T_world"] = prev_pred, prev_pose
+            cur_t["prior_prediction"], cur_t["prior_cam_T_world"] = prev_pred_ref, prev_pose.cpu()
+        out = m("test", cur_c, src_c, return_mask=True)
+        ref = ON.bd_forward(sd, enc_cpu, cur_t, src_t, m.run_opts, torch_volume=True)
+        assert tuple(out["pred_0"].shape) == (1, 1, 240, 320)
+        assert tuple(out["lowest_cost_bhw"].shape) == (1, 120, 160)
+        assert rel_err(out["pred_0"].cpu().numpy(), ref["pred_0"].numpy()) < TOL
+        if prev_pred is not None:
+            assert (cur_c["prior_mask"].cpu().numpy() != ref["prior_mask"].numpy()).mean() < 2e-3
+        # carry the state forward exactly like the evaluation loop (sigmoid of the logits, test_bd.py:212-214)
+        prev_pred = torch.sigmoid(out["pred_0"])
+        prev_pred_ref = prev_pred.cpu()  # same state on both sides: the comparison stays per-frame
+        prev_pose = cur_c["cam_T_world_b44"]

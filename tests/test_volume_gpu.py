@@ -177,3 +177,30 @@ def test_error_behaviour():
     mgr2 = B200CostVolumeManager(4, 4, num_depth_bins=4).cuda()
     with pytest.raises(ValueError):
         mgr2(min_depth=mn, max_depth=mx, **t)
+
+
+@pytest.mark.parametrize("D", [16, 32, 128, 256])
+def test_plane_count_sweep_vs_oracle(D):
+    """BASELINE config 5: the plane count is a run-time size of both volume kernels (16 ... 256 planes)."""
+    B, K, h, w = 1, 7, 24, 32
+    inp = synthetic.make_volume_inputs(500 + D, B, K, 16, h, w)
+    t = dev(inp)
+    mn, mx = depth_range()
+    mgr = B200CostVolumeManager(h, w, num_depth_bins=D).cuda()
+    cost, lowest, planes_bdhw, _ = mgr(min_depth=mn, max_depth=mx, **t)
+    planes = planes_bdhw[0, :, 0, 0].cpu().numpy()
+    np.testing.assert_allclose(planes, O.generate_depth_planes(0.25, 5.0, D), rtol=1e-6)
+    ref, _, _ = O.cost_volume_dot(inp["cur_feats"], inp["src_feats"], inp["src_extrinsics"], inp["src_Ks"],
+                                  inp["cur_invK"], planes)
+    assert rel_err(cost.cpu().numpy(), ref) < TOL
+    np.testing.assert_array_equal(planes_to_idx(lowest.cpu().numpy(), planes), np.argmax(cost.cpu().numpy(), 1))
+    fv = B200FeatureVolumeManager(h, w, num_depth_bins=D, num_source_views=K).cuda()
+    torch.manual_seed(D)
+    for p in fv.parameters():
+        torch.nn.init.normal_(p, std=0.1)
+    W = [(fv.mlp.net[i].weight.detach().cpu().numpy(), fv.mlp.net[i].bias.detach().cpu().numpy()) for i in (0, 2, 4)]
+    vol, flow, _, mask = fv(min_depth=mn, max_depth=mx, return_mask=True, **t)
+    rvol, _, _, rmask = O.feature_volume_mlp(inp["cur_feats"], inp["src_feats"], inp["src_extrinsics"],
+                                             inp["src_poses"], inp["src_Ks"], inp["cur_invK"], planes, W)
+    assert rel_err(vol.cpu().numpy(), rvol) < TOL
+    np.testing.assert_array_equal(planes_to_idx(flow.cpu().numpy(), planes), np.argmax(vol.cpu().numpy(), 1))
