@@ -296,8 +296,11 @@ def main_b200(args):
         K_SRC, st.h, st.w))
     fv_flops = 2.0 * D_PLANES * N * (202 * 128 + 128 * 128 + 128) * B
     dotm = B200CostVolumeManager(st.h, st.w, num_depth_bins=D_PLANES).to(dev)
+    # the same features re-laid as texel records (gather layout 0, what cv_dot reads; csrc/common.cuh)
+    rec = st.feats_pm.view(-1, 4, N, 4).permute(0, 2, 1, 3).contiguous()
+    cur_rec, src_rec = rec[:B], rec[B:].view(B, K_SRC, N, -1)
     dot_ms = time_call(lambda: dotm.forward_pixel_major(
-        cur_pm, src_pm, extr, poses, src[f"K_s{ms_}_b44"], cur[f"invK_s{ms_}_b44"], model._mn, model._mx, None, False, B,
+        cur_rec, src_rec, extr, poses, src[f"K_s{ms_}_b44"], cur[f"invK_s{ms_}_b44"], model._mn, model._mx, None, False, B,
         K_SRC, st.h, st.w))
     dot_bytes = 4.0 * N * (16 * (K_SRC + 1) + D_PLANES) * B  # compulsory HBM bytes
     roofline = {"kernel": "fv_tc_kernel (fused warp + metadata MLP, tcgen05)", "bound": "tensor",

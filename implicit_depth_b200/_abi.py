@@ -19,12 +19,13 @@ c_ll = ctypes.c_longlong
 # name -> argument types (return type is always int, 0 = ok)
 SIGNATURES = {
     "b200_volume_prepare": [c_f] * 12 + [c_i] * 4 + [ctypes.c_void_p],
-    "b200_feats_to_pixel_major": [c_f, c_f, c_i, c_i, c_i, c_ll, c_ll, ctypes.c_void_p],
+    "b200_feats_to_pixel_major": [c_f, c_f, c_i, c_i, c_i, c_ll, c_ll, c_i, ctypes.c_void_p],
     "b200_volume_argmax": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
     "b200_cv_dot": [c_f] * 7 + [c_i] * 6 + [ctypes.c_void_p],
     "b200_fv_mlp_simt": [c_f] * 13 + [c_i] * 7 + [ctypes.c_void_p],
     "b200_fv_mlp_tc": [c_f] * 12 + [c_i] * 6 + [ctypes.c_void_p],
     "b200_fv_tc_wimage_bytes": [c_i],
+    "b200_fv_tc_layout": [c_i, ctypes.c_void_p],
     "b200_conv_create": [ctypes.c_void_p, ctypes.c_void_p],
     "b200_conv_run": [ctypes.c_void_p, ctypes.c_void_p],
     "b200_conv_destroy": [ctypes.c_void_p],
@@ -34,7 +35,7 @@ SIGNATURES = {
     "b200_f32_to_split": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_ll, c_ll, c_ll, c_ll, ctypes.c_void_p],
     "b200_split_to_nchw": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, ctypes.c_void_p],
     "b200_upsample2x": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, ctypes.c_void_p],
-    "b200_instance_norm": [c_f] * 7 + [c_i] * 6 + [ctypes.c_float, ctypes.c_float, ctypes.c_void_p],
+    "b200_instance_norm": [c_f] * 7 + [c_i] * 6 + [ctypes.c_float, ctypes.c_float, c_i, ctypes.c_void_p],
     "b200_instance_norm_ws_bytes": [c_i, c_i, ctypes.c_void_p, ctypes.c_void_p],
     "b200_stem_conv7": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
     "b200_stem_conv7_tc": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
@@ -71,6 +72,8 @@ def load():
     lib.b200_last_error.restype = ctypes.c_char_p
     lib.b200_abi_version.restype = ctypes.c_int
     lib.b200_conv_wimage_bytes.restype = ctypes.c_longlong
+    lib.b200_fv_tc_layout.argtypes = [c_i, ctypes.c_void_p]
+    lib.b200_fv_tc_layout.restype = ctypes.c_int
     _lib = lib
     return lib
 

@@ -154,7 +154,8 @@ class B200BDModel(nn.Module):
         D = self.run_opts.matching_num_depth_bins
         slots = {}
         pre = Plan(dev)  # matching encoder
-        feats_pm, h, w = self.matching_model.plan(pre, lambda: slots["images"], B * (K + 1), H, W)
+        feats_pm, h, w = self.matching_model.plan(pre, lambda: slots["images"], B * (K + 1), H, W,
+                                                  feat_layout=self.cost_volume.FEAT_LAYOUT)
         post = Plan(dev)  # cost-volume encoder, decoder, binary MLP
         enc_ch = list(self.encoder.num_ch_enc)
         img_feats = [post.from_f32((lambda i=i: slots["enc"][i]), B, enc_ch[i], H // 2 ** (i + 1), W // 2 ** (i + 1))
@@ -170,7 +171,7 @@ class B200BDModel(nn.Module):
             pred = self.binary_mlp.plan_val(post, res[0], lambda: slots["rendered_depth"], P,
                                             get_prior=(lambda: slots.get("prior")))
         return SimpleNamespace(slots=slots, pre=pre, post=post, feats_pm=feats_pm, h=h, w=w, pred=pred,
-                               search_depths=search_depths)
+                               search_depths=search_depths, feat_layout=self.cost_volume.FEAT_LAYOUT)
 
     def num_kernel_launches(self, B, K, H, W, P, search=False):
         """Hand-written kernel launches per forward for this signature (matching encoder + volume + nets)."""
@@ -187,7 +188,7 @@ class B200BDModel(nn.Module):
         H, W = cur_image.shape[-2:]
         P = rendered_depth.shape[1]
         key = (B, K, H, W, P, search)
-        if key not in self._state:
+        if key not in self._state or self._state[key].feat_layout != self.cost_volume.FEAT_LAYOUT:
             self._state = {key: self._build(B, K, H, W, P, cur_image.device, search)}
         st = self._state[key]
         # relative poses, bd_model.py:196-204

@@ -84,8 +84,10 @@ def _as_f32c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def _pixel_major(feats, n_img, C, h, w):
-    """[..., C, h, w] (any batch strides, dense planes) -> [n_img, h*w, C] via the layout kernel."""
+def _pixel_major(feats, n_img, C, h, w, layout=0):
+    """[..., C, h, w] (any batch strides, dense planes) -> one of the kernels' gather layouts (csrc/common.cuh) via
+    the layout kernel: 0 = texel records [n_img, h*w, C] (dot-product kernel), 1 = quarter-planar
+    [n_img, C/4, h*w, 4] (feature-volume kernels; returned as an opaque buffer of the same shape)."""
     if feats.dtype != torch.float32:
         feats = feats.float()
     f = feats.reshape(n_img, C, h, w) if feats.dim() != 4 else feats
@@ -94,12 +96,14 @@ def _pixel_major(feats, n_img, C, h, w):
     # images must be evenly strided
     out = torch.empty((n_img, h * w, C), device=f.device, dtype=torch.float32)
     _abi.call("b200_feats_to_pixel_major", _abi.ptr(f), _abi.ptr(out), n_img, C, h * w,
-              f.stride(0) if n_img > 1 else C * h * w, f.stride(1), _abi.stream_ptr())
+              f.stride(0) if n_img > 1 else C * h * w, f.stride(1), layout, _abi.stream_ptr())
     return out
 
 
 class B200CostVolumeManager(nn.Module):
     """Dot-product plane-sweep volume; drop-in for `CostVolumeManager` / `EfficientCostVolumeManager`."""
+
+    FEAT_LAYOUT = 0  # gather layout `forward_pixel_major` expects (csrc/common.cuh)
 
     def __init__(self, matching_height, matching_width, num_depth_bins=64, matching_dim_size=None,
                  num_source_views=None):
@@ -167,9 +171,9 @@ class B200CostVolumeManager(nn.Module):
                 depth_planes_bdhw=None, return_mask=False):
         _abi.require_cuda(cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK)
         B, K, C, h, w = self._check_shapes(cur_feats, src_feats)
-        cur_pm = _pixel_major(cur_feats, B, C, h, w)
+        cur_pm = _pixel_major(cur_feats, B, C, h, w, self.FEAT_LAYOUT)
         src_pm = _pixel_major(src_feats.reshape(B * K, C, h, w) if src_feats.is_contiguous()
-                              else src_feats.contiguous().view(B * K, C, h, w), B * K, C, h, w)
+                              else src_feats.contiguous().view(B * K, C, h, w), B * K, C, h, w, self.FEAT_LAYOUT)
         return self.forward_pixel_major(cur_pm, src_pm, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth,
                                         max_depth, depth_planes_bdhw, return_mask, B, K, h, w)
 
@@ -196,6 +200,8 @@ class B200CostVolumeManager(nn.Module):
 
 class B200FeatureVolumeManager(B200CostVolumeManager):
     """Metadata-MLP feature volume; drop-in for `FeatureVolumeManager` / `FastFeatureVolumeManager`."""
+
+    FEAT_LAYOUT = 1
 
     def __init__(self, matching_height, matching_width, num_depth_bins=64, mlp_channels=None, matching_dim_size=16,
                  num_source_views=7, impl="auto"):
@@ -231,6 +237,24 @@ class B200FeatureVolumeManager(B200CostVolumeManager):
         perm += [off_zd]
         return perm
 
+    @staticmethod
+    def tc_channel_layout(K, C=FEAT_C):
+        """K-dimension layout of the tensor-core kernel (csrc/fv_tc.cu): reference channel index of every kernel
+        channel, -1 for zero padding.  Role A builds views 0..KA-1 + cur[0..7], role B the other views +
+        cur[8..15], the current ray and z_d; each role is padded to whole 32-channel halves."""
+        import ctypes
+
+        out = (ctypes.c_int * 4)()
+        _abi.load().b200_fv_tc_layout(K, out)
+        KA, HA, HB, nchunk = out[0], out[1], out[2], out[3]
+        ref = B200FeatureVolumeManager.channel_permutation(K, C)  # view-major order: K view blocks, then the tail
+        view = lambda k: ref[k * VIEW_CH:(k + 1) * VIEW_CH]
+        tail = ref[K * VIEW_CH:]  # cur[0..15], curray[0..2], z_d
+        a = [c for k in range(KA) for c in view(k)] + tail[:8]
+        b = [c for k in range(KA, K) for c in view(k)] + tail[8:]
+        assert len(a) <= 32 * HA and len(b) <= 32 * HB and HA + HB == 2 * nchunk
+        return a + [-1] * (32 * HA - len(a)) + b + [-1] * (32 * HB - len(b))
+
     def _pack(self, device):
         lin = [self.mlp.net[0], self.mlp.net[2], self.mlp.net[4]]
         key = tuple((p.data_ptr(), p._version) for l in lin for p in (l.weight, l.bias)) + (str(device),)
@@ -243,9 +267,9 @@ class B200FeatureVolumeManager(B200CostVolumeManager):
         KP = (kin + 15) // 16 * 16
         W1p = torch.zeros((KP, MLP_HID), device=device, dtype=torch.float32)
         W1p[:kin] = W1[:, perm].t()
-        kc = (kin + 63) // 64 * 64
-        W1n = torch.zeros((MLP_HID, kc), device=device, dtype=torch.float32)
-        W1n[:, :kin] = W1[:, perm]
+        layout = torch.tensor(self.tc_channel_layout(K), device=device, dtype=torch.long)
+        W1n = torch.zeros((MLP_HID, layout.numel()), device=device, dtype=torch.float32)
+        W1n[:, layout >= 0] = W1[:, layout[layout >= 0]]
         W2 = lin[1].weight.detach().to(device=device, dtype=torch.float32)
         h1, l1 = split_bf16(W1n)
         h2, l2 = split_bf16(W2)

@@ -20,6 +20,16 @@
 #define CAM_T 21
 #define CAM_POSE 24
 
+// Matching features reach the volume kernels in one of two fp32 gather layouts (C = 16):
+//   layout 0, texel records [image][N][16]: one 64-byte record per texel.  The quad-per-pixel gather of cv_dot
+//     (lane j = channels 4j..4j+3) reads 8 neighbouring records = 512 contiguous bytes per LDG.128.
+//   layout 1, quarter-planar [image][C/4][N][4]: four planes of float4 per image.  The thread-per-row gather of
+//     the feature-volume kernels reads 32 neighbouring float4 of ONE plane per LDG.128 (512 contiguous bytes when
+//     neighbouring pixels sample neighbouring texels, ~4 L1 wavefronts) where texel records cost it 16 lines.
+// (Measured: cv_dot on layout 1 is 2x slower, fv_tc on layout 0 1.2x slower.)
+#define FEAT_Q 4                       // channels per plane
+#define FEAT_NQ (B200_FEAT_C / FEAT_Q)  // planes per image
+
 // error plumbing for the C ABI: entry points return 0 or a negative code and keep a message.
 extern "C" const char* b200_last_error(void);
 void b200_set_error(const char* fmt, ...);

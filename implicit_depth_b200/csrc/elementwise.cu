@@ -197,11 +197,11 @@ __global__ void instnorm_final_kernel(const double* __restrict__ partial, float*
 }
 // apply: y = (x - mean) * rstd, optional LeakyReLU; output either split NHWC with a replicated border of
 // `pad` pixels (feeds the padding_mode="replicate" conv of networks.py:279-282 as a plain valid conv) or
-// fp32 pixel-major [B, HW, C] (the matching features the volume kernels gather).
+// fp32 matching features in one of the two gather layouts of the volume kernels (common.cuh).
 __global__ void instnorm_apply_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                                       const float* __restrict__ stats, __nv_bfloat16* __restrict__ oh,
                                       __nv_bfloat16* __restrict__ ol, float* __restrict__ of32, int B, int H, int W,
-                                      int C, int pad, int act, float slope) {
+                                      int C, int pad, int act, float slope, int qplanar) {
   const int cg = C >> 3;
   const int OH = H + 2 * pad, OW = W + 2 * pad;
   const size_t total = (size_t)B * OH * OW * cg;
@@ -224,16 +224,21 @@ __global__ void instnorm_apply_kernel(const __nv_bfloat16* __restrict__ hi, cons
     }
     const size_t o = (((size_t)b * OH + oy) * OW + ox) * C + c8 * 8;
     if (oh) store8(oh, ol, o, v);
-    if (of32) {
+    if (of32 && !qplanar) {  // texel records [B, H*W, C]
       *reinterpret_cast<float4*>(of32 + o) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(of32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else if (of32) {  // quarter-planar fp32 [B, C/4, H*W, 4] (common.cuh); pad == 0 here
+      const size_t npix = (size_t)OH * OW, pix = (size_t)oy * OW + ox;
+      float* q0 = of32 + (((size_t)b * (C >> 2) + 2 * c8) * npix + pix) * 4;
+      *reinterpret_cast<float4*>(q0) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(q0 + npix * 4) = make_float4(v[4], v[5], v[6], v[7]);
     }
   }
 }
 
 extern "C" int b200_instance_norm(const void* in_hi, const void* in_lo, double* partial_ws, float* stats_ws,
                                   void* out_hi, void* out_lo, float* out_f32, int B, int H, int W, int C, int pad,
-                                  int act, float slope, float eps, void* stream) {
+                                  int act, float slope, float eps, int f32_layout, void* stream) {
   B200_CHECK_ARG(in_hi && in_lo && partial_ws && stats_ws && (out_hi || out_f32), "instance_norm: null pointer");
   B200_CHECK_ARG(C % 8 == 0 && C <= 1024, "instance_norm: C must be a multiple of 8, at most 1024 (got %d)", C);
   B200_CHECK_ARG(!(out_f32 && pad != 0), "instance_norm: fp32 output has no border");
@@ -246,7 +251,7 @@ extern "C" int b200_instance_norm(const void* in_hi, const void* in_lo, double* 
   if (blocks > 148 * 16) blocks = 148 * 16;
   instnorm_apply_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo, stats_ws,
                                                (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32, B, H, W, C,
-                                               pad, act, slope);
+                                               pad, act, slope, f32_layout);
   B200_CHECK_LAUNCH("instance_norm");
   return 0;
 }

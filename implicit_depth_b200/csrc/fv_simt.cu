@@ -76,10 +76,10 @@ fv_simt_kernel(const float* __restrict__ cur, const float* __restrict__ src, con
     const int y = p / w, x = p - y * w;
     const PixelCtx pc = make_pixel_ctx(x, y, invk_s);
     float c16[16];
-    const float* cp = cur + ((size_t)b * N + p) * B200_FEAT_C;
+    const float* cp = cur + (size_t)b * N * B200_FEAT_C + (size_t)p * FEAT_Q;  // quarter-planar (common.cuh)
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-      const float4 t4 = ldg4(cp + 4 * v);
+      const float4 t4 = ldg4(cp + (size_t)v * N * FEAT_Q);
       c16[4 * v] = t4.x; c16[4 * v + 1] = t4.y; c16[4 * v + 2] = t4.z; c16[4 * v + 3] = t4.w;
     }
     float* arow = a_s + row * lda;

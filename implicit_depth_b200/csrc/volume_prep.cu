@@ -1,5 +1,5 @@
 // Small set-up kernels of the plane-sweep path: camera records, depth planes, hoisted
-// MLP bias, layout change to pixel-major features, arg-max over planes.
+// MLP bias, layout change to the quarter-planar gather layout, arg-max over planes.
 #include <stdarg.h>
 
 #include "common.cuh"
@@ -116,12 +116,11 @@ extern "C" int b200_volume_prepare(const float* src_Ks, const float* src_extrins
 }
 
 // ---------------------------------------------------------------------------------------
-// [n_img, C, HW] (strided planes) -> [n_img, HW, C] pixel-major, C = 16: one 64-byte record
-// per texel, the unit the warp kernels gather.  32x16 tile through shared memory so both
-// sides are coalesced.
+// [n_img, C, HW] (strided planes) -> texel records [n_img, HW, C] (layout 0, cv_dot) or quarter-planar
+// [n_img, C/4, HW, 4] (layout 1, feature-volume kernels; common.cuh), C = 16.  32x16 tile through shared memory so both sides are coalesced.
 // ---------------------------------------------------------------------------------------
 __global__ void nchw_to_pixel_major_kernel(const float* __restrict__ in, float* __restrict__ out, int HW,
-                                           long long img_stride, long long ch_stride) {
+                                           long long img_stride, long long ch_stride, int qplanar) {
   __shared__ float tile[B200_FEAT_C][33];
   int img = blockIdx.y;
   int p0 = blockIdx.x * 32;
@@ -131,19 +130,24 @@ __global__ void nchw_to_pixel_major_kernel(const float* __restrict__ in, float* 
     tile[c][p] = (p0 + p < HW) ? src[(size_t)c * ch_stride + p0 + p] : 0.f;
   }
   __syncthreads();
-  float* dst = out + ((size_t)img * HW + p0) * B200_FEAT_C;
+  float* dst = out + (size_t)img * HW * B200_FEAT_C;
   for (int i = threadIdx.x; i < B200_FEAT_C * 32; i += blockDim.x) {
-    int p = i / B200_FEAT_C, c = i % B200_FEAT_C;
-    if (p0 + p < HW) dst[i] = tile[c][p];
+    if (qplanar) {
+      int q = i / (32 * FEAT_Q), p = (i / FEAT_Q) % 32, cc = i % FEAT_Q;
+      if (p0 + p < HW) dst[((size_t)q * HW + p0 + p) * FEAT_Q + cc] = tile[q * FEAT_Q + cc][p];
+    } else {
+      int p = i / B200_FEAT_C, c = i % B200_FEAT_C;
+      if (p0 + p < HW) dst[(size_t)(p0 + p) * B200_FEAT_C + c] = tile[c][p];
+    }
   }
 }
 
 extern "C" int b200_feats_to_pixel_major(const float* in, float* out, int n_img, int C, int HW,
-                                         long long img_stride, long long ch_stride, void* stream) {
+                                         long long img_stride, long long ch_stride, int layout, void* stream) {
   B200_CHECK_ARG(C == B200_FEAT_C, "feats_to_pixel_major: only %d channels supported (got %d)", B200_FEAT_C, C);
   B200_CHECK_ARG(in && out && n_img > 0 && HW > 0, "feats_to_pixel_major: bad arguments");
   dim3 grid((HW + 31) / 32, n_img);
-  nchw_to_pixel_major_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, HW, img_stride, ch_stride);
+  nchw_to_pixel_major_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, HW, img_stride, ch_stride, layout);
   B200_CHECK_LAUNCH("feats_to_pixel_major");
   return 0;
 }

@@ -103,7 +103,7 @@ class Plan:
                                    a.W, _abi.stream_ptr()))
         return out
 
-    def instance_norm(self, a, pad=0, act="none", slope=LRELU, eps=1e-5, f32_pixel_major=False):
+    def instance_norm(self, a, pad=0, act="none", slope=LRELU, eps=1e-5, f32_pixel_major=False, f32_layout=0):
         partial = self.empty((a.B, 32, a.C, 2), torch.float64)
         stats = self.empty((a.B, a.C, 2))
         out = None if f32_pixel_major else self.act(a.B, a.H + 2 * pad, a.W + 2 * pad, a.C)
@@ -111,7 +111,8 @@ class Plan:
         self.add(lambda: _abi.call("b200_instance_norm", _abi.ptr(a.hi), _abi.ptr(a.lo), _abi.ptr(partial),
                                    _abi.ptr(stats), _abi.ptr(out.hi) if out else None,
                                    _abi.ptr(out.lo) if out else None, _abi.ptr(out32), a.B, a.H, a.W, a.C, pad,
-                                   1 if act == "lrelu" else 0, slope, eps, _abi.stream_ptr()), launches=3)
+                                   1 if act == "lrelu" else 0, slope, eps, f32_layout, _abi.stream_ptr()),
+                 launches=3)
         return out if out is not None else out32
 
 
@@ -428,8 +429,9 @@ class ResnetMatchingEncoder(_PlannedModule):
             nn.InstanceNorm2d(num_ch_out),
         )
 
-    def plan(self, g: Plan, get_images, n, H, W):
-        """Returns the fp32 pixel-major feature tensor [n, (H/4)*(W/4), C] the volume kernels consume."""
+    def plan(self, g: Plan, get_images, n, H, W, feat_layout=0):
+        """Returns the fp32 pixel-major feature buffer [n, (H/4)*(W/4), C] the volume kernels consume, in gather layout
+        `feat_layout` (csrc/common.cuh: 0 = texel records, 1 = quarter-planar)."""
         net = self.net
         dev = g.device
         w7, b7 = _fold_bn(net[0].weight, net[1])
@@ -467,7 +469,7 @@ class ResnetMatchingEncoder(_PlannedModule):
         x, _ = g.conv([(x, net[5].weight, 1, 0)], net[5].bias, 128, act="none")
         x = g.instance_norm(x, pad=1, act="lrelu", slope=0.2, eps=net[6].eps)  # replicate border for net[8]
         x, _ = g.conv([(x, net[8].weight, 1, 0)], net[8].bias, self.num_ch_out, act="none")
-        return g.instance_norm(x, eps=net[9].eps, f32_pixel_major=True), H4, W4
+        return g.instance_norm(x, eps=net[9].eps, f32_pixel_major=True, f32_layout=feat_layout), H4, W4
 
     @torch.no_grad()
     def forward(self, input_image):

@@ -7,7 +7,9 @@
  *     synchronisation), so they can sit between the CUDA events of test_bd.py:196-212;
  *   - return value 0 = ok; negative = error (-1 bad argument, -2 CUDA error), message via
  *     b200_last_error().  Nothing aborts.
- *   - "pixel-major" features: [n_images, h*w, 16], i.e. one 64-byte record per texel.
+ *   - "pixel-major" features come in two gather layouts: layout 0 = texel records [n_images, h*w, 16] (one 64-byte
+ *     record per texel; consumed by b200_cv_dot), layout 1 = quarter-planar [n_images, 4, h*w, 4] (channels
+ *     4q..4q+3 of texel t at ((img*4 + q)*h*w + t)*4; consumed by b200_fv_mlp_*).
  *
  * Citations are file:line in the reference repository (nianticlabs/implicit-depth).
  */
@@ -36,9 +38,9 @@ int b200_volume_prepare(const float* src_Ks, const float* src_extrinsics, const 
                         const float* planes_in, const float* W1, const float* b1, float* cams, float* planes,
                         float* bias_eff, int B, int K, int D, int C, void* stream);
 
-/* [n_img, C=16, HW] planes (image stride / channel stride in elements) -> pixel-major. */
+/* [n_img, C=16, HW] planes (image stride / channel stride in elements) -> pixel-major, layout 0 | 1 (see top). */
 int b200_feats_to_pixel_major(const float* in, float* out, int n_img, int C, int HW, long long img_stride,
-                              long long ch_stride, void* stream);
+                              long long ch_stride, int layout, void* stream);
 
 /* argmax over planes (first maximum, modules/cost_volume.py:352-356) + gather of the plane depth.
  *   vol [B,D,N]; planes [B,D]; out: lowest [B,N] float, best_idx [B,N] int32 or NULL. */
@@ -49,7 +51,7 @@ int b200_volume_argmax(const float* vol, const float* planes, float* lowest, int
  * (modules/cost_volume.py:221-358) / EfficientCostVolumeManager (:1245-1304):
  * warp (grid_sample bilinear/zeros/align_corners=False, :192-198), dot with the current
  * features, sum over views (:302-311), argmax + depth gather (:352-356).
- *   cur [B,N,16], src [B,K,N,16] pixel-major; cams/planes from b200_volume_prepare;
+ *   cur [B,N,16], src [B,K,N,16] pixel-major layout 0; cams/planes from b200_volume_prepare;
  *   out: cost [B,D,h,w]; lowest [B,h,w] or NULL; best_idx [B,h,w] int32 or NULL. */
 int b200_cv_dot(const float* cur, const float* src, const float* cams, const float* planes, float* cost,
                 float* lowest, int* best_idx, int B, int K, int C, int h, int w, int D, void* stream);
@@ -77,6 +79,10 @@ int b200_fv_mlp_tc(const float* cur, const float* src, const float* cams, const 
                    const float* w3, const float* b3, float* vol, unsigned char* mask_out, int B, int K, int C,
                    int h, int w, int D, void* stream);
 int b200_fv_tc_wimage_bytes(int K);
+/* K-dimension layout of that image: out[0] = views built by role A (the rest by role B), out[1] / out[2] =
+ * 32-channel halves of role A / B, out[3] = 64-channel chunks; returns the image size in bytes
+ * (implicit_depth_b200/cost_volume.py: tc_channel_layout turns it into the column permutation of W1). */
+int b200_fv_tc_layout(int K, int* out);
 
 /* ---- tensor-core convolution (csrc/conv_tc.cu) ------------------------------------------------
  * Implicit-GEMM conv over NHWC split-bf16 activations (two bf16 planes hi/lo with x = hi + lo).
@@ -125,11 +131,11 @@ int b200_split_to_nchw(const void* hi, const void* lo, float* out, int B, int C,
 int b200_upsample2x(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int B, int H, int W, int C,
                     int mode, void* stream);
 /* nn.InstanceNorm2d (affine=False, biased variance; modules/networks.py:277,283) + optional LeakyReLU;
- * out = split NHWC with a replicated border of `pad` pixels, and/or fp32 pixel-major [B,H*W,C] (pad 0).
+ * out = split NHWC with a replicated border of `pad` pixels, and/or fp32 pixel-major in layout `f32_layout` (pad 0).
  * Workspaces sized by b200_instance_norm_ws_bytes. Deterministic, batch-invariant reduction. */
 int b200_instance_norm(const void* in_hi, const void* in_lo, double* partial_ws, float* stats_ws, void* out_hi,
                        void* out_lo, float* out_f32, int B, int H, int W, int C, int pad, int act, float slope,
-                       float eps, void* stream);
+                       float eps, int f32_layout, void* stream);
 int b200_instance_norm_ws_bytes(int B, int C, long long* partial_bytes, long long* stats_bytes);
 /* Matching-encoder stem conv 7x7/2 (3->64, BatchNorm folded) + ReLU (modules/networks.py:264-266):
  * img fp32 NCHW [n,3,H,W]; wt [147,64] tap-major (c,dy,dx); out NHWC split [n,H/2,W/2,64]. */

@@ -17,12 +17,14 @@ def timeit(fn, n=10):
         a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     ts.sort(); return ts[len(ts)//2]
-cur_pm = _pixel_major(t["cur_feats"], B, C, h, w)
-src_pm = _pixel_major(t["src_feats"].reshape(B * K, C, h, w), B * K, C, h, w)
+pm = lambda layout: (_pixel_major(t["cur_feats"], B, C, h, w, layout),
+                     _pixel_major(t["src_feats"].reshape(B * K, C, h, w), B * K, C, h, w, layout))
+cur_pm, src_pm = pm(0)
 geo = (t["src_extrinsics"], t["src_poses"], t["src_Ks"], t["cur_invK"], mn, mx, None)
 dot = B200CostVolumeManager(h, w, num_depth_bins=D).cuda()
 print("dot manager (layout + prep + kernel) ms:", timeit(lambda: dot(min_depth=mn, max_depth=mx, **t)))
 print("dot pixel-major (prep + kernel) ms:", timeit(lambda: dot.forward_pixel_major(cur_pm, src_pm, *geo, False, B, K, h, w)))
+cur_pm, src_pm = pm(1)
 for impl in ("tc", "simt"):
     if impl == "simt" and os.environ.get("NO_SIMT"): continue
     fv = B200FeatureVolumeManager(h, w, num_depth_bins=D, impl=impl).cuda()

@@ -95,3 +95,22 @@ def test_channel_permutation_is_a_permutation_of_the_variable_channels():
         const = set(range(16 * (K + 1), 16 * (K + 1) + K)) | set(range(cin - 3 * K, cin))
         assert len(perm) == 22 * K + 20 == len(set(perm))
         assert set(perm) | const == set(range(cin)) and not (set(perm) & const)
+
+
+def test_tc_channel_layout_covers_every_variable_channel_once():
+    """K-dimension layout of the tensor-core feature-volume kernel: every (pixel, plane)-dependent reference channel
+    appears exactly once, padding only at the end of each role's share, whole 64-channel chunks."""
+    from implicit_depth_b200 import B200FeatureVolumeManager
+
+    for K in range(1, 9):
+        ref = B200FeatureVolumeManager.channel_permutation(K)
+        lay = B200FeatureVolumeManager.tc_channel_layout(K)
+        real = [c for c in lay if c >= 0]
+        assert sorted(real) == sorted(ref) and len(lay) % 64 == 0
+        assert _abi_bytes(K) == (2 * (len(lay) // 64) + 4) * 16384
+
+
+def _abi_bytes(K):
+    from implicit_depth_b200 import _abi
+
+    return _abi.load().b200_fv_tc_wimage_bytes(K)
