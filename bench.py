@@ -29,6 +29,12 @@ METRIC = "frames/sec (512x384, 7 src views, 64 planes)"
 WORKLOAD = "cfg2: B=4 per GPU, 512x384, 7 source views, 64 depth planes, implicit_depth.yaml (mlp_feature_volume, unet_pp), random weights"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2 (B=4) from the committed `ncu --set full` captures
+# (the cost volume written by either kernel stays in the 126 MB L2 for the consuming kernel, hence ~ the input bytes)
+NCU_SOURCE = "profiles/r01c_ncu_full_volume.md"
+NCU_DRAM_BYTES = {"fv_tc_kernel": 23.8e6, "cv_dot_kernel": 23.6e6}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -108,6 +114,12 @@ def cpu_reference_run(steps, warmup, budget_s=240.0):
     from oracle import networks as ON  # the only place bench.py executes oracle/: the CPU baseline
 
     torch.set_grad_enabled(False)
+    # all the host threads this process may use (torchrun pins OMP_NUM_THREADS=1 for its workers: undo that here)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(max(1, avail))
     cores = torch.get_num_threads()
     opts = default_options(image_width=IMAGE_W, image_height=IMAGE_H, matching_num_depth_bins=D_PLANES)
     model = B200BDModel(opts)  # parameter container only (CPU); never called
@@ -172,10 +184,11 @@ def main_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # keeps NCCL's banner off stdout (one JSON line)
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     _abi.load()
     torch.set_grad_enabled(False)
-    # strict fp32 for the out-of-scope cuDNN image encoder, like the reference's fp32 test path
     opts = default_options(image_width=IMAGE_W, image_height=IMAGE_H, matching_num_depth_bins=D_PLANES)
     model = B200BDModel(opts)
     synthetic.init_model_weights(model, seed=0)
@@ -305,12 +318,14 @@ def main_b200(args):
     dot_bytes = 4.0 * N * (16 * (K_SRC + 1) + D_PLANES) * B  # compulsory HBM bytes
     roofline = {"kernel": "fv_tc_kernel (fused warp + metadata MLP, tcgen05)", "bound": "tensor",
                 "achieved": fv_flops / (fv_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": fv_flops / (fv_ms * 1e-3) / 1e12 / tf_peak, "traffic": None, "ms_per_launch": fv_ms,
+                "frac": fv_flops / (fv_ms * 1e-3) / 1e12 / tf_peak, "traffic": NCU_DRAM_BYTES["fv_tc_kernel"],
+                "traffic_source": NCU_SOURCE, "ms_per_launch": fv_ms,
                 "algorithmic_flops_per_launch": fv_flops, "peak_source": peak_src + ", bf16 burst",
                 "note": "algorithmic fp32 FLOPs of the reference MLP; the kernel issues 3 bf16 MMAs per product"}
     roofline_dot = {"kernel": "cv_dot_kernel (fused warp + dot + view-sum + argmax)", "bound": "hbm",
                     "achieved": dot_bytes / (dot_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": dot_bytes / (dot_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "ms_per_launch": dot_ms,
+                    "frac": dot_bytes / (dot_ms * 1e-3) / 1e9 / hbm_peak, "traffic": NCU_DRAM_BYTES["cv_dot_kernel"],
+                    "traffic_source": NCU_SOURCE, "ms_per_launch": dot_ms,
                     "algorithmic_bytes_per_launch": dot_bytes, "peak_source": peak_src,
                     "secondary_gather_GBps": 4.0 * 16 * 4 * K_SRC * D_PLANES * N * B / (dot_ms * 1e-3) / 1e9}
 
@@ -319,7 +334,11 @@ def main_b200(args):
     stage_ms = {}
     try:
         cur_image, src_image = cur["image_b3hw"], src["image_b3hw"]
-        stage_ms["image_encoder_cudnn"] = time_call(lambda: model.encoder(cur_image), 5)
+        if st.encp is not None:
+            st.slots["cur_image"] = cur_image
+            stage_ms["image_encoder"] = time_call(st.encp.run, 5)
+        else:
+            stage_ms["image_encoder_torch"] = time_call(lambda: model.encoder(cur_image), 5)
         st.slots["images"] = torch.cat([cur_image, src_image.reshape(B * K_SRC, 3, IMAGE_H, IMAGE_W)], 0).contiguous()
         stage_ms["matching_encoder"] = time_call(st.pre.run, 5)
         stage_ms["feature_volume"] = fv_ms
@@ -330,7 +349,7 @@ def main_b200(args):
     model.use_cuda_graph = not args.no_graph
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # rank 0 at N=1 only
         try:
             r = cpu_reference_run(steps=2, warmup=1, budget_s=30.0)
             cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -346,7 +365,9 @@ def main_b200(args):
                          "the per-step CUDA-event brackets",
                    "timing": "sum of per-step CUDA-event durations, max over ranks",
                    "cuda_graph": not args.no_graph,
-                   "image_encoder": "torchvision EfficientNetV2-S features via cuDNN (out of scope, SURVEY 2 row 20)"},
+                   "image_encoder": "EfficientNetV2-S (torchvision layout) on the hand-written conv / MBConv kernels, "
+                                    "fp32-grade split-bf16 like the rest of the forward (cuDNN TF32 would put pred_0 "
+                                    "1.7e-2 off the fp32 reference)"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "how": "FramePipeline: pinned host dicts -> H2D -> forward -> D2H into pinned host memory every step, "
                        "copies of neighbouring steps overlapped with the forward on separate streams; one CUDA-event "

@@ -8,7 +8,7 @@ import torch
 
 from . import _abi
 
-ACT = {"none": 0, "lrelu": 1, "elu": 2, "relu": 3}
+ACT = {"none": 0, "lrelu": 1, "elu": 2, "relu": 3, "silu": 4}
 MAX_SEG = 4
 
 

@@ -68,6 +68,10 @@ __device__ __forceinline__ float leaky(float x, float slope) { return x >= 0.f ?
 // order one, far inside the 1e-3 parity budget, at 3 instructions instead of expm1f's ~50.
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
 
+// SiLU x * sigmoid(x) (EfficientNetV2 image encoder): SFU exp and reciprocal, relative error ~1e-6.
+__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+__device__ __forceinline__ float sigmoidf_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+
 // Projection of the pixel-centre ray through plane depth zd into one source view.
 // Mp = M @ (x+.5, y+.5, 1); returns source pixel coords and clamped depth
 // (geometry_utils.py:84-89: z = max(c_z, 1e-5), xy / z).

@@ -30,7 +30,7 @@
 #define CV_TW 16
 #define CV_MAX_SEG 4
 
-enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_ELU = 2, ACT_RELU = 3 };
+enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_ELU = 2, ACT_RELU = 3, ACT_SILU = 4 };
 
 struct ConvKParams {
   CUtensorMap maps[2 * CV_MAX_SEG];  // [2s] = hi plane, [2s+1] = lo plane of segment s
@@ -57,6 +57,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   if (act == ACT_LRELU) return v >= 0.f ? v : v * slope;
   if (act == ACT_RELU) return fmaxf(v, 0.f);
   if (act == ACT_ELU) return elu1(v);
+  if (act == ACT_SILU) return silu(v);
   return v;
 }
 
@@ -283,6 +284,12 @@ extern "C" int b200_conv_ntile(int Cout) { return Cout <= 128 ? Cout : 128; }
 extern "C" int b200_conv_uses_halo(const b200_conv_desc* d) {
   if (!d || getenv("B200_CONV_NO_HALO") != nullptr) return 0;
   if (d->Cout % 64 != 0 || d->out_f32 != nullptr || d->out_hi == nullptr) return 0;
+  // a pure 1x1 conv uses every halo patch for a single tap, so the halo kernel's 2-deep patch ring exposes the TMA
+  // latency of each 32-channel block (51 us for the 1536->256 project conv of the image encoder); the plain kernel
+  // streams 64-channel boxes through a 3..6-stage ring instead
+  bool all_1x1 = true;
+  for (int s = 0; s < d->nseg; ++s) all_1x1 = all_1x1 && d->seg[s].ksize == 1;
+  if (all_1x1 && getenv("B200_CONV_1X1_HALO") == nullptr) return 0;
   for (int s = 0; s < d->nseg; ++s) {
     const b200_conv_seg& sg = d->seg[s];
     const bool ok = sg.stride == 1 && ((sg.ksize == 3 && (sg.pad == 0 || sg.pad == 1)) || (sg.ksize == 1 && sg.pad == 0));

@@ -1,0 +1,233 @@
+// Memory-bound pieces of the EfficientNetV2 image encoder's MBConv blocks (torchvision efficientnet_v2_s layout,
+// the stand-in for timm's tf_efficientnetv2_s_in21ft1k at the reference call site bd_model.py:46-51), on NHWC
+// split-bf16 activations:
+//   dwconv3x3_kernel   depthwise 3x3 (stride 1|2, pad 1) + folded BatchNorm bias + SiLU
+//   se_pool_kernel     squeeze: per-(frame, channel) mean over the image, deterministic two-level reduction
+//   se_fc_kernel       excitation: fc1 + SiLU + fc2 + sigmoid -> scale[b, c]  (fc2 weights transposed)
+//   se_scale_kernel    x * scale[b, c]
+// The 1x1 expand / project convolutions and the fused 3x3 convolutions run on the tensor-core conv kernels.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+__device__ __forceinline__ float mb_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float mb_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ void mb_load8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t off, float v[8]) {
+  const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + off));
+  const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + off));
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e] = mb_lo(hw[e]) + mb_lo(lw[e]);
+    v[2 * e + 1] = mb_hi(hw[e]) + mb_hi(lw[e]);
+  }
+}
+__device__ __forceinline__ void mb_store8(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, const float v[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) tc::split2(v[2 * e], v[2 * e + 1], h[e], l[e]);
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ---------------------------------------------------------------------------------------
+// depthwise 3x3: one thread per (output pixel, 8 channels); weights [9][C] tap-major fp32.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dwconv3x3_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                 const float* __restrict__ wt, const float* __restrict__ bias, __nv_bfloat16* __restrict__ oh,
+                 __nv_bfloat16* __restrict__ ol, int B, int H, int W, int C, int stride, int OH, int OW) {
+  const int cg = C >> 3;
+  const size_t total = (size_t)B * OH * OW * cg;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg);
+    size_t r = i / cg;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const int b = (int)(r / OH);
+    float acc[8];
+    {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8 + 4));
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+      acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int y = oy * stride + dy - 1;
+      if (y < 0 || y >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int x = ox * stride + dx - 1;
+        if (x < 0 || x >= W) continue;
+        float v[8];
+        mb_load8(hi, lo, (((size_t)b * H + y) * W + x) * C + c8 * 8, v);
+        const float* wp = wt + (size_t)(dy * 3 + dx) * C + c8 * 8;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+        acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
+        acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
+        acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
+        acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = silu(acc[e]);
+    mb_store8(oh, ol, (((size_t)b * OH + oy) * OW + ox) * C + c8 * 8, acc);
+  }
+}
+
+extern "C" int b200_dwconv3x3_silu(const void* in_hi, const void* in_lo, const float* wt, const float* bias,
+                                   void* out_hi, void* out_lo, int B, int H, int W, int C, int stride, void* stream) {
+  B200_CHECK_ARG(in_hi && in_lo && wt && bias && out_hi && out_lo, "dwconv3x3: null pointer");
+  B200_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2),
+                 "dwconv3x3: bad arguments (C %% 8 == 0, stride 1|2; got C=%d stride=%d)", C, stride);
+  const int OH = (H + 2 - 3) / stride + 1, OW = (W + 2 - 3) / stride + 1;
+  const size_t total = (size_t)B * OH * OW * (C / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  dwconv3x3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo,
+                                                            wt, bias, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
+                                                            B, H, W, C, stride, OH, OW);
+  B200_CHECK_LAUNCH("dwconv3x3");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// squeeze: mean[b, c] over the HW pixels.  Block = (frame, 64 channels): 32 pixel lanes x 8 channel groups;
+// per-thread serial sums over a fixed pixel stride, then a fixed-order tree in shared memory (deterministic).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+se_pool_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, float* __restrict__ mean,
+               int HW, int C) {
+  __shared__ float red[32][65];
+  const int b = blockIdx.y, c0 = blockIdx.x * 64;
+  const int cgp = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c = c0 + cgp * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    for (int p = pl; p < HW; p += 32) {
+      float v[8];
+      mb_load8(hi, lo, ((size_t)b * HW + p) * C + c, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[pl][cgp * 8 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) s += red[r][threadIdx.x];
+    if (c0 + threadIdx.x < C) mean[(size_t)b * C + c0 + threadIdx.x] = s / (float)HW;
+  }
+}
+
+// excitation: block = (256-channel slice, frame).  w1 [S][C], b1 [S], w2t [S][C] (fc2 transposed: coalesced over
+// channels), b2 [C]  (fp32, S <= 128).  Every block recomputes the small fc1 (S x C MACs) for its frame.
+__global__ void __launch_bounds__(256)
+se_fc_kernel(const float* __restrict__ mean, const float* __restrict__ w1, const float* __restrict__ b1,
+             const float* __restrict__ w2t, const float* __restrict__ b2, float* __restrict__ scale, int C, int S) {
+  __shared__ float s1[128];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* m = mean + (size_t)b * C;
+  // fc1: a warp takes four rows at a time (four independent load streams sharing the mean vector)
+  for (int j0 = warp * 4; j0 < S; j0 += 32) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int c = lane; c < C; c += 32) {
+      const float mv = m[c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (j0 + i < S) acc[i] = fmaf(__ldg(w1 + (size_t)(j0 + i) * C + c), mv, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0 && j0 + i < S) s1[j0 + i] = silu(a + b1[j0 + i]);
+    }
+  }
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float acc = b2[c];
+#pragma unroll 8
+    for (int j = 0; j < S; ++j) acc = fmaf(__ldg(w2t + (size_t)j * C + c), s1[j], acc);
+    scale[(size_t)b * C + c] = sigmoidf_fast(acc);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+se_scale_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                const float* __restrict__ scale, __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol,
+                int B, int HW, int C) {
+  const int cg = C >> 3;
+  const size_t total = (size_t)B * HW * cg;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg);
+    const int b = (int)(i / ((size_t)HW * cg));
+    float v[8];
+    mb_load8(hi, lo, i * 8, v);
+    const float* sp = scale + (size_t)b * C + c8 * 8;
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(sp + 4));
+    v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
+    v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+    mb_store8(oh, ol, i * 8, v);
+  }
+}
+
+// Squeeze-and-excitation of one MBConv block (torchvision SqueezeExcitation: avgpool, fc1, SiLU, fc2, sigmoid, scale).
+// mean_ws / scale_ws: [B, C] fp32 workspaces.  In place when out == in.
+extern "C" int b200_squeeze_excite(const void* in_hi, const void* in_lo, const float* w1, const float* b1,
+                                   const float* w2t, const float* b2, float* mean_ws, float* scale_ws, void* out_hi,
+                                   void* out_lo, int B, int HW, int C, int S, void* stream) {
+  B200_CHECK_ARG(in_hi && in_lo && w1 && b1 && w2t && b2 && mean_ws && scale_ws && out_hi && out_lo,
+                 "squeeze_excite: null pointer");
+  B200_CHECK_ARG(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && S > 0 && S <= 128,
+                 "squeeze_excite: bad sizes (C %% 8 == 0, S <= 128; got C=%d S=%d)", C, S);
+  cudaStream_t st = (cudaStream_t)stream;
+  se_pool_kernel<<<dim3((C + 63) / 64, B), 256, 0, st>>>((const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo,
+                                                        mean_ws, HW, C);
+  se_fc_kernel<<<dim3((C + 255) / 256, B), 256, 0, st>>>(mean_ws, w1, b1, w2t, b2, scale_ws, C, S);
+  const size_t total = (size_t)B * HW * (C / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  se_scale_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo, scale_ws,
+                                         (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, B, HW, C);
+  B200_CHECK_LAUNCH("squeeze_excite");
+  return 0;
+}
+
+// a + b on split activations (8 channels per thread).
+__global__ void __launch_bounds__(256)
+split_add_kernel(const __nv_bfloat16* __restrict__ ah, const __nv_bfloat16* __restrict__ al,
+                 const __nv_bfloat16* __restrict__ bh, const __nv_bfloat16* __restrict__ bl,
+                 __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, size_t n8) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    mb_load8(ah, al, i * 8, a);
+    mb_load8(bh, bl, i * 8, b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] += b[e];
+    mb_store8(oh, ol, i * 8, a);
+  }
+}
+
+extern "C" int b200_split_add(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* out_hi,
+                              void* out_lo, long long n, void* stream) {
+  B200_CHECK_ARG(a_hi && a_lo && b_hi && b_lo && out_hi && out_lo && n > 0 && n % 8 == 0, "split_add: bad arguments");
+  const size_t n8 = (size_t)n / 8;
+  int blocks = (int)((n8 + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split_add_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)a_hi, (const __nv_bfloat16*)a_lo, (const __nv_bfloat16*)b_hi, (const __nv_bfloat16*)b_lo,
+      (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, n8);
+  B200_CHECK_LAUNCH("split_add");
+  return 0;
+}

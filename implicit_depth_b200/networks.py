@@ -118,9 +118,13 @@ class Plan:
 
 def _split_weight(w, parts):
     """Split a conv weight [Cout, sum(C_i), k, k] along its input channels like torch.cat's inputs."""
-    sizes = [p.C for p in parts]
+    sizes = [getattr(p, "Cl", p.C) for p in parts]  # logical channels (zero-padded activations carry p.C > p.Cl)
     assert sum(sizes) == w.shape[1], f"concat widths {sizes} do not match conv input {w.shape[1]}"
-    return list(torch.split(w.detach(), sizes, dim=1))
+    pieces = list(torch.split(w.detach(), sizes, dim=1))
+    for i, (p, piece) in enumerate(zip(parts, pieces)):
+        if p.C != piece.shape[1]:  # zero weight columns for the padding channels
+            pieces[i] = torch.cat([piece, piece.new_zeros((piece.shape[0], p.C - piece.shape[1]) + tuple(piece.shape[2:]))], 1)
+    return pieces
 
 
 # =====================================================================================

@@ -137,6 +137,21 @@ int b200_instance_norm(const void* in_hi, const void* in_lo, double* partial_ws,
                        void* out_lo, float* out_f32, int B, int H, int W, int C, int pad, int act, float slope,
                        float eps, int f32_layout, void* stream);
 int b200_instance_norm_ws_bytes(int B, int C, long long* partial_bytes, long long* stats_bytes);
+/* ---- EfficientNetV2 image-prior encoder (reference call site bd_model.py:46-51: timm tf_efficientnetv2_s,
+ * features_only; torchvision efficientnet_v2_s layout).  Its dense convolutions run on b200_conv_* (act 4 = SiLU);
+ * these are the memory-bound parts of the MBConv blocks, NHWC split-bf16 in and out. ---- */
+/* depthwise 3x3 (stride 1|2, pad 1) + bias (BatchNorm folded) + SiLU; wt [9][C] tap-major fp32. */
+int b200_dwconv3x3_silu(const void* in_hi, const void* in_lo, const float* wt, const float* bias, void* out_hi,
+                        void* out_lo, int B, int H, int W, int C, int stride, void* stream);
+/* SqueezeExcitation: mean over H*W -> fc1 w1 [S][C] + SiLU -> fc2 (transposed: w2t [S][C]) + sigmoid -> x * scale
+ * (in place when out == in).  mean_ws / scale_ws: [B,C] fp32.  Deterministic reduction. */
+int b200_squeeze_excite(const void* in_hi, const void* in_lo, const float* w1, const float* b1, const float* w2t,
+                        const float* b2, float* mean_ws, float* scale_ws, void* out_hi, void* out_lo, int B, int HW,
+                        int C, int S, void* stream);
+/* out = a + b on split activations of n elements (n % 8 == 0). */
+int b200_split_add(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* out_hi, void* out_lo,
+                   long long n, void* stream);
+
 /* Matching-encoder stem conv 7x7/2 (3->64, BatchNorm folded) + ReLU (modules/networks.py:264-266):
  * img fp32 NCHW [n,3,H,W]; wt [147,64] tap-major (c,dy,dx); out NHWC split [n,H/2,W/2,64]. */
 int b200_stem_conv7(const float* img, const float* wt, const float* bias, void* out_hi, void* out_lo, int n_img,

@@ -261,3 +261,30 @@ def test_cfg4_temporal_model_640x480_96_planes_vs_oracle():
         prev_pred = torch.sigmoid(out["pred_0"])
         prev_pred_ref = prev_pred.cpu()  # same state on both sides: the comparison stays per-frame
         prev_pose = cur_c["cam_T_world_b44"]
+
+
+def test_native_image_encoder_vs_torch_fp32():
+    """EfficientNetV2-S image encoder on the hand-written kernels (image_encoder.py) against the same torchvision
+    module evaluated by torch on the CPU in fp32; zero-padded channels must stay exactly zero."""
+    from implicit_depth_b200.bd_model import EffNetV2SFeatures
+    from implicit_depth_b200.image_encoder import plan_efficientnet_v2_s
+    from implicit_depth_b200.networks import Plan
+
+    enc = EffNetV2SFeatures().eval()
+    synthetic.init_model_weights(enc, seed=3)
+    rng = np.random.default_rng(3100)
+    for (B, H, W) in ((2, 96, 128), (1, 192, 256)):
+        img = torch.from_numpy(rng.standard_normal((B, 3, H, W)).astype(np.float32))
+        with torch.no_grad():
+            ref = enc(img)
+        g = Plan("cuda")
+        slots = {"img": img.cuda()}
+        acts = plan_efficientnet_v2_s(g, enc.features, lambda: slots["img"], B, H, W, taps=enc.TAPS)
+        g.run()
+        torch.cuda.synchronize()
+        assert [a.Cl for a in acts] == [24, 48, 64, 160, 256]
+        for a, r in zip(acts, ref):
+            got = a.float_nchw().cpu().numpy()
+            assert got.shape[2:] == tuple(r.shape[2:])
+            assert rel_err(got[:, :a.Cl], r.numpy()) < TOL
+            assert not got[:, a.Cl:].any()
