@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  tc::grid_dependency_wait();  // PDL: inputs of the previous kernel are complete and visible from here on
 
   if (warp == 0) {
     // =========================== TMA producer (whole warp loops, one elected lane issues) ===========

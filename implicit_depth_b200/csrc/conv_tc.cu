@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  tc::grid_dependency_wait();  // PDL: inputs of the previous kernel are complete and visible from here on
 
   if (warp == 0) {
     {
@@ -467,16 +468,39 @@ extern "C" int b200_conv_run(void* plan, void* stream) {
   B200_CHECK_ARG(plan, "conv_run: null plan");
   ConvPlan* p = (ConvPlan*)plan;
   cudaStream_t st = (cudaStream_t)stream;
+  // Programmatic dependent launch: the kernels call griddepcontrol.wait after their prologue (barrier init, TMEM
+  // allocation, tensor-map prefetch, bias staging), so on SMs the previous kernel has already left, the prologue
+  // of this one overlaps the previous kernel's tail.  Captured into CUDA graphs as programmatic edges.
+  static int use_pdl = -1;
+  if (use_pdl < 0) {
+    const char* e = getenv("B200_PDL");
+    use_pdl = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p->grid);
+  cfg.blockDim = dim3(p->k.halo ? CVH_THREADS : CV_THREADS);
+  cfg.dynamicSmemBytes = p->smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  cudaError_t le;
   if (!p->k.halo)
-    conv_tc_kernel<<<p->grid, CV_THREADS, p->smem, st>>>(p->k);
+    le = cudaLaunchKernelEx(&cfg, conv_tc_kernel, p->k);
   else if (p->k.prof == nullptr) {
-    if (p->k.NT == 128) conv_halo_kernel<1, 2, false><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
-    else if (p->k.sub == 2) conv_halo_kernel<2, 1, false><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
-    else conv_halo_kernel<1, 1, false><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
+    if (p->k.NT == 128) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 2, false>, p->k);
+    else if (p->k.sub == 2) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<2, 1, false>, p->k);
+    else le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 1, false>, p->k);
   } else {
-    if (p->k.NT == 128) conv_halo_kernel<1, 2, true><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
-    else if (p->k.sub == 2) conv_halo_kernel<2, 1, true><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
-    else conv_halo_kernel<1, 1, true><<<p->grid, CVH_THREADS, p->smem, st>>>(p->k);
+    if (p->k.NT == 128) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 2, true>, p->k);
+    else if (p->k.sub == 2) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<2, 1, true>, p->k);
+    else le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 1, true>, p->k);
+  }
+  if (le != cudaSuccess) {
+    b200_set_error("conv_run: launch failed: %s", cudaGetErrorString(le));
+    return -2;
   }
   B200_CHECK_LAUNCH("conv_run");
   return 0;

@@ -50,6 +50,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // generic-proxy writes (st.shared) -> visible to the async proxy (tcgen05.mma / TMA reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Wait until the grids this one depends on have completed and their memory is visible (no-op when the kernel was
+// launched without the programmatic-serialization attribute), then let the next kernel in the stream begin launching:
+// its CTAs become resident as ours exit and run their prologue up to their own wait.
+__device__ __forceinline__ void grid_dependency_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ TMA
 // 4-D tiled tensor-map load (innermost coordinate first), completion signalled on an mbarrier.
 __device__ __forceinline__ void tma_load_4d(void* dst_smem, const void* tmap, int c0, int c1, int c2, int c3,
