@@ -10,8 +10,8 @@ import torch
 import torch.nn.functional as F
 
 
-def _pix(h, w, dtype):
-    xx, yy = torch.meshgrid(torch.arange(w), torch.arange(h), indexing="xy")
+def _pix(h, w, dtype, device=None):
+    xx, yy = torch.meshgrid(torch.arange(w, device=device), torch.arange(h, device=device), indexing="xy")
     p = torch.stack((xx, yy), 0).to(dtype) + 0.5
     return torch.cat([p, torch.ones_like(p[:1])], 0).flatten(1).unsqueeze(0)  # geometry_utils.py:34-48
 
@@ -29,9 +29,9 @@ def _warp(src_feats, src_extr, src_Ks, cur_invK, z, pix, h, w):
     Xh = torch.cat([X, torch.ones_like(X[:, :1])], 1).repeat_interleave(K, 0)
     P = (src_Ks.reshape(-1, 4, 4) @ src_extr.reshape(-1, 4, 4))[:, :3]  # geometry_utils.py:82-84
     c = P @ Xh
-    zc = torch.maximum(c[:, 2:], torch.tensor(1e-5, dtype=c.dtype))
+    zc = torch.clamp(c[:, 2:], min=1e-5)
     xy = c[:, :2] / zc
-    uv = 2 * xy.view(-1, 2, h, w).permute(0, 2, 3, 1) * torch.tensor([1 / w, 1 / h], dtype=c.dtype) - 1
+    uv = 2 * xy.view(-1, 2, h, w).permute(0, 2, 3, 1) * torch.tensor([1 / w, 1 / h], dtype=c.dtype, device=c.device) - 1
     warped = F.grid_sample(src_feats.reshape(-1, C, h, w), uv, padding_mode="zeros", mode="bilinear",
                            align_corners=False).view(B, K, C, h, w)
     return X, xy.view(B, K, 2, h, w), zc.view(B, K, h, w), warped
@@ -39,7 +39,7 @@ def _warp(src_feats, src_extr, src_Ks, cur_invK, z, pix, h, w):
 
 def cost_volume_dot(cur_feats, src_feats, src_extr, src_Ks, cur_invK, planes):
     B, K, C, h, w = src_feats.shape
-    pix = _pix(h, w, cur_feats.dtype)
+    pix = _pix(h, w, cur_feats.dtype, cur_feats.device)
     out = []
     for z in planes:
         _, _, zc, warped = _warp(src_feats, src_extr, src_Ks, cur_invK, z, pix, h, w)
@@ -54,7 +54,7 @@ def feature_volume_mlp(cur_feats, src_feats, src_extr, src_poses, src_Ks, cur_in
     """weights: [(W1,b1),(W2,b2),(W3,b3)] torch tensors.  Same outputs as oracle.planesweep.feature_volume_mlp."""
     B, K, C, h, w = src_feats.shape
     dt = cur_feats.dtype
-    pix = _pix(h, w, dt)
+    pix = _pix(h, w, dt, cur_feats.device)
     R = src_poses[..., :3, :3]
     t = src_poses[..., :3, 3]
     tr = R.diagonal(dim1=-1, dim2=-2).sum(-1)
@@ -71,7 +71,7 @@ def feature_volume_mlp(cur_feats, src_feats, src_extr, src_poses, src_Ks, cur_in
         src_ray = F.normalize(X.view(B, 1, 3, h * w) - t[..., None], dim=2).view(B, K, 3, h, w)
         ang = F.cosine_similarity(cur_ray.expand(B, K, 3, h, w), src_ray, dim=2, eps=1e-5)
         dot = (warped * cur_feats.unsqueeze(1)).sum(2) * mask
-        feats = torch.cat([warped.flatten(1, 2), cur_feats, mask, zc, torch.full((B, 1, h, w), float(z), dtype=dt), dot,
+        feats = torch.cat([warped.flatten(1, 2), cur_feats, mask, zc, torch.full((B, 1, h, w), float(z), dtype=dt, device=cur_feats.device), dot,
                            ang, cur_ray.flatten(1, 2), src_ray.flatten(1, 2), expand(d_m), expand(r_m), expand(t_m)],
                           1)  # cost_volume.py:681-695
         x = feats.permute(0, 2, 3, 1)

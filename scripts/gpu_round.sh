@@ -9,9 +9,13 @@ timeout 120 python scripts/time_conv.py > gpurun_out/time_conv.log 2>&1; cat gpu
 timeout 120 python scripts/time_volume.py > gpurun_out/time_volume.log 2>&1; cat gpurun_out/time_volume.log
 timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/launches.csv python scripts/profile_step.py > gpurun_out/ncu_launch.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'fv_tc_kernel|cv_dot_kernel' -s 12 -c 2 \
-    -f -o gpurun_out/prof_volume python scripts/time_volume.py > gpurun_out/ncu_volume.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'conv_' -s 3 -c 1 \
+NO_SIMT=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:cv_dot_kernel -s 8 -c 1 \
+    -f -o gpurun_out/prof_cvdot python scripts/time_volume.py > gpurun_out/ncu_cvdot.log 2>&1
+NO_SIMT=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:fv_tc_kernel -s 8 -c 1 \
+    -f -o gpurun_out/prof_fvtc python scripts/time_volume.py > gpurun_out/ncu_fvtc.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_halo -s 3 -c 1 \
     -f -o gpurun_out/prof_conv python scripts/time_conv.py > gpurun_out/ncu_conv.log 2>&1
-tail -3 gpurun_out/ncu_*.log
+timeout 300 python scripts/plane_sweep.py > gpurun_out/plane_sweep.log 2>&1; cat gpurun_out/plane_sweep.log
+timeout 300 python scripts/torch_gpu_baseline.py > gpurun_out/torch_gpu_baseline.json 2> gpurun_out/torch_gpu_baseline.err; cat gpurun_out/torch_gpu_baseline.json; tail -3 gpurun_out/torch_gpu_baseline.err
+for f in gpurun_out/ncu_*.log; do tail -n 2 $f; done
 ls -la gpurun_out
