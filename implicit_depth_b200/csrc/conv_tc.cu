@@ -345,7 +345,18 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   if (halo) {
     // two M=128 sub-tiles per item share every weight chunk when the N tile is 64 wide and there is enough work
     k.sub = (k.NT == 64) ? 2 : 1;
-    if (k.sub == 2 && d->B * ((d->OW + 15) / 16) * ((d->OH + CVH_ROWS - 1) / CVH_ROWS) * k.n_ntiles < n_sm) k.sub = 1;
+    if (k.sub == 2) {
+      // wave quantisation on the persistent grid: an item of two sub-tiles costs ~1.7x an item of one (shared weight
+      // chunks), so e.g. 192 double items on 148 SMs (2 waves = 3.4 units) lose to 384 single items (3 waves)
+      const int rows = (d->OH + CVH_ROWS - 1) / CVH_ROWS;
+      const int items2 = d->B * ((d->OW + 15) / 16) * rows * k.n_ntiles;
+      const int items1 = d->B * ((d->OW + 7) / 8) * rows * k.n_ntiles;
+      const int waves2 = (items2 + n_sm - 1) / n_sm, waves1 = (items1 + n_sm - 1) / n_sm;
+      if (items2 < n_sm || 10 * waves1 < 17 * waves2) k.sub = 1;
+      const char* e = getenv("B200_CONV_SUB");  // dev override
+      if (e != nullptr && atoi(e) == 2) k.sub = 2;
+      if (e != nullptr && atoi(e) == 1) k.sub = 1;
+    }
   }
   const int cw = halo ? 32 : 64;  // channels per K chunk
   for (int s = 0; s < d->nseg; ++s) {
