@@ -6,8 +6,11 @@ import torch
 from implicit_depth_b200 import B200CostVolumeManager, B200FeatureVolumeManager, synthetic
 
 B, K, C, h, w = 4, 7, 16, 96, 128
-peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) \
-    if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+import importlib.util
+_spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "bench.py"))
+_bench = importlib.util.module_from_spec(_spec); _spec.loader.exec_module(_bench)
+_h, _t, _ = _bench.load_peaks()
+peaks = {"hbm_gbs": _h, "bf16_tflops": _t}
 t = {k: torch.from_numpy(v).cuda() for k, v in synthetic.make_volume_inputs(2000, B, K, C, h, w).items()}
 mn = torch.tensor(0.25, device="cuda").view(1, 1, 1, 1); mx = torch.tensor(5.0, device="cuda").view(1, 1, 1, 1)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
