@@ -74,6 +74,14 @@ def fold_batchnorm(module):
     return walk(copy.deepcopy(module).eval())
 
 
+def _clone(o):
+    if o is None:
+        return None
+    if isinstance(o, (tuple, list)):
+        return tuple(_clone(x) for x in o)
+    return o.clone()
+
+
 class B200BDModel(nn.Module):
     def __init__(self, opts=None, encoder=None):
         super().__init__()
@@ -202,15 +210,19 @@ class B200BDModel(nn.Module):
         cv = post.from_f32(lambda: slots["cv"], B, D, h, w)
         cv_feats = self.cost_volume_net.plan(post, cv, img_feats[ms:])
         dec_in = img_feats[:ms] + cv_feats
-        res, _ = self.depth_decoder.plan(post, dec_in, outputs=(0,))
-        search_depths = None
-        if search:
-            search_depths, pred = self.binary_mlp.plan_search(post, res[0], get_prior=(lambda: slots.get("prior")))
-        else:
-            pred = self.binary_mlp.plan_val(post, res[0], lambda: slots["rendered_depth"], P,
-                                            get_prior=(lambda: slots.get("prior")))
+        pred, search_depths = self._plan_head(post, dec_in, slots, P, search)
         return SimpleNamespace(slots=slots, pre=pre, post=post, encp=encp, feats_pm=feats_pm, h=h, w=w, pred=pred,
                                search_depths=search_depths, feat_layout=self.cost_volume.FEAT_LAYOUT)
+
+    def _plan_head(self, post, dec_in, slots, P, search):
+        """Decoder + per-pixel binary-occupancy MLP (bd_model.py:260-304).  Returns (pred, search_depths)."""
+        res, _ = self.depth_decoder.plan(post, dec_in, outputs=(0,))
+        if search:
+            search_depths, pred = self.binary_mlp.plan_search(post, res[0], get_prior=(lambda: slots.get("prior")))
+            return pred, search_depths
+        pred = self.binary_mlp.plan_val(post, res[0], lambda: slots["rendered_depth"], P,
+                                        get_prior=(lambda: slots.get("prior")))
+        return pred, None
 
     def num_kernel_launches(self, B, K, H, W, P, search=False):
         """Hand-written kernel launches per forward for this signature (matching encoder + volume + nets)."""
@@ -307,8 +319,7 @@ class B200BDModel(nn.Module):
             pred, lowest, mask, search = self._forward_graphed(args, prior, return_mask, bool(infer_depth))
         else:
             pred, lowest, mask, search = self._forward_impl(*args, prior, return_mask, bool(infer_depth))
-            pred = pred.clone()
-            search = None if search is None else search.clone()
+            pred, search = _clone(pred), _clone(search)
         out = {"pred_0": pred}
         if infer_depth:
             out["search_depths"] = search  # bd_model.py:292
@@ -339,4 +350,4 @@ class B200BDModel(nn.Module):
         if prior is not None:
             sprior.copy_(prior)
         graph.replay()
-        return tuple(None if o is None else o.clone() for o in outs)
+        return tuple(_clone(o) for o in outs)

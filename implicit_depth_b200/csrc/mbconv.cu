@@ -231,3 +231,46 @@ extern "C" int b200_split_add(const void* a_hi, const void* a_lo, const void* b_
   B200_CHECK_LAUNCH("split_add");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// 1x1 convolution to ONE channel + exp: the last layer of the regression heads of DepthDecoderPP
+// (modules/networks.py:160-163: nn.Conv2d(C, 1, 1)) and SkipDecoderRegression (networks_fast.py:106-112), with the
+// exp() of DepthModel.forward (depth_model.py:426-435).  8 lanes per pixel, fixed-order shuffle reduction.
+//   in: split NHWC [n_pix, C]; w [C], bias [1]; out_log / out_exp: [n_pix] fp32 (= [B,1,H,W]).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+channel_dot_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                   const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out_log,
+                   float* __restrict__ out_exp, long long n_pix, int C) {
+  const int sub = threadIdx.x & 7;
+  const long long pix = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
+  const long long p = pix < n_pix ? pix : n_pix - 1;  // keep the 8-lane group convergent
+  float acc = 0.f;
+  for (int c = sub * 8; c < C; c += 64) {
+    float v[8];
+    mb_load8(hi, lo, (size_t)p * C + c, v);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + c + 4));
+    acc = fmaf(v[0], w0.x, acc); acc = fmaf(v[1], w0.y, acc); acc = fmaf(v[2], w0.z, acc); acc = fmaf(v[3], w0.w, acc);
+    acc = fmaf(v[4], w1.x, acc); acc = fmaf(v[5], w1.y, acc); acc = fmaf(v[6], w1.z, acc); acc = fmaf(v[7], w1.w, acc);
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (sub == 0 && pix < n_pix) {
+    const float v = acc + bias[0];
+    out_log[pix] = v;
+    if (out_exp) out_exp[pix] = expf(v);
+  }
+}
+
+extern "C" int b200_channel_dot_exp(const void* in_hi, const void* in_lo, const float* w, const float* bias,
+                                    float* out_log, float* out_exp, long long n_pix, int C, void* stream) {
+  B200_CHECK_ARG(in_hi && in_lo && w && bias && out_log && n_pix > 0 && C > 0 && C % 8 == 0,
+                 "channel_dot_exp: bad arguments (C %% 8 == 0; got C=%d)", C);
+  const long long threads = n_pix * 8;
+  channel_dot_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo, w, bias, out_log, out_exp, n_pix, C);
+  B200_CHECK_LAUNCH("channel_dot_exp");
+  return 0;
+}

@@ -103,6 +103,20 @@ class Plan:
                                    a.W, _abi.stream_ptr()))
         return out
 
+    def channel_dot(self, a, conv):
+        """nn.Conv2d(C, 1, 1) on a split activation -> (log fp32 [B,1,H,W], exp(log) fp32 [B,1,H,W])."""
+        assert conv.out_channels == 1 and conv.kernel_size == (1, 1)
+        cl = conv.in_channels
+        w = torch.zeros(a.C, device=self.device, dtype=torch.float32)
+        w[:cl] = conv.weight.detach().to(self.device, torch.float32).reshape(-1)
+        b = conv.bias.detach().to(self.device, torch.float32).reshape(1).contiguous()
+        out_log = self.empty((a.B, 1, a.H, a.W))
+        out_exp = self.empty((a.B, 1, a.H, a.W))
+        self._keep += [w, b]
+        self.add(lambda: _abi.call("b200_channel_dot_exp", _abi.ptr(a.hi), _abi.ptr(a.lo), _abi.ptr(w), _abi.ptr(b),
+                                   _abi.ptr(out_log), _abi.ptr(out_exp), a.B * a.H * a.W, a.C, _abi.stream_ptr()))
+        return out_log, out_exp
+
     def instance_norm(self, a, pad=0, act="none", slope=LRELU, eps=1e-5, f32_pixel_major=False, f32_layout=0):
         partial = self.empty((a.B, 32, a.C, 2), torch.float64)
         stats = self.empty((a.B, a.C, 2))
@@ -310,6 +324,40 @@ class BDDecoderPP(_PlannedModule):
         return {f"feature_s{i}_b1hw": o.clone() for i, o in outs.items()}
 
 
+class DepthDecoderPP(BDDecoderPP):
+    """Regression UNet++ of modules/networks.py:118-183: the BD decoder's graph with every `output_i` live and a
+    1x1 conv to one log-depth channel behind it (`convs.output_{i}.1`)."""
+
+    def __init__(self, num_ch_enc, scales=range(4), num_output_channels=1, use_skips=True):
+        super().__init__(num_ch_enc, outputs=(0, 1, 2, 3))
+        if num_output_channels != 1:
+            raise ValueError("B200 DepthDecoderPP predicts one log-depth channel")
+        for i in range(4):
+            c = int(self.num_ch_dec[i])
+            self.convs[f"output_{i}"] = nn.Sequential(BasicBlock(c, c) if i != 0 else nn.Identity(), nn.Conv2d(c, 1, 1))
+
+    def plan_depth(self, g: Plan, feats):
+        """Returns {i: (log_depth, depth)} fp32 [B,1,H_i,W_i] for the four scales."""
+        res, _ = self.plan(g, feats, outputs=(0, 1, 2, 3))
+        return {i: g.channel_dot(res[i], self.convs[f"output_{i}"][1]) for i in range(4)}
+
+    @torch.no_grad()
+    def forward(self, input_features):
+        sig = tuple(tuple(f.shape) for f in input_features)
+
+        def build():
+            g = Plan(input_features[0].device)
+            slots = {}
+            fa = [g.from_f32((lambda i=i: slots[i]), *f.shape) for i, f in enumerate(input_features)]
+            return g, slots, self.plan_depth(g, fa)
+
+        g, slots, outs = self._get_plan(sig, build)
+        for i, f in enumerate(input_features):
+            slots[i] = f
+        g.run()
+        return {f"log_depth_pred_s{i}_b1hw": o[0].clone() for i, o in outs.items()}
+
+
 class _ConvBlock(nn.Module):
     """modules/networks_fast.py:10-28: conv3x3 -> ELU -> conv3x3 -> ELU."""
 
@@ -379,6 +427,45 @@ class SkipDecoder(_PlannedModule):
             slots[i] = f
         g.run()
         return {f"feature_s{i}_b1hw": o.clone() for i, o in outs.items()}
+
+
+class SkipDecoderRegression(SkipDecoder):
+    """modules/networks_fast.py:102-145: SkipDecoder + one 1x1-conv MLP head (C -> 128 -> 128 -> 1, ELU) per scale;
+    `out1` reads feature_s3 ... `out4` reads feature_s0."""
+
+    def __init__(self, input_channels, use_bn=False):
+        super().__init__(input_channels, use_bn=use_bn)
+        for n in range(4):
+            setattr(self, f"out{n + 1}", nn.Sequential(
+                nn.Conv2d(self.output_channels[n], 128, 1), nn.ELU(inplace=True), nn.Conv2d(128, 128, 1),
+                nn.ELU(inplace=True), nn.Conv2d(128, 1, 1)))
+
+    def plan_depth(self, g, feats):
+        res, _ = self.plan(g, feats, outputs=(0, 1, 2, 3))
+        out = {}
+        for n in range(4):
+            scale = 3 - n
+            head = getattr(self, f"out{n + 1}")
+            h, _ = g.conv([(res[scale], head[0].weight, 1, 0)], head[0].bias, 128, act="elu")
+            h, _ = g.conv([(h, head[2].weight, 1, 0)], head[2].bias, 128, act="elu")
+            out[scale] = g.channel_dot(h, head[4])
+        return out
+
+    @torch.no_grad()
+    def forward(self, features):
+        sig = tuple(tuple(f.shape) for f in features)
+
+        def build():
+            g = Plan(features[0].device)
+            slots = {}
+            fa = [g.from_f32((lambda i=i: slots[i]), *f.shape) for i, f in enumerate(features)]
+            return g, slots, self.plan_depth(g, fa)
+
+        g, slots, outs = self._get_plan(sig, build)
+        for i, f in enumerate(features):
+            slots[i] = f
+        g.run()
+        return {f"log_depth_pred_s{i}_b1hw": o[0].clone() for i, o in outs.items()}
 
 
 # ---- matching encoder ---------------------------------------------------------------

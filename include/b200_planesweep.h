@@ -152,6 +152,12 @@ int b200_squeeze_excite(const void* in_hi, const void* in_lo, const float* w1, c
 int b200_split_add(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* out_hi, void* out_lo,
                    long long n, void* stream);
 
+/* 1x1 convolution to one channel (+ exp): the last layer of the regression heads of DepthDecoderPP
+ * (modules/networks.py:160-163) / SkipDecoderRegression (networks_fast.py:106-112) and the exp() of
+ * DepthModel.forward (depth_model.py:426-435).  in: split NHWC [n_pix, C]; out_log, out_exp (or NULL): [n_pix]. */
+int b200_channel_dot_exp(const void* in_hi, const void* in_lo, const float* w, const float* bias, float* out_log,
+                         float* out_exp, long long n_pix, int C, void* stream);
+
 /* Matching-encoder stem conv 7x7/2 (3->64, BatchNorm folded) + ReLU (modules/networks.py:264-266):
  * img fp32 NCHW [n,3,H,W]; wt [147,64] tap-major (c,dy,dx); out NHWC split [n,H/2,W/2,64]. */
 int b200_stem_conv7(const float* img, const float* wt, const float* bias, void* out_hi, void* out_lo, int n_img,

@@ -83,6 +83,14 @@ def bd_decoder_pp(sd, p, feats):
     return result
 
 
+def depth_decoder_pp(sd, p, feats):
+    """`DepthDecoderPP.forward`, modules/networks.py:164-183: the UNet++ graph of `bd_decoder_pp` with the heads
+    `output_i = (BasicBlock | Identity) -> Conv2d(C, 1, 1)` (:160-163)."""
+    feats_out = bd_decoder_pp(sd, p, feats)
+    return {f"log_depth_pred_s{i}_b1hw": _conv(sd, f"{p}.convs.output_{i}.1", feats_out[f"feature_s{i}_b1hw"])
+            for i in range(4)}
+
+
 def _conv_block(sd, p, x):
     """`ConvBlock.forward`, modules/networks_fast.py:21-28."""
     x = F.elu(_conv(sd, p + ".conv1", x, 1, 1))
@@ -98,6 +106,55 @@ def skip_decoder(sd, p, feats):
         x = F.interpolate(x, scale_factor=2, mode="nearest")
         x = _conv_block(sd, f"{p}.block{n + 1}.post_concat_conv", torch.cat([x, feats[-2 - n]], 1))
         out[f"feature_s{3 - n}_b1hw"] = x
+    return out
+
+
+def skip_decoder_regression(sd, p, feats):
+    """`SkipDecoderRegression.forward`, modules/networks_fast.py:137-145 (heads :106-135)."""
+    f = skip_decoder(sd, p, feats)
+    out = {}
+    for n in range(4):
+        x = f[f"feature_s{3 - n}_b1hw"]
+        x = F.elu(_conv(sd, f"{p}.out{n + 1}.0", x))
+        x = F.elu(_conv(sd, f"{p}.out{n + 1}.2", x))
+        out[f"log_depth_pred_s{3 - n}_b1hw"] = _conv(sd, f"{p}.out{n + 1}.4", x)
+    return out
+
+
+def depth_forward(sd, encoder, cur, src, opts):
+    """`DepthModel.forward(phase="test")`, depth_model.py:280-440 (no flip): the chain of `bd_forward` up to the
+    decoder, then the regression decoder and exp()."""
+    ms = opts.matching_scale
+    cur_image, src_image = cur["image_b3hw"], src["image_b3hw"]
+    B, K = src_image.shape[:2]
+    src_cam_T_cur_cam = src["cam_T_world_b44"] @ cur["world_T_cam_b44"].unsqueeze(1)
+    cur_cam_T_src_cam = cur["cam_T_world_b44"].unsqueeze(1) @ src["world_T_cam_b44"]
+    with torch.no_grad():
+        enc = encoder(cur_image)
+        frames = torch.cat([cur_image.unsqueeze(1), src_image], 1).flatten(0, 1)
+        mf = torch.cat([matching_encoder(sd, "matching_model", f[None]) for f in frames], 0)
+        mf = mf.view(B, K + 1, *mf.shape[1:])
+        from . import planesweep_torch as PT
+
+        tp = PT.depth_planes(opts.min_matching_depth, opts.max_matching_depth, opts.matching_num_depth_bins)
+        if opts.feature_volume_type == "mlp_feature_volume":
+            W = [(sd[f"cost_volume.mlp.net.{i}.weight"], sd[f"cost_volume.mlp.net.{i}.bias"]) for i in (0, 2, 4)]
+            vol, _, lowest, mask = PT.feature_volume_mlp(mf[:, 0], mf[:, 1:], src_cam_T_cur_cam, cur_cam_T_src_cam,
+                                                         src[f"K_s{ms}_b44"], cur[f"invK_s{ms}_b44"], tp, W, True)
+        else:
+            vol, _, lowest = PT.cost_volume_dot(mf[:, 0], mf[:, 1:], src_cam_T_cur_cam, src[f"K_s{ms}_b44"],
+                                                cur[f"invK_s{ms}_b44"], tp)
+            mask = None
+        cvf = cv_encoder(sd, "cost_volume_net", vol, enc[ms:])
+        feats = list(enc[:ms]) + cvf
+        if opts.depth_decoder_name == "unet_pp":
+            out = depth_decoder_pp(sd, "depth_decoder", feats)
+        else:
+            out = skip_decoder_regression(sd, "depth_decoder", feats)
+        for k in list(out.keys()):
+            out[k.replace("log_", "")] = torch.exp(out[k])  # depth_model.py:426-435
+    out["lowest_cost_bhw"] = lowest
+    out["overall_mask_bhw"] = mask
     return out
 
 

@@ -172,6 +172,37 @@ def network_goldens():
         print("model", fv_type, {k: v.shape for k, v in g.items()}, "pred range", g["pred_0"].min(), g["pred_0"].max())
 
 
+def depth_goldens():
+    """Reference DepthModel.forward (depth_model.py:280-440) at 256x192, 7 views, 16 planes, for both
+    regression decoders, with the state dict of the seeded B200 container (identical keys)."""
+    import options as ref_options  # reference
+    from experiment_modules.depth_model import DepthModel  # reference
+
+    from implicit_depth_b200.bd_model import default_options
+    from implicit_depth_b200.depth_model import B200DepthModel
+
+    for dec_name in ("unet_pp", "skip"):
+        opts = default_options(image_width=256, image_height=192, matching_num_depth_bins=16, depth_decoder_name=dec_name)
+        mine = B200DepthModel(opts)
+        checksum = synthetic.init_model_weights(mine, seed=0)
+        ro = ref_options.Options()
+        ro.image_width, ro.image_height, ro.matching_num_depth_bins = 256, 192, 16
+        ro.depth_decoder_name = dec_name
+        ref = DepthModel(ro)
+        ref.load_state_dict(dict(mine.state_dict()), strict=True)
+        ref.eval()
+        cur, src = synthetic.make_frame_batch(5007, 1, 7, 192, 256)
+        cur_t = {k: torch.from_numpy(v) for k, v in cur.items()}
+        src_t = {k: torch.from_numpy(v) for k, v in src.items()}
+        o = ref("test", cur_t, src_t, unbatched_matching_encoder_forward=True, return_mask=True)
+        g = {"checksum": np.array(checksum), "lowest_cost_bhw": o["lowest_cost_bhw"].numpy(),
+             "overall_mask_bhw": o["overall_mask_bhw"].numpy()}
+        for i in range(4):
+            g[f"log_depth_pred_s{i}_b1hw"] = o[f"log_depth_pred_s{i}_b1hw"].numpy()
+        np.savez_compressed(os.path.join(HERE, f"depth_model_256x192_{dec_name}.npz"), **g)
+        print("depth model", dec_name, {k: v.shape for k, v in g.items()})
+
+
 def temporal_goldens():
     """use_prior model (implicit_depth_temporal.yaml): prior warp + 66-input binary MLP; and the infer_depth
     bisection of the plain model.  256x192, 7 views, 16 planes, one rendered plane."""
@@ -239,7 +270,11 @@ if __name__ == "__main__":
     if "--temporal-only" in sys.argv:
         temporal_goldens()
         sys.exit(0)
+    if "--depth-only" in sys.argv:
+        depth_goldens()
+        sys.exit(0)
     if "--nets-only" not in sys.argv:
         volume_goldens()
     network_goldens()
     temporal_goldens()
+    depth_goldens()

@@ -288,3 +288,38 @@ def test_native_image_encoder_vs_torch_fp32():
             assert got.shape[2:] == tuple(r.shape[2:])
             assert rel_err(got[:, :a.Cl], r.numpy()) < TOL
             assert not got[:, a.Cl:].any()
+
+
+@pytest.mark.parametrize("dec_name", ["unet_pp", "skip"])
+def test_depth_model_forward_vs_reference_golden_and_oracle(dec_name):
+    """B200DepthModel (regression heads on the same kernels) against the reference DepthModel golden
+    and the CPU oracle: log-depth at 4 scales, depth = exp(log-depth), lowest cost, mask."""
+    from implicit_depth_b200.depth_model import B200DepthModel
+
+    g = np.load(f"{GOLDEN}/depth_model_256x192_{dec_name}.npz")
+    opts = default_options(image_width=256, image_height=192, matching_num_depth_bins=16, depth_decoder_name=dec_name)
+    m = B200DepthModel(opts)
+    checksum = synthetic.init_model_weights(m, seed=0)
+    golden_ok = abs(checksum - float(g["checksum"])) <= 1e-6 * checksum
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    cpu_enc = B200DepthModel(opts).encoder
+    cpu_enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")})
+    cur, src = synthetic.make_frame_batch(5007, 1, 7, 192, 256)
+    ref = ON.depth_forward(sd, cpu_enc.eval(), {k: torch.from_numpy(v) for k, v in cur.items()},
+                           {k: torch.from_numpy(v) for k, v in src.items()}, opts)
+    m = m.cuda().eval()
+    c = {k: torch.from_numpy(v).cuda() for k, v in cur.items()}
+    s = {k: torch.from_numpy(v).cuda() for k, v in src.items()}
+    for graph in (False, True):
+        m.use_cuda_graph = graph
+        out = m("test", c, s, return_mask=True)
+        assert set(out) == {f"{p}depth_pred_s{i}_b1hw" for p in ("log_", "") for i in range(4)} | {
+            "lowest_cost_bhw", "overall_mask_bhw"}
+        for i in range(4):
+            got = out[f"log_depth_pred_s{i}_b1hw"].cpu().numpy()
+            assert got.shape == tuple(ref[f"log_depth_pred_s{i}_b1hw"].shape)
+            assert rel_err(got, ref[f"log_depth_pred_s{i}_b1hw"].numpy()) < TOL
+            if golden_ok:
+                assert rel_err(got, g[f"log_depth_pred_s{i}_b1hw"]) < TOL
+            np.testing.assert_allclose(out[f"depth_pred_s{i}_b1hw"].cpu().numpy(), np.exp(got), rtol=1e-5)
+        assert (out["overall_mask_bhw"].cpu().numpy() != g["overall_mask_bhw"]).mean() < 1e-3
