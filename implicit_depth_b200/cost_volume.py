@@ -253,7 +253,15 @@ class B200FeatureVolumeManager(B200CostVolumeManager):
         a = [c for k in range(KA) for c in view(k)] + tail[:8]
         b = [c for k in range(KA, K) for c in view(k)] + tail[8:]
         assert len(a) <= 32 * HA and len(b) <= 32 * HB and HA + HB == 2 * nchunk
-        return a + [-1] * (32 * HA - len(a)) + b + [-1] * (32 * HB - len(b))
+        a = a + [-1] * (32 * HA - len(a))
+        b = b + [-1] * (32 * HB - len(b))
+        # the roles' 32-channel halves are interleaved in K (A0 B0 A1 B1 ..., then the longer role's remainder):
+        # FvCfg::half_pos in csrc/fv_tc.cu
+        halves, hmin = [], min(HA, HB)
+        for h in range(hmin):
+            halves += [a[32 * h:32 * h + 32], b[32 * h:32 * h + 32]]
+        halves += [a[32 * h:32 * h + 32] for h in range(hmin, HA)] + [b[32 * h:32 * h + 32] for h in range(hmin, HB)]
+        return [c for half in halves for c in half]
 
     def _pack(self, device):
         lin = [self.mlp.net[0], self.mlp.net[2], self.mlp.net[4]]

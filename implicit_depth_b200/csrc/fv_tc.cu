@@ -25,7 +25,8 @@
 // implicit_depth_b200/cost_volume.py: tc_channel_layout): 32-channel "halves";
 //   role A: view blocks 0..KA-1 (22 ch each, fv_rows.cuh) | cur[0..7]           | zero pad to HA halves
 //   role B: view blocks KA..K-1                            | cur[8..15] curray zd | zero pad to HB halves
-// with HA + HB even; two halves form one 64-channel MMA chunk = one ring slot.
+// with HA + HB even; the halves of the two roles are interleaved in K (A0 B0 A1 B1 ..., FvCfg::half_pos) and two
+// consecutive halves form one 64-channel MMA chunk = one ring slot, so chunks complete while the build goes on.
 //
 // Replaces FeatureVolumeManager.build_cost_volume (modules/cost_volume.py:437-706) /
 // FastFeatureVolumeManager.build_cost_volume (:938-1146) + MLP (modules/networks.py:218-233).
@@ -70,6 +71,12 @@ struct FvCfg {
   static constexpr int NCHUNK = (HA + (CB + 31) / 32 + 1) / 2;
   static constexpr int HB = 2 * NCHUNK - HA;
   static constexpr int W_BYTES = (2 * NCHUNK + 4) * 16384;
+  static constexpr int HMIN = HA < HB ? HA : HB;
+  // Position of a role's h-th half in the row's K dimension: the two roles' halves are interleaved (A0 B0 A1 B1 ...)
+  // so that 64-channel chunks complete progressively while both roles are still gathering -- with role A's halves
+  // first and role B's last, two of the three chunks only completed at the very end of the build and their 24 MMAs
+  // sat in every tile's critical path.
+  __host__ __device__ static constexpr int half_pos(int role, int h) { return h < HMIN ? 2 * h + role : 2 * HMIN + (h - HMIN); }
 };
 
 // Flush one 32-channel half (global half index `hg` within the row) into the ring slot of its chunk.
@@ -99,7 +106,7 @@ __device__ __forceinline__ bool build_row_share(const FvTcParams& prm, const Pix
                                                 uint32_t a_base, GroupSync* gs, uint32_t g0) {
   using Cfg = FvCfg<K>;
   constexpr int V0 = ROLE ? Cfg::KA : 0, NV = ROLE ? Cfg::KB : Cfg::KA;
-  constexpr int H0 = ROLE ? Cfg::HA : 0, NH = ROLE ? Cfg::HB : Cfg::HA;
+  constexpr int NH = ROLE ? Cfg::HB : Cfg::HA;
   constexpr int NT = ROLE ? 12 : 8;
   float buf[32];
   bool inb = false;
@@ -113,7 +120,7 @@ __device__ __forceinline__ bool build_row_share(const FvTcParams& prm, const Pix
     for (int c = 0; c < FV_VIEW_CH; ++c) {
       const int ch = v * FV_VIEW_CH + c;
       buf[ch & 31] = out[c];
-      if ((ch & 31) == 31) flush_half(buf, a_base, gs, H0 + (ch >> 5), g0);
+      if ((ch & 31) == 31) flush_half(buf, a_base, gs, Cfg::half_pos(ROLE, ch >> 5), g0);
     }
   }
 #pragma unroll
@@ -127,7 +134,7 @@ __device__ __forceinline__ bool build_row_share(const FvTcParams& prm, const Pix
       else v = zd;
     }
     buf[ch & 31] = v;
-    if ((ch & 31) == 31) flush_half(buf, a_base, gs, H0 + (ch >> 5), g0);
+    if ((ch & 31) == 31) flush_half(buf, a_base, gs, Cfg::half_pos(ROLE, ch >> 5), g0);
   }
   return inb;
 }
