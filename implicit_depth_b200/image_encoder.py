@@ -61,7 +61,8 @@ def _dwconv(g: Plan, x, cna, stride):
     y.Cl = getattr(x, "Cl", C)
     g._keep += [wt, bias]
     g.add(lambda: _abi.call("b200_dwconv3x3_silu", _abi.ptr(x.hi), _abi.ptr(x.lo), _abi.ptr(wt), _abi.ptr(bias),
-                            _abi.ptr(y.hi), _abi.ptr(y.lo), x.B, x.H, x.W, C, stride, _abi.stream_ptr()))
+                            _abi.ptr(y.hi), _abi.ptr(y.lo), x.B, x.H, x.W, C, stride, _abi.stream_ptr()),
+          reads=[x], writes=[y])
     return y
 
 
@@ -80,7 +81,7 @@ def _squeeze_excite(g: Plan, x, se):
     g._keep += [w1, b1, w2, b2]
     g.add(lambda: _abi.call("b200_squeeze_excite", _abi.ptr(x.hi), _abi.ptr(x.lo), _abi.ptr(w1), _abi.ptr(b1),
                             _abi.ptr(w2), _abi.ptr(b2), _abi.ptr(mean), _abi.ptr(scale), _abi.ptr(x.hi),
-                            _abi.ptr(x.lo), x.B, x.H * x.W, C, S, _abi.stream_ptr()), launches=3)
+                            _abi.ptr(x.lo), x.B, x.H * x.W, C, S, _abi.stream_ptr()), launches=3, reads=[x], writes=[x])
     return x
 
 
@@ -136,5 +137,5 @@ def _add(g: Plan, a, b):
     out.Cl = getattr(a, "Cl", a.C)
     n = a.B * a.H * a.W * a.C
     g.add(lambda: _abi.call("b200_split_add", _abi.ptr(a.hi), _abi.ptr(a.lo), _abi.ptr(b.hi), _abi.ptr(b.lo),
-                            _abi.ptr(out.hi), _abi.ptr(out.lo), n, _abi.stream_ptr()))
+                            _abi.ptr(out.hi), _abi.ptr(out.lo), n, _abi.stream_ptr()), reads=[a, b], writes=[out])
     return out

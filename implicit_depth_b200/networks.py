@@ -34,9 +34,14 @@ class Plan:
 
     def __init__(self, device):
         self.device = torch.device(device)
-        self.ops = []
+        self.ops = []  # (fn, reads | None, writes | None)
         self.n_launches = 0
         self._keep = []
+        import os
+
+        self.dag = os.environ.get("B200_PLAN_DAG", "1") != "0"  # dev knob: 0 = strictly sequential launches
+        self.n_streams = int(os.environ.get("B200_PLAN_STREAMS", "3"))
+        self._pool = None
 
     def act(self, B, H, W, C):
         return SplitAct(B, H, W, C, self.device)
@@ -46,13 +51,92 @@ class Plan:
         self._keep.append(t)
         return t
 
-    def add(self, fn, launches=1):
-        self.ops.append(fn)
+    def add(self, fn, launches=1, reads=None, writes=None):
+        """Append one op.  `reads` / `writes`: the buffers (SplitActs / tensors of this plan) it touches -- ops that
+        declare them are scheduled by data dependence (see `run`); an op that declares nothing is a barrier: it
+        runs on the caller's stream after everything before it and before everything after it."""
+        self.ops.append((fn, None if reads is None else [b for b in reads if b is not None],
+                         None if writes is None else [b for b in writes if b is not None]))
         self.n_launches += launches
 
     def run(self):
-        for fn in self.ops:
-            fn()
+        """Launch the plan.  Ops with declared buffers are list-scheduled over a few CUDA streams: an op goes onto
+        the stream whose tail produced one of its inputs (chains stay on one stream, no event needed), otherwise onto
+        an idle / round-robin stream, and waits on the events of its other producers (and of earlier readers of a
+        buffer it overwrites).  Under CUDA-graph capture this becomes the true dependency DAG of the step, so the
+        independent BasicBlocks of the UNet++ decoder and the cost-volume encoder chain run side by side: kernels of
+        small grids (low-resolution layers) share the machine and the tails of full-grid kernels overlap."""
+        if not self.dag or all(r is None for _, r, _ in self.ops):
+            for fn, _, _ in self.ops:
+                fn()
+            return
+        main = torch.cuda.current_stream()
+        if self._pool is None:
+            self._pool = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams)]
+        streams = [main] + self._pool
+        n = len(streams)
+        tail = [None] * n            # index of the last op enqueued on each stream since the last barrier
+        synced = [True] + [False] * (n - 1)
+        start = torch.cuda.Event()
+        start.record(main)
+        last_write, readers, op_stream, op_event = {}, {}, {}, {}
+        rr = 0
+        for idx, (fn, reads, writes) in enumerate(self.ops):
+            if reads is None:  # barrier
+                for k in range(1, n):
+                    if tail[k] is not None:
+                        main.wait_stream(streams[k])
+                fn()
+                tail = [None] * n
+                synced = [True] + [False] * (n - 1)
+                start = torch.cuda.Event()
+                start.record(main)
+                last_write, readers = {}, {}
+                continue
+            deps = set()
+            for b in reads:
+                if id(b) in last_write:
+                    deps.add(last_write[id(b)])
+            for b in writes:
+                if id(b) in last_write:
+                    deps.add(last_write[id(b)])
+                deps.update(readers.get(id(b), ()))
+            k = None
+            for d in sorted(deps, reverse=True):
+                if tail[op_stream[d]] == d:
+                    k = op_stream[d]
+                    break
+            if k is None:
+                idle = [q for q in range(n) if tail[q] is None]
+                if idle:
+                    k = idle[0]
+                else:
+                    rr = rr % n
+                    k = rr
+                    rr += 1
+            st = streams[k]
+            if not synced[k]:
+                st.wait_event(start)
+                synced[k] = True
+            for d in deps:
+                if op_stream[d] != k:
+                    st.wait_event(op_event[d])
+            if k == 0:
+                fn()
+            else:
+                with torch.cuda.stream(st):
+                    fn()
+            ev = torch.cuda.Event()
+            ev.record(st)
+            op_event[idx], op_stream[idx], tail[k] = ev, k, idx
+            for b in reads:
+                readers.setdefault(id(b), []).append(idx)
+            for b in writes:
+                last_write[id(b)] = idx
+                readers[id(b)] = []
+        for k in range(1, n):
+            if tail[k] is not None:
+                main.wait_stream(streams[k])
 
     # ---- op builders --------------------------------------------------------------------
     def conv(self, segs, bias, cout, act="none", slope=LRELU, residual=None, want_f32=False, want_split=True,
@@ -71,14 +155,14 @@ class Plan:
         b = None if bias is None else bias.detach().to(self.device, torch.float32).contiguous()
         plan = ConvPlan([(a, w.shape[-1], s, p) for a, w, s, p in segs], [w for _, w, _, _ in segs], b, out, B, cout, act=act,
                         slope=slope, residual=residual, out_f32=out_f32)
-        self.add(plan.run)
+        self.add(plan.run, reads=[a for a, _, _, _ in segs] + [residual], writes=[out, out_f32])
         return out, out_f32
 
     def upsample2x(self, a, mode):
         out = self.act(a.B, 2 * a.H, 2 * a.W, a.C)
         m = {"bilinear": 0, "nearest": 1}[mode]
         self.add(lambda: _abi.call("b200_upsample2x", _abi.ptr(a.hi), _abi.ptr(a.lo), _abi.ptr(out.hi),
-                                   _abi.ptr(out.lo), a.B, a.H, a.W, a.C, m, _abi.stream_ptr()))
+                                   _abi.ptr(out.lo), a.B, a.H, a.W, a.C, m, _abi.stream_ptr()), reads=[a], writes=[out])
         return out
 
     def from_f32(self, getter, B, C, H, W):
@@ -94,13 +178,13 @@ class Plan:
             _abi.call("b200_f32_to_split", _abi.ptr(t), _abi.ptr(out.hi), _abi.ptr(out.lo), B, C, H, W, t.stride(0),
                       t.stride(1), t.stride(2), t.stride(3), _abi.stream_ptr())
 
-        self.add(op)
+        self.add(op, reads=[], writes=[out])
         return out
 
     def to_nchw(self, a):
         out = self.empty((a.B, a.C, a.H, a.W))
         self.add(lambda: _abi.call("b200_split_to_nchw", _abi.ptr(a.hi), _abi.ptr(a.lo), _abi.ptr(out), a.B, a.C, a.H,
-                                   a.W, _abi.stream_ptr()))
+                                   a.W, _abi.stream_ptr()), reads=[a], writes=[out])
         return out
 
     def channel_dot(self, a, conv):
@@ -114,7 +198,8 @@ class Plan:
         out_exp = self.empty((a.B, 1, a.H, a.W))
         self._keep += [w, b]
         self.add(lambda: _abi.call("b200_channel_dot_exp", _abi.ptr(a.hi), _abi.ptr(a.lo), _abi.ptr(w), _abi.ptr(b),
-                                   _abi.ptr(out_log), _abi.ptr(out_exp), a.B * a.H * a.W, a.C, _abi.stream_ptr()))
+                                   _abi.ptr(out_log), _abi.ptr(out_exp), a.B * a.H * a.W, a.C, _abi.stream_ptr()),
+                 reads=[a], writes=[out_log, out_exp])
         return out_log, out_exp
 
     def instance_norm(self, a, pad=0, act="none", slope=LRELU, eps=1e-5, f32_pixel_major=False, f32_layout=0):

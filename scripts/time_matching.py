@@ -11,7 +11,7 @@ g = Plan("cuda"); enc.plan(g, lambda: img, n, H, W)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for _ in range(3): g.run()
 tot = 0
-for i, op in enumerate(g.ops):
+for i, (op, _, _) in enumerate(g.ops):
     ts = []
     for _ in range(5):
         flush.zero_(); a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)

@@ -129,9 +129,10 @@ def test_stem_conv7_tensor_core_matches_fp64(shape):
     # run only the first op of the plan (the stem) and read its output buffer back
     g = Plan("cuda")
     enc.plan(g, lambda: img, n, H, W)
-    g.ops[0]()
+    stem_op = g.ops[0][0]  # ops are (fn, reads, writes)
+    stem_op()
     torch.cuda.synchronize()
-    s1 = [t for t in (getattr(o, "__closure__", None) and [c.cell_contents for c in o.__closure__] for o in g.ops[:1])][0]
+    s1 = [c.cell_contents for c in stem_op.__closure__]
     act = [c for c in s1 if isinstance(c, SplitAct)][0]
     got = act.float_nchw().double()
     bn = enc.net[1]
