@@ -204,6 +204,12 @@ class B200BDModel(nn.Module):
             encp = Plan(dev)  # image-prior encoder on the conv kernels
             img_feats = plan_efficientnet_v2_s(encp, self.encoder.features, lambda: slots["cur_image"], B, H, W,
                                                taps=self.encoder.TAPS)
+            # the encoder runs on its own stream from the start of the forward; every consumer in `post` waits for
+            # the one feature map it reads, so the deep encoder stages overlap the first cost-volume-encoder levels
+            for a in img_feats:
+                ev = torch.cuda.Event()
+                post.external[id(a)] = ev
+                encp.add((lambda ev=ev: ev.record()), launches=0, reads=[a], writes=[])
         else:
             img_feats = [post.from_f32((lambda i=i: slots["enc"][i]), B, enc_ch[i], H // 2 ** (i + 1),
                                        W // 2 ** (i + 1)) for i in range(5)]
@@ -265,12 +271,15 @@ class B200BDModel(nn.Module):
         cost_volume, lowest_cost, _, overall_mask = self.cost_volume.forward_pixel_major(
             cur_pm, src_pm, src_cam_T_cur_cam, cur_cam_T_src_cam, src_K, cur_invK, mn, mx, None, return_mask, B, K,
             st.h, st.w)
-        join_encoder()
+        if st.encp is None:
+            join_encoder()
         st.slots["enc"] = enc_feats
         st.slots["cv"] = cost_volume
         st.slots["rendered_depth"] = rendered_depth
         st.slots["prior"] = prior
         st.post.run()
+        if st.encp is not None:
+            join_encoder()  # formal join of the side stream (its last op already gates the decoder)
         return st.pred, lowest_cost, overall_mask, st.search_depths
 
     def sample_prior(self, rendered_depth, prior_prediction, cam_to_world, prior_world_to_cam, K, invK):

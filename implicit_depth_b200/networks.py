@@ -42,6 +42,7 @@ class Plan:
         self.dag = os.environ.get("B200_PLAN_DAG", "1") != "0"  # dev knob: 0 = strictly sequential launches
         self.n_streams = int(os.environ.get("B200_PLAN_STREAMS", "3"))
         self._pool = None
+        self.external = {}  # id(buffer produced outside this plan, possibly on another stream) -> event to wait on
 
     def act(self, B, H, W, C):
         return SplitAct(B, H, W, C, self.device)
@@ -67,10 +68,13 @@ class Plan:
         independent BasicBlocks of the UNet++ decoder and the cost-volume encoder chain run side by side: kernels of
         small grids (low-resolution layers) share the machine and the tails of full-grid kernels overlap."""
         if not self.dag or all(r is None for _, r, _ in self.ops):
+            for ev in self.external.values():
+                torch.cuda.current_stream().wait_event(ev)
             for fn, _, _ in self.ops:
                 fn()
             return
         main = torch.cuda.current_stream()
+        ext_waited = set()
         if self._pool is None:
             self._pool = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams)]
         streams = [main] + self._pool
@@ -86,6 +90,10 @@ class Plan:
                 for k in range(1, n):
                     if tail[k] is not None:
                         main.wait_stream(streams[k])
+                for b, ev in self.external.items():
+                    if (0, b) not in ext_waited:
+                        main.wait_event(ev)
+                        ext_waited.add((0, b))
                 fn()
                 tail = [None] * n
                 synced = [True] + [False] * (n - 1)
@@ -121,6 +129,10 @@ class Plan:
             for d in deps:
                 if op_stream[d] != k:
                     st.wait_event(op_event[d])
+            for b in reads:
+                if id(b) in self.external and (k, id(b)) not in ext_waited:
+                    st.wait_event(self.external[id(b)])
+                    ext_waited.add((k, id(b)))
             if k == 0:
                 fn()
             else:
