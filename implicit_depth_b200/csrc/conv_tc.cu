@@ -449,6 +449,7 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   }
   const int items = k.B * k.tiles_x * k.tiles_y * k.n_ntiles;
   p->grid = items < n_sm ? items : n_sm;
+  if (b200_sm_cap() > 0 && p->grid > b200_sm_cap()) p->grid = b200_sm_cap();
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -368,6 +368,7 @@ static int launch_fv_tc(const FvTcParams& prm, int n_sm, cudaStream_t stream) {
   const int N = prm.h * prm.w;
   const long long total_tiles = (long long)prm.B * ((N + FVT_ROWS - 1) / FVT_ROWS) * prm.D;
   int grid = n_sm;
+  if (b200_sm_cap() > 0 && grid > b200_sm_cap()) grid = b200_sm_cap();
   if ((long long)grid * 2 > total_tiles) grid = (int)((total_tiles + 1) / 2);
   fv_tc_kernel<K><<<grid, FVT_THREADS, smem, stream>>>(prm);
   B200_CHECK_LAUNCH("fv_mlp_tc");

@@ -283,6 +283,7 @@ extern "C" int b200_stem_conv7_tc(const float* img, const void* wimage, const fl
   }
   const long long total_tiles = (long long)n_img * p.tiles_x * p.tiles_y;
   int grid = n_sm;
+  if (b200_sm_cap() > 0 && grid > b200_sm_cap()) grid = b200_sm_cap();
   if ((long long)grid * 2 > total_tiles) grid = (int)((total_tiles + 1) / 2);
   stem_tc_kernel<<<grid, ST_THREADS, ST_SMEM, (cudaStream_t)stream>>>(p);
   B200_CHECK_LAUNCH("stem_conv7_tc");

@@ -14,6 +14,13 @@ void b200_set_error(const char* fmt, ...) {
 }
 extern "C" int b200_abi_version(void) { return 1; }
 
+static int g_sm_cap = 0;
+extern "C" int b200_sm_cap(void) { return g_sm_cap; }
+extern "C" int b200_set_sm_cap(int n) {
+  g_sm_cap = n < 0 ? 0 : n;
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // One thread per (b, k): P = (K @ T)[:3], M = P3 @ invK3, t, pose distances.
 // One thread per (b, d): z_d = exp(log zmin + log(zmax / zmin) * ramp_d)   (cost_volume.py:123-126)

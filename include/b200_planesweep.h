@@ -20,6 +20,10 @@
 extern "C" {
 #endif
 
+/* Upper bound on the CTAs of the persistent kernels planned / launched from now on (0 = all SMs): keeps SMs free for
+ * work the caller runs concurrently on another stream. */
+int b200_set_sm_cap(int n);
+int b200_sm_cap(void);
 int b200_abi_version(void);
 const char* b200_last_error(void);
 
