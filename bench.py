@@ -205,9 +205,12 @@ def main_b200(args):
         raise SystemExit("bench.py --impl b200 needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # keeps NCCL's banner off stdout (one JSON line)
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL prints its version banner on stdout from native code: send fd 1 to stderr until the JSON line is due
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     _abi.load()
     torch.set_grad_enabled(False)
@@ -399,6 +402,10 @@ def main_b200(args):
         "roofline": roofline, "roofline_warp_dot": roofline_dot, "stage_ms": stage_ms, "clocks": clocks,
         "cpu_baseline": cpu_baseline,
     }
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
