@@ -44,6 +44,7 @@ SIGNATURES = {
     "b200_squeeze_excite": [c_f] * 10 + [c_i] * 4 + [ctypes.c_void_p],
     "b200_split_add": [c_f] * 6 + [c_ll, ctypes.c_void_p],
     "b200_channel_dot_exp": [c_f] * 6 + [c_ll, c_i, ctypes.c_void_p],
+    "b200_sigmoid_resize": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, ctypes.c_float, c_i, c_i, ctypes.c_void_p],
     "b200_set_sm_cap": [c_i],
     "b200_sm_cap": [],
     "b200_sample_prior": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],

@@ -79,6 +79,14 @@ struct FvCfg {
   __host__ __device__ static constexpr int half_pos(int role, int h) { return h < HMIN ? 2 * h + role : 2 * HMIN + (h - HMIN); }
 };
 
+// 16-byte shared-memory load through an explicit shared address (the tables are carved out of the dynamic shared
+// memory block through generic pointers, which otherwise compile to generic LD.32, one per value).
+__device__ __forceinline__ float4 lds4(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(tc::smem_u32(p)));
+  return v;
+}
+
 // Flush one 32-channel half (global half index `hg` within the row) into the ring slot of its chunk.
 // `g0` = chunks issued by this group before this tile: chunk G = g0 + hg/2 lives in slot G & 1 and is that slot's
 // (G >> 1)-th use.
@@ -260,11 +268,14 @@ __global__ void __launch_bounds__(FVT_THREADS, 1) fv_tc_kernel(const FvTcParams 
         tc::wait_ld();
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = 32 * q + 2 * j;
-          const float v0 = leaky(__uint_as_float(r[2 * j]) + my_bias[n], 0.01f);
-          const float v1 = leaky(__uint_as_float(r[2 * j + 1]) + my_bias[n + 1], 0.01f);
-          tc::split2(v0, v1, hi[j], lo[j]);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bb = lds4(my_bias + 32 * q + 4 * j4);
+          const float v0 = leaky(__uint_as_float(r[4 * j4]) + bb.x, 0.01f);
+          const float v1 = leaky(__uint_as_float(r[4 * j4 + 1]) + bb.y, 0.01f);
+          const float v2 = leaky(__uint_as_float(r[4 * j4 + 2]) + bb.z, 0.01f);
+          const float v3 = leaky(__uint_as_float(r[4 * j4 + 3]) + bb.w, 0.01f);
+          tc::split2(v0, v1, hi[2 * j4], lo[2 * j4]);
+          tc::split2(v2, v3, hi[2 * j4 + 1], lo[2 * j4 + 1]);
         }
         tc::tmem_st16(a_base + 16 * q, hi);
         tc::tmem_st16(a_base + 64 + 16 * q, lo);
@@ -284,8 +295,13 @@ __global__ void __launch_bounds__(FVT_THREADS, 1) fv_tc_kernel(const FvTcParams 
         tc::tmem_ld32(acc_base + 32 * q, r);
         tc::wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          o = fmaf(leaky(__uint_as_float(r[j]) + b2_s[32 * q + j], 0.01f), w3_s[32 * q + j], o);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bb = lds4(b2_s + 32 * q + 4 * j4), ww = lds4(w3_s + 32 * q + 4 * j4);
+          o = fmaf(leaky(__uint_as_float(r[4 * j4]) + bb.x, 0.01f), ww.x, o);
+          o = fmaf(leaky(__uint_as_float(r[4 * j4 + 1]) + bb.y, 0.01f), ww.y, o);
+          o = fmaf(leaky(__uint_as_float(r[4 * j4 + 2]) + bb.z, 0.01f), ww.z, o);
+          o = fmaf(leaky(__uint_as_float(r[4 * j4 + 3]) + bb.w, 0.01f), ww.w, o);
+        }
       }
       float2* slot = my_part + (tiles & 1u) * FVT_ROWS + row;
       if (role == 1) *slot = make_float2(o, inb ? 1.f : 0.f);

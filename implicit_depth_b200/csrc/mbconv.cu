@@ -274,3 +274,52 @@ extern "C" int b200_channel_dot_exp(const void* in_hi, const void* in_lo, const 
   B200_CHECK_LAUNCH("channel_dot_exp");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// Output side of the evaluation scripts: sigmoid_custom (modules/layers.py:138-139) followed by
+// F.interpolate to the ground-truth size, bilinear (align_corners=False) or nearest (test_bd.py:225-243,
+// inference/inference.py:159-162), one pass.  in [N, h, w] -> out [N, H, W] fp32 (N = B * planes).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sigmoid_resize_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int h, int w, int H, int W,
+                      float multiplier, int nearest, int apply_sigmoid) {
+  const size_t total = (size_t)N * H * W;
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;  // ATen area_pixel_compute_scale (no align_corners)
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W);
+    const int Y = (int)((i / W) % H);
+    const float* src = in + (i / ((size_t)W * H)) * (size_t)h * w;
+    float v;
+    if (nearest) {  // ATen nearest_neighbor_compute_source_index: min(floor(dst * scale), size - 1)
+      const int y = min((int)floorf(Y * sy), h - 1), x = min((int)floorf(X * sx), w - 1);
+      v = src[y * w + x];
+      if (apply_sigmoid) v = 1.f / (1.f + expf(-multiplier * v));
+    } else {        // ATen area_pixel_compute_source_index: max((dst + 0.5) * scale - 0.5, 0)
+      const float fy = fmaxf((Y + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf((X + 0.5f) * sx - 0.5f, 0.f);
+      const int y0 = min((int)fy, h - 1), x0 = min((int)fx, w - 1);
+      const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+      const float ly = fy - (float)y0, lx = fx - (float)x0;
+      float t00 = src[y0 * w + x0], t01 = src[y0 * w + x1], t10 = src[y1 * w + x0], t11 = src[y1 * w + x1];
+      if (apply_sigmoid) {  // the reference applies the sigmoid BEFORE interpolating
+        t00 = 1.f / (1.f + expf(-multiplier * t00));
+        t01 = 1.f / (1.f + expf(-multiplier * t01));
+        t10 = 1.f / (1.f + expf(-multiplier * t10));
+        t11 = 1.f / (1.f + expf(-multiplier * t11));
+      }
+      v = (1.f - ly) * ((1.f - lx) * t00 + lx * t01) + ly * ((1.f - lx) * t10 + lx * t11);
+    }
+    out[i] = v;
+  }
+}
+
+extern "C" int b200_sigmoid_resize(const float* in, float* out, int N, int h, int w, int H, int W, float multiplier,
+                                   int nearest, int apply_sigmoid, void* stream) {
+  B200_CHECK_ARG(in && out && N > 0 && h > 0 && w > 0 && H > 0 && W > 0, "sigmoid_resize: bad arguments");
+  const size_t total = (size_t)N * H * W;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sigmoid_resize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, N, h, w, H, W, multiplier, nearest,
+                                                                 apply_sigmoid);
+  B200_CHECK_LAUNCH("sigmoid_resize");
+  return 0;
+}

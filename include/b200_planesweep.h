@@ -162,6 +162,12 @@ int b200_split_add(const void* a_hi, const void* a_lo, const void* b_hi, const v
 int b200_channel_dot_exp(const void* in_hi, const void* in_lo, const float* w, const float* bias, float* out_log,
                          float* out_exp, long long n_pix, int C, void* stream);
 
+/* Output side of the evaluation scripts: sigmoid_custom (modules/layers.py:138-139) + F.interpolate to the
+ * ground-truth size, bilinear (align_corners=False) or nearest (test_bd.py:225-243, inference/inference.py:159-162).
+ * in [N,h,w] -> out [N,H,W] fp32; apply_sigmoid = 0 resizes only (rendered_depth / search_depths, test_bd.py:245-271). */
+int b200_sigmoid_resize(const float* in, float* out, int N, int h, int w, int H, int W, float multiplier, int nearest,
+                        int apply_sigmoid, void* stream);
+
 /* Matching-encoder stem conv 7x7/2 (3->64, BatchNorm folded) + ReLU (modules/networks.py:264-266):
  * img fp32 NCHW [n,3,H,W]; wt [147,64] tap-major (c,dy,dx); out NHWC split [n,H/2,W/2,64]. */
 int b200_stem_conv7(const float* img, const float* wt, const float* bias, void* out_hi, void* out_lo, int n_img,

@@ -346,3 +346,21 @@ def test_scheduled_plan_is_bit_identical_to_sequential_launches(monkeypatch):
         for o in run("1", "1", graph, 4):
             for k in ("pred_0", "lowest_cost_bhw", "overall_mask_bhw"):
                 assert torch.equal(o[k], ref[k]), f"{k} differs (graph={graph})"
+
+
+@pytest.mark.parametrize("mode", ["bilinear", "nearest"])
+def test_sigmoid_upsample_matches_torch(mode):
+    """sigmoid_custom + F.interpolate of test_bd.py:225-243 as one kernel, against torch on the GPU."""
+    import torch.nn.functional as F
+
+    from implicit_depth_b200 import postprocess
+
+    torch.manual_seed(5)
+    for (B, P, h, w, H, W) in ((2, 8, 96, 128, 480, 640), (1, 3, 37, 53, 111, 74), (1, 1, 192, 256, 192, 256)):
+        x = torch.randn(B, P, h, w, device="cuda") * 3
+        for mult in (1.0, 2.5):
+            ref = F.interpolate(1 / (1 + torch.exp(-mult * x)), size=(H, W), mode=mode)
+            got = postprocess.sigmoid_upsample(x, (H, W), multiplier=mult, mode=mode)
+            assert got.shape == ref.shape and (got - ref).abs().max().item() < 2e-6
+        ref = F.interpolate(x, size=(H, W), mode=mode)
+        assert (postprocess.resize(x, (H, W), mode=mode) - ref).abs().max().item() < 2e-6
