@@ -16,6 +16,6 @@ NO_SIMT=1 timeout 300 ncu --set full --clock-control none --import-source on -k 
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_halo -s 3 -c 1 \
     -f -o gpurun_out/prof_conv python scripts/time_conv.py > gpurun_out/ncu_conv.log 2>&1
 timeout 300 python scripts/plane_sweep.py > gpurun_out/plane_sweep.log 2>&1; cat gpurun_out/plane_sweep.log
-timeout 300 python scripts/torch_gpu_baseline.py > gpurun_out/torch_gpu_baseline.json 2> gpurun_out/torch_gpu_baseline.err; cat gpurun_out/torch_gpu_baseline.json; tail -3 gpurun_out/torch_gpu_baseline.err
+
 for f in gpurun_out/ncu_*.log; do tail -n 2 $f; done
 ls -la gpurun_out
