@@ -126,23 +126,48 @@ se_pool_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __rest
   }
 }
 
-// excitation: block = (256-channel slice, frame).  w1 [S][C], b1 [S], w2t [S][C] (fc2 transposed: coalesced over
-// channels), b2 [C]  (fp32, S <= 128).  Every block recomputes the small fc1 (S x C MACs) for its frame.
-__global__ void __launch_bounds__(256)
+// excitation: block = (512-channel slice, frame), 16 warps.  w1 [S][C], b1 [S], w2t [S][C] (fc2 transposed:
+// coalesced over channels), b2 [C]  (fp32, S <= 128).  Every block recomputes the small fc1 (S x C MACs) for its
+// frame: a warp takes four rows at a time, eight channel steps unrolled = 32 independent weight loads in flight per
+// lane (the kernel is pure load latency; it sits on the critical path of every MBConv block).
+#define SE_FC_THREADS 512
+__global__ void __launch_bounds__(SE_FC_THREADS)
 se_fc_kernel(const float* __restrict__ mean, const float* __restrict__ w1, const float* __restrict__ b1,
              const float* __restrict__ w2t, const float* __restrict__ b2, float* __restrict__ scale, int C, int S) {
   __shared__ float s1[128];
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* m = mean + (size_t)b * C;
-  // fc1: a warp takes four rows at a time (four independent load streams sharing the mean vector)
-  for (int j0 = warp * 4; j0 < S; j0 += 32) {
+  for (int j0 = warp * 4; j0 < S; j0 += 4 * (SE_FC_THREADS / 32)) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-    for (int c = lane; c < C; c += 32) {
-      const float mv = m[c];
+    const float* r0 = w1 + (size_t)min(j0, S - 1) * C;
+    const float* r1 = w1 + (size_t)min(j0 + 1, S - 1) * C;
+    const float* r2 = w1 + (size_t)min(j0 + 2, S - 1) * C;
+    const float* r3 = w1 + (size_t)min(j0 + 3, S - 1) * C;
+    int c = lane;
+    for (; c + 7 * 32 < C; c += 8 * 32) {
+      float mv[8], a0[8], a1[8], a2[8], a3[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (j0 + i < S) acc[i] = fmaf(__ldg(w1 + (size_t)(j0 + i) * C + c), mv, acc[i]);
+      for (int u = 0; u < 8; ++u) {
+        mv[u] = __ldg(m + c + 32 * u);
+        a0[u] = __ldg(r0 + c + 32 * u);
+        a1[u] = __ldg(r1 + c + 32 * u);
+        a2[u] = __ldg(r2 + c + 32 * u);
+        a3[u] = __ldg(r3 + c + 32 * u);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc[0] = fmaf(a0[u], mv[u], acc[0]);
+        acc[1] = fmaf(a1[u], mv[u], acc[1]);
+        acc[2] = fmaf(a2[u], mv[u], acc[2]);
+        acc[3] = fmaf(a3[u], mv[u], acc[3]);
+      }
+    }
+    for (; c < C; c += 32) {
+      const float mv = __ldg(m + c);
+      acc[0] = fmaf(__ldg(r0 + c), mv, acc[0]);
+      acc[1] = fmaf(__ldg(r1 + c), mv, acc[1]);
+      acc[2] = fmaf(__ldg(r2 + c), mv, acc[2]);
+      acc[3] = fmaf(__ldg(r3 + c), mv, acc[3]);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -153,10 +178,10 @@ se_fc_kernel(const float* __restrict__ mean, const float* __restrict__ w1, const
     }
   }
   __syncthreads();
-  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int c = blockIdx.x * SE_FC_THREADS + threadIdx.x;
   if (c < C) {
     float acc = b2[c];
-#pragma unroll 8
+#pragma unroll 16
     for (int j = 0; j < S; ++j) acc = fmaf(__ldg(w2t + (size_t)j * C + c), s1[j], acc);
     scale[(size_t)b * C + c] = sigmoidf_fast(acc);
   }
@@ -194,7 +219,8 @@ extern "C" int b200_squeeze_excite(const void* in_hi, const void* in_lo, const f
   cudaStream_t st = (cudaStream_t)stream;
   se_pool_kernel<<<dim3((C + 63) / 64, B), 256, 0, st>>>((const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo,
                                                         mean_ws, HW, C);
-  se_fc_kernel<<<dim3((C + 255) / 256, B), 256, 0, st>>>(mean_ws, w1, b1, w2t, b2, scale_ws, C, S);
+  se_fc_kernel<<<dim3((C + SE_FC_THREADS - 1) / SE_FC_THREADS, B), SE_FC_THREADS, 0, st>>>(mean_ws, w1, b1, w2t, b2,
+                                                                                          scale_ws, C, S);
   const size_t total = (size_t)B * HW * (C / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
