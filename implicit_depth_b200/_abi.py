@@ -30,6 +30,7 @@ SIGNATURES = {
     "b200_conv_run": [ctypes.c_void_p, ctypes.c_void_p],
     "b200_conv_destroy": [ctypes.c_void_p],
     "b200_conv_ntile": [c_i],
+    "b200_conv_ntile_for": [ctypes.c_void_p],
     "b200_conv_wimage_bytes": [ctypes.c_void_p, ctypes.c_void_p, c_i, c_i, c_i],
     "b200_conv_uses_halo": [ctypes.c_void_p],
     "b200_f32_to_split": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_ll, c_ll, c_ll, c_ll, ctypes.c_void_p],

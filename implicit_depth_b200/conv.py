@@ -78,13 +78,13 @@ def _swizzle64_last(t):
     return torch.gather(v, -2, idx).reshape(t.shape)
 
 
-def pack_conv_weights(weights, seg_channels, cout, halo=False):
+def pack_conv_weights(weights, seg_channels, cout, halo=False, nt=None):
     """weights: list (one per segment) of [Cout, C_s, k, k] fp32 tensors.  Returns the uint8 weight image in the
     producer's chunk order (plain: segment, tap, channel block; halo: segment, channel block, tap):
       plain kernel  [n_ntiles][chunk][hi NT x 64 | lo NT x 64]  64-channel chunks, 128-byte swizzle
       halo kernel   [n_ntiles][chunk][hi NT x 32 | lo NT x 32]  32-channel chunks, 64-byte swizzle; hi and lo are
                     adjacent rows of ONE tile so that A_hi x [B_hi | B_lo] is a single N = 2*NT MMA."""
-    NT = ntile(cout)
+    NT = ntile(cout) if nt is None else nt
     n_nt = (cout + NT - 1) // NT
     cw = 32 if halo else 64
     chunks = []
@@ -135,7 +135,8 @@ class ConvPlan:
         d.slope = slope
         lib = _abi.load()
         self.halo = bool(lib.b200_conv_uses_halo(ctypes.byref(d)))  # decides the weight-image layout
-        wimage = pack_conv_weights(weights, [a.C for a, _, _, _ in segs], cout, halo=self.halo)
+        self.nt = int(lib.b200_conv_ntile_for(ctypes.byref(d)))  # N tile of this conv (weight-image layout)
+        wimage = pack_conv_weights(weights, [a.C for a, _, _, _ in segs], cout, halo=self.halo, nt=self.nt)
         d.wimage = wimage.data_ptr()
         self._keep = (segs, wimage, bias, out, residual, out_f32)  # keep buffers alive
         self.handle = ctypes.c_void_p()

@@ -280,6 +280,19 @@ struct b200_conv_desc {
 
 extern "C" int b200_conv_ntile(int Cout) { return Cout <= 128 ? Cout : 128; }
 
+extern "C" int b200_conv_uses_halo(const b200_conv_desc* d);
+
+// N tile of a particular conv (decides the weight-image layout together with b200_conv_uses_halo).  The plain ring
+// kernel on a low-resolution map has only a handful of 128-pixel M tiles, each streaming ALL of its weights: with
+// fewer items than half the SMs a 64-wide N tile doubles the CTAs and halves the weight stream per CTA (the
+// 1536 -> 256 project convs of the image encoder at 12x16: 16 CTAs x 24 chunks -> 32 CTAs).
+extern "C" int b200_conv_ntile_for(const b200_conv_desc* d) {
+  const int nt = b200_conv_ntile(d->Cout);
+  if (nt < 128 || b200_conv_uses_halo(d) || getenv("B200_CONV_NT128") != nullptr) return nt;
+  const int m_tiles = d->B * ((d->OW + CV_TW - 1) / CV_TW) * ((d->OH + CV_TH - 1) / CV_TH);
+  return (m_tiles * (d->Cout / 128) <= 74) ? 64 : 128;
+}
+
 // 1 if this conv runs on the halo kernel (weight image in 32-channel chunks, 64-byte swizzle, [hi | lo] per
 // chunk), 0 for the plain kernel (64-channel chunks, 128-byte swizzle).  Pure function of the geometry.
 extern "C" int b200_conv_uses_halo(const b200_conv_desc* d) {
@@ -336,7 +349,7 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   int dev = 0, n_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  k.NT = b200_conv_ntile(d->Cout);
+  k.NT = b200_conv_ntile_for(d);
   k.n_ntiles = (d->Cout + k.NT - 1) / k.NT;
   const bool halo = b200_conv_uses_halo(d) != 0;
   k.halo = halo ? 1 : 0;

@@ -116,6 +116,9 @@ typedef struct {
   float slope;
 } b200_conv_desc;
 int b200_conv_ntile(int Cout);
+/* N tile of this particular conv (64 instead of 128 for ring-kernel convs with few M tiles); the weight image must be
+ * packed for it. */
+int b200_conv_ntile_for(const b200_conv_desc* d);
 /* which kernel (and weight-image layout) a conv gets: 1 = halo-patch kernel (all segments stride 1, Cout % 64 == 0,
  * no fp32 copy), 0 = per-tap kernel.  Depends only on the geometry fields of the descriptor. */
 int b200_conv_uses_halo(const b200_conv_desc* desc);
