@@ -31,14 +31,14 @@ WORKLOAD = "cfg2: B=4 per GPU, 512x384, 7 source views, 64 depth planes, implici
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2 (B=4) from the committed `ncu --set full` captures
 # (the cost volume written by either kernel stays in the 126 MB L2 for the consuming kernel, hence ~ the input bytes)
-NCU_SOURCE = "profiles/r01d_ncu_full_volume.md"
+NCU_SOURCE = "profiles/r01e_ncu_full_volume.md"
 NCU_DRAM_BYTES = {"fv_tc_kernel": 24.3e6, "cv_dot_kernel": 23.6e6}
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
