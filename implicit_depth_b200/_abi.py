@@ -49,6 +49,8 @@ SIGNATURES = {
     "b200_set_sm_cap": [c_i],
     "b200_sm_cap": [],
     "b200_sample_prior": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
+    "b200_relative_poses": [c_f] * 6 + [c_i, c_i, ctypes.c_void_p],
+    "b200_intrinsics_pyramid": [c_f, c_f, c_f, c_i, c_i, ctypes.c_void_p],
     "b200_binary_mlp_create": [ctypes.c_void_p, ctypes.c_void_p],
     "b200_binary_mlp_planes": [ctypes.c_void_p, c_f, c_i, c_f, c_f, ctypes.c_void_p],
     "b200_binary_mlp_search": [ctypes.c_void_p, c_f, c_i, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_f, c_f,

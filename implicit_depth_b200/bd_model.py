@@ -3,8 +3,8 @@
 Same call signature and output dictionary as the reference, same sub-module names and state-dict keys
 (`matching_model`, `cost_volume`, `cost_volume_net`, `depth_decoder`, `binary_mlp`, `encoder`), so
 `test_bd.py` / `inference/inference.py` can call it unchanged.  Everything on the hot path of SURVEY
-section 8 runs as hand-written sm_100a kernels; the EfficientNetV2 image-prior encoder is out of scope
- and stays a PyTorch/cuDNN module that can be injected.
+section 8 runs as hand-written sm_100a kernels, including the built-in EfficientNetV2-S image-prior encoder
+(image_encoder.py); an encoder injected by the caller stays the PyTorch/cuDNN module it is.
 """
 from __future__ import annotations
 
@@ -16,6 +16,7 @@ from torch import nn
 from . import _abi
 from .cost_volume import B200CostVolumeManager, B200FeatureVolumeManager, _Eps, _PixGrid
 from .networks import BDDecoderPP, BinaryMLPNetwork, CVEncoder, Plan, ResnetMatchingEncoder, SkipDecoder
+from .staging import StagedDict, relative_poses
 
 
 def default_options(**kw):
@@ -252,11 +253,14 @@ class B200BDModel(nn.Module):
         if st is None:
             return None
         vol = 4 if isinstance(self.cost_volume, B200FeatureVolumeManager) else 2  # prepare, kernel(, argmax)
-        return st.pre.n_launches + st.post.n_launches + vol + (st.encp.n_launches if st.encp is not None else 0)
+        # + 1: b200_relative_poses
+        return st.pre.n_launches + st.post.n_launches + vol + 1 + (st.encp.n_launches if st.encp is not None else 0)
 
     @torch.no_grad()
     def _forward_impl(self, cur_image, src_image, src_K, cur_invK, src_cam_T_world, src_world_T_cam, cur_cam_T_world,
-                      cur_world_T_cam, rendered_depth, prior, return_mask, search=False):
+                      cur_world_T_cam, rendered_depth, prior, return_mask, search=False, images_all=None):
+        """`images_all`: the matching encoder's batch [B*(K+1),3,H,W] (current frames first) when the caller staged
+        it that way (`staging.FrameStaging`); otherwise it is concatenated here like bd_model.py:162-165."""
         B, K = src_image.shape[:2]
         H, W = cur_image.shape[-2:]
         P = rendered_depth.shape[1]
@@ -264,9 +268,9 @@ class B200BDModel(nn.Module):
         if key not in self._state or self._state[key].feat_layout != self.cost_volume.FEAT_LAYOUT:
             self._state = {key: self._build(B, K, H, W, P, cur_image.device, search)}
         st = self._state[key]
-        # relative poses, bd_model.py:196-204
-        src_cam_T_cur_cam = src_cam_T_world @ cur_world_T_cam.unsqueeze(1)
-        cur_cam_T_src_cam = cur_cam_T_world.unsqueeze(1) @ src_world_T_cam
+        # relative poses, bd_model.py:196-204: both batched products in one launch
+        src_cam_T_cur_cam, cur_cam_T_src_cam = relative_poses(src_cam_T_world, src_world_T_cam, cur_cam_T_world,
+                                                              cur_world_T_cam)
         # image-prior encoder: native plan on a side stream, or the injected PyTorch module
         if st.encp is not None:
             st.slots["cur_image"] = cur_image
@@ -274,7 +278,8 @@ class B200BDModel(nn.Module):
         else:
             enc_feats, join_encoder = self._run_image_encoder(cur_image)
         # matching features for the current + source frames in one batch-invariant pass
-        st.slots["images"] = torch.cat([cur_image, src_image.reshape(B * K, 3, H, W)], 0).contiguous()
+        st.slots["images"] = images_all if images_all is not None else \
+            torch.cat([cur_image, src_image.reshape(B * K, 3, H, W)], 0).contiguous()
         st.pre.run()
         N = st.h * st.w
         cur_pm = st.feats_pm[:B]
@@ -317,6 +322,15 @@ class B200BDModel(nn.Module):
                   _abi.ptr(f(invK)), _abi.ptr(out), B, H, W, _abi.stream_ptr())
         return out
 
+    def _staged_images(self, cur_data, src_data, cur_image):
+        """The staged matching-encoder batch when both dictionaries are views of one device `StagedFrame`."""
+        frame = getattr(cur_data, "frame", None)
+        staged = (isinstance(cur_data, StagedDict) and isinstance(src_data, StagedDict) and frame is not None
+                  and src_data.frame is frame and frame.buf.is_cuda
+                  and frame.staging.matching_scale == self.run_opts.matching_scale
+                  and cur_image.data_ptr() == frame.fields["images"].data_ptr())
+        return frame.fields["images"] if staged else None
+
     @torch.no_grad()
     def forward(self, phase, cur_data, src_data, unbatched_matching_encoder_forward=False, return_mask=False,
                 infer_depth=False, infer_res=None):
@@ -344,10 +358,15 @@ class B200BDModel(nn.Module):
                 cur_data["prior_mask"] = prior
             else:
                 prior = -torch.ones_like(args[-1][:, :1]).contiguous()  # bd_model.py:433-434
+        # a batch staged by `staging.FrameStaging` (one buffer, images already in matching-encoder order): the
+        # forward reads the staging slot in place -- no per-tensor copies, no image concatenation
+        images_all = self._staged_images(cur_data, src_data, args[0])
         if self.use_cuda_graph:
-            pred, lowest, mask, search = self._forward_graphed(args, prior, return_mask, bool(infer_depth))
+            pred, lowest, mask, search = self._forward_graphed(args, prior, return_mask, bool(infer_depth),
+                                                               images_all=images_all)
         else:
-            pred, lowest, mask, search = self._forward_impl(*args, prior, return_mask, bool(infer_depth))
+            pred, lowest, mask, search = self._forward_impl(*args, prior, return_mask, bool(infer_depth),
+                                                            images_all=images_all)
             pred, search = _clone(pred), _clone(search)
         out = {"pred_0": pred}
         if infer_depth:
@@ -357,25 +376,37 @@ class B200BDModel(nn.Module):
         return out
 
     # ------------------------------------------------------------------------------------
-    def _forward_graphed(self, args, prior, return_mask, search=False):
-        """Whole forward captured once per input signature into a CUDA graph and replayed."""
-        key = tuple(tuple(a.shape) for a in args) + (prior is not None, return_mask, search)
+    MAX_STAGED_GRAPHS = 8  # one graph per staging slot in use (FramePipeline has two)
+
+    def _forward_graphed(self, args, prior, return_mask, search=False, images_all=None):
+        """Whole forward captured once per input signature into a CUDA graph and replayed.  Ordinary inputs are
+        copied into the graph's static tensors every call; a staged batch (`images_all` given) is read in place:
+        the graph is captured on the staging slot itself, one graph per slot, all sharing the launch plans."""
+        sig = tuple(tuple(a.shape) for a in args) + (prior is not None, return_mask, search)
+        key = sig + ((images_all.data_ptr(),) if images_all is not None else ())
         if key not in self._graphs:
-            static = [a.clone() for a in args]
+            static = list(args) if images_all is not None else [a.clone() for a in args]
             sprior = None if prior is None else prior.clone()
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 for _ in range(2):  # warm-up: builds plans, packs weights, sets kernel attributes
-                    self._forward_impl(*static, sprior, return_mask, search)
+                    self._forward_impl(*static, sprior, return_mask, search, images_all=images_all)
             torch.cuda.current_stream().wait_stream(s)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                outs = self._forward_impl(*static, sprior, return_mask, search)
-            self._graphs = {key: (graph, static, sprior, outs)}
-        graph, static, sprior, outs = self._graphs[key]
+                outs = self._forward_impl(*static, sprior, return_mask, search, images_all=images_all)
+            # graphs of the same signature (other staging slots, the dictionary path) replay the same launch plans:
+            # keep them; any other signature rebuilt the plans, so its graphs are dropped
+            keep = {k: v for k, v in self._graphs.items() if k[:len(sig)] == sig}
+            while len(keep) >= self.MAX_STAGED_GRAPHS:
+                keep.pop(next(iter(keep)))
+            keep[key] = (graph, static, sprior, outs, images_all is not None)
+            self._graphs = keep
+        graph, static, sprior, outs, in_place = self._graphs[key]
         for s_, a in zip(static, args):
-            s_.copy_(a)
+            if not in_place or s_.data_ptr() != a.data_ptr():  # (a staged entry the caller replaced is copied in)
+                s_.copy_(a)
         if prior is not None:
             sprior.copy_(prior)
         graph.replay()

@@ -62,10 +62,11 @@ class B200DepthModel(B200BDModel):
         args = [f(cur_image).contiguous(), f(src_data["image_b3hw"]), f(src_data[f"K_s{ms}_b44"]),
                 f(cur_data[f"invK_s{ms}_b44"]), f(src_data["cam_T_world_b44"]), f(src_data["world_T_cam_b44"]),
                 f(cur_data["cam_T_world_b44"]), f(cur_data["world_T_cam_b44"]), no_planes]
+        images_all = self._staged_images(cur_data, src_data, args[0])
         if self.use_cuda_graph:
-            pred, lowest, mask, _ = self._forward_graphed(args, None, return_mask, False)
+            pred, lowest, mask, _ = self._forward_graphed(args, None, return_mask, False, images_all=images_all)
         else:
-            pred, lowest, mask, _ = self._forward_impl(*args, None, return_mask, False)
+            pred, lowest, mask, _ = self._forward_impl(*args, None, return_mask, False, images_all=images_all)
             pred = tuple(p.clone() for p in pred)
         out = {}
         for i in range(4):

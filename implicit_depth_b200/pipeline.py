@@ -3,11 +3,14 @@
 `FramePipeline` keeps two device-side input slots and two pinned host-side output slots and runs three CUDA
 streams: while batch i is in the forward (compute stream), batch i+1 is uploaded (copy-in stream) and the outputs
 of batch i-1 are downloaded (copy-out stream).  Ordering is by CUDA events only; the host blocks once per batch,
-on the event of the batch whose results it hands back.  This is the path `bench.py` times as `e2e`.
+on the event of the batch whose results it hands back.  This is the path `bench.py` times as `e2e`.  Batches staged
+with `staging.FrameStaging` go up as one copy and are read by the forward in place.
 """
 from __future__ import annotations
 
 import torch
+
+from .staging import FrameStaging, StagedDict, StagedFrame
 
 
 class FramePipeline:
@@ -24,9 +27,24 @@ class FramePipeline:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def _upload(self, slot, cur, src):
+    def _upload_staged(self, slot, frame):
+        """A batch staged by `staging.FrameStaging`: ONE H2D copy of the whole pinned buffer into the slot's device
+        frame, which the forward then reads in place."""
+        if not isinstance(self.slots[slot], StagedFrame) or self.slots[slot].staging.fields != frame.staging.fields:
+            self.slots[slot] = frame.staging.device_frame(self.device)
+        with torch.cuda.stream(self.s_in):
+            if self.ev_free[slot] is not None:
+                self.s_in.wait_event(self.ev_free[slot])
+            self.h2d_bytes = FrameStaging.upload(frame, self.slots[slot])
+            ev = torch.cuda.Event()
+            ev.record(self.s_in)
+        return ev
+
+    def _upload(self, slot, cur, src=None):
         """Enqueue the H2D copies of one batch on the copy-in stream; returns the event that marks their end."""
-        if self.slots[slot] is None:
+        if isinstance(cur, StagedFrame):
+            return self._upload_staged(slot, cur)
+        if not isinstance(self.slots[slot], tuple):
             mk = lambda d: {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in d.items()}
             self.slots[slot] = (mk(cur), mk(src))
         dcur, dsrc = self.slots[slot]
@@ -46,8 +64,14 @@ class FramePipeline:
     def _forward(self, slot, ev_in):
         main = torch.cuda.current_stream(self.device)
         main.wait_event(ev_in)
-        dcur, dsrc = self.slots[slot]
-        out = self.model("test", dict(dcur), dsrc, **self.kw)
+        if isinstance(self.slots[slot], StagedFrame):
+            frame = self.slots[slot]
+            dcur, dsrc = StagedDict(frame.cur), frame.src  # (the forward may add keys to cur_data)
+            dcur.frame = frame
+        else:
+            dcur, dsrc = self.slots[slot]
+            dcur = dict(dcur)
+        out = self.model("test", dcur, dsrc, **self.kw)
         if self.gather is not None:
             g = self.gather(out)
             out = {k: (g[k] if k in g else v) for k, v in out.items()}
@@ -72,17 +96,19 @@ class FramePipeline:
         return ev
 
     def run(self, host_batches):
-        """host_batches: iterable of (cur_data, src_data) dictionaries of PINNED host tensors.  Yields one dictionary
-        of pinned host tensors per batch (valid until two more batches have been yielded)."""
+        """host_batches: iterable of (cur_data, src_data) dictionaries of PINNED host tensors, or of host
+        `staging.StagedFrame`s (one pinned buffer per batch, one copy).  Yields one dictionary of pinned host tensors
+        per batch (valid until two more batches have been yielded)."""
+        as_args = lambda b: (b,) if isinstance(b, StagedFrame) else b
         pending = None  # (slot, event of the D2H copy)
         it = iter(host_batches)
         nxt = next(it, None)
         i = 0
-        ev_in = self._upload(0, *nxt) if nxt is not None else None
+        ev_in = self._upload(0, *as_args(nxt)) if nxt is not None else None
         while nxt is not None:
             slot = i & 1
             following = next(it, None)
-            ev_next = self._upload(slot ^ 1, *following) if following is not None else None
+            ev_next = self._upload(slot ^ 1, *as_args(following)) if following is not None else None
             out, ev_fwd = self._forward(slot, ev_in)
             ev_done = self._download(slot, out, ev_fwd)
             if pending is not None:

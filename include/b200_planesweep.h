@@ -211,6 +211,19 @@ int b200_binary_mlp_destroy(void* plan);
 int b200_sample_prior(const float* rendered_depth, const float* prior_prediction, const float* P, const float* invK,
                       float* out, int B, int H, int W, void* stream);
 
+/* Input side of the step.
+ * Relative poses of BDModel.forward (experiment_modules/bd_model.py:196-204), one launch for both products:
+ *   src_cam_T_cur_cam[b,k] = src_cam_T_world[b,k] @ cur_world_T_cam[b]   (cur -> src, the managers' src_extrinsics)
+ *   cur_cam_T_src_cam[b,k] = cur_cam_T_world[b] @ src_world_T_cam[b,k]   (src -> cur, the managers' src_poses)
+ *   src_* [B,K,4,4]; cur_* [B,4,4]; outputs [B,K,4,4]. */
+int b200_relative_poses(const float* src_cam_T_world, const float* src_world_T_cam, const float* cur_cam_T_world,
+                        const float* cur_world_T_cam, float* src_cam_T_cur_cam, float* cur_cam_T_src_cam, int B,
+                        int K, void* stream);
+/* Intrinsics pyramid of the datasets (datasets/scannet_dataset.py:479-484): K_s[i] = K_s0 with rows 0,1 divided by
+ * 2^i, invK_s[i] = inverse(K_s[i]) (fp64 adjugate rounded to fp32; the reference inverts with fp32 LAPACK).
+ *   K_s0 [n,4,4]; out: K_s, invK_s [levels,n,4,4]. */
+int b200_intrinsics_pyramid(const float* K_s0, float* K_s, float* invK_s, int n, int levels, void* stream);
+
 /* Self-test of the tcgen05/TMEM building blocks: D[128,N] = A[128,K] * Bm[N,K]^T on one CTA.
  *   mode 0: bf16 operands from shared memory; 1: A from tensor memory; 2/3: split-bf16 (fp32-grade)
  *   with A from tensor / shared memory.  K in {64,128,192}, N multiple of 16 up to 128. */

@@ -308,3 +308,39 @@ def sample_prior(rendered_depth, prior_prediction, cam_to_world, prior_world_to_
         v = np.where(rendered_depth[b].reshape(-1) > 0, v, dt(-1))
         out[b, 0] = v.reshape(H, W)
     return out
+
+
+# --------------------------------------------------------------------------- #
+# input side of the step; pinned by tests/golden/input_side.npz
+# --------------------------------------------------------------------------- #
+def relative_poses(src_cam_T_world, src_world_T_cam, cur_cam_T_world, cur_world_T_cam):
+    """`experiment_modules/bd_model.py:196-204`: src poses [B,K,4,4], current poses [B,4,4] ->
+    (src_cam_T_cur_cam, cur_cam_T_src_cam), the managers' `src_extrinsics` / `src_poses`."""
+    src_cam_T_cur_cam = src_cam_T_world @ cur_world_T_cam[:, None]   # bd_model.py:200
+    cur_cam_T_src_cam = cur_cam_T_world[:, None] @ src_world_T_cam   # bd_model.py:204
+    return src_cam_T_cur_cam, cur_cam_T_src_cam
+
+
+def intrinsics_pyramid(K_s0, levels=5):
+    """`datasets/scannet_dataset.py:479-484`: K_s{i} = K with rows 0, 1 divided by 2**i and its
+    inverse (`np.linalg.inv`, in the dtype of the input), i < levels.  K_s0 [..., 4, 4] ->
+    (K_s, invK_s), each [levels, ..., 4, 4]."""
+    Ks, invKs = [], []
+    for i in range(levels):
+        K_scaled = np.array(K_s0, copy=True)
+        K_scaled[..., :2, :] /= 2 ** i
+        Ks.append(K_scaled)
+        invKs.append(np.linalg.inv(K_scaled))
+    return np.stack(Ks), np.stack(invKs)
+
+
+def scaled_depth_intrinsics(K_file, file_size, depth_size, flip=False, dtype=np.float32):
+    """`datasets/scannet_dataset.py:465-477`: intrinsics read from the scan (at `file_size` = (depthWidth,
+    depthHeight)), optionally mirrored, rescaled to the configured depth resolution -- the level-0 matrix the
+    pyramid starts from."""
+    K = np.array(K_file, dtype=dtype)
+    if flip:
+        K[0, 2] = dtype(file_size[0]) - K[0, 2]
+    K[0] *= dtype(depth_size[0] / float(file_size[0]))
+    K[1] *= dtype(depth_size[1] / float(file_size[1]))
+    return K

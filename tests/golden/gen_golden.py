@@ -266,7 +266,75 @@ def temporal_goldens():
         torch.nn.Module.cuda = real_cuda
 
 
+def input_side_goldens():
+    """Input side of the step: the reference's own intrinsics pyramid
+    (`ScannetDataset.load_intrinsics`, datasets/scannet_dataset.py:435-486, run unbound on files written to a
+    scratch directory) and the relative poses its forward hands to the manager (bd_model.py:196-204, captured
+    with a forward pre-hook on `BDModel.cost_volume`)."""
+    import tempfile
+    import types
+
+    # the reference's `datasets/` is a namespace package that the installed HuggingFace `datasets` shadows
+    pkg = types.ModuleType("datasets")
+    pkg.__path__ = ["/root/reference/datasets"]
+    sys.modules["datasets"] = pkg
+    from datasets import scannet_dataset as ref_sd  # reference
+
+    import options as ref_options  # reference
+    from experiment_modules.bd_model import BDModel  # reference
+
+    from implicit_depth_b200.bd_model import B200BDModel, default_options
+
+    cams = np.array([
+        [[577.870605, 0, 319.5, 0], [0, 577.870605, 239.5, 0], [0, 0, 1, 0], [0, 0, 0, 1]],       # ScanNet depth
+        [[1170.187988, 0, 647.75, 0], [0, 1170.187988, 483.75, 0], [0, 0, 1, 0], [0, 0, 0, 1]],   # ScanNet colour
+        [[886.81, 1.5, 512.0, 0], [0, 890.2, 384.0, 0], [0, 0, 1, 0], [0, 0, 0, 1]],              # skewed pinhole
+    ], dtype=np.float64)
+    sizes = [(640, 480), (1296, 968), (1024, 768)]
+    g = {"K_file": cams, "depth_size": np.array(sizes)}
+    with tempfile.TemporaryDirectory() as root:
+        Ks, invKs = [], []
+        for i, (Kf, (dw, dh)) in enumerate(zip(cams, sizes)):
+            scan = f"scene{i:04d}_00"
+            os.makedirs(os.path.join(root, scan, "intrinsic"))
+            with open(os.path.join(root, scan, f"{scan}.txt"), "w") as f:
+                f.write(f"depthWidth = {dw}\ndepthHeight = {dh}\n")
+            np.savetxt(os.path.join(root, scan, "intrinsic", "intrinsic_depth.txt"), Kf)
+            fake = types.SimpleNamespace(scenes_path=root, include_full_depth_K=False, depth_width=256,
+                                         depth_height=192)
+            o = ref_sd.ScannetDataset.load_intrinsics(fake, scan, flip=(i == 1))
+            Ks.append(np.stack([np.asarray(o[f"K_s{j}_b44"], dtype=np.float32) for j in range(5)]))
+            invKs.append(np.stack([np.asarray(o[f"invK_s{j}_b44"], dtype=np.float32) for j in range(5)]))
+        g["K_s"] = np.stack(Ks, 1)        # [5 levels, 3 cameras, 4, 4]
+        g["invK_s"] = np.stack(invKs, 1)
+
+    opts = default_options(image_width=256, image_height=192, matching_num_depth_bins=16,
+                           feature_volume_type="simple_cost_volume", num_source_views=2)
+    mine = B200BDModel(opts)
+    synthetic.init_model_weights(mine, seed=0)
+    ro = ref_options.Options()
+    ro.image_width, ro.image_height, ro.matching_num_depth_bins = 256, 192, 16
+    ro.feature_volume_type = "simple_cost_volume"
+    ro.binary_loss_positive_weight = 1.0
+    ro.bd_edge_regularision = False
+    ref = BDModel(ro)
+    ref.load_state_dict(dict(mine.state_dict()), strict=True)
+    ref.eval()
+    seen = {}
+    ref.cost_volume.register_forward_pre_hook(lambda m, a, kw: seen.update(kw), with_kwargs=True)
+    cur, src = synthetic.make_frame_batch(4100, 2, 5, 192, 256)  # B=2, K=5 frames
+    ref("test", {k: torch.from_numpy(v) for k, v in cur.items()}, {k: torch.from_numpy(v) for k, v in src.items()},
+        unbatched_matching_encoder_forward=True, return_mask=False)
+    g["src_cam_T_cur_cam"] = seen["src_extrinsics"].numpy()
+    g["cur_cam_T_src_cam"] = seen["src_poses"].numpy()
+    np.savez_compressed(os.path.join(HERE, "input_side.npz"), **g)
+    print("input side", {k: v.shape for k, v in g.items()})
+
+
 if __name__ == "__main__":
+    if "--inputs-only" in sys.argv:
+        input_side_goldens()
+        sys.exit(0)
     if "--temporal-only" in sys.argv:
         temporal_goldens()
         sys.exit(0)
@@ -278,3 +346,4 @@ if __name__ == "__main__":
     network_goldens()
     temporal_goldens()
     depth_goldens()
+    input_side_goldens()
