@@ -161,13 +161,23 @@ class B200BDModel(nn.Module):
         # half the machine each: measured optimum on B200 (cap 148 -> 10.70 ms, 100 -> 10.16, 74 -> 9.98, 56 -> 10.27)
         return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count // 2
 
+    def _fv_sm_cap(self):
+        """CTA cap of the plane-sweep kernel (same window as `_front_sm_cap`; separate dev knob)."""
+        import os
+
+        if "B200_FV_SM_CAP" in os.environ and self.native_image_encoder and self.overlap_image_encoder:
+            return int(os.environ["B200_FV_SM_CAP"])
+        return self._front_sm_cap()
+
     def _run_native_encoder(self, st, dev):
         """Launches the native encoder plan (side stream when `overlap_image_encoder`); returns join()."""
         if not self.overlap_image_encoder:
             st.encp.run()
             return lambda: None
         if self._side is None:
-            self._side = torch.cuda.Stream(device=dev)
+            import os
+
+            self._side = torch.cuda.Stream(device=dev, priority=int(os.environ.get("B200_ENC_PRIORITY", "0")))
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
@@ -289,7 +299,7 @@ class B200BDModel(nn.Module):
         mx = torch.tensor(self.run_opts.max_matching_depth, device=cur_image.device).view(1, 1, 1, 1) \
             if not hasattr(self, "_mx") or self._mx.device != cur_image.device else self._mx
         self._mn, self._mx = mn, mx
-        _abi.call("b200_set_sm_cap", self._front_sm_cap())
+        _abi.call("b200_set_sm_cap", self._fv_sm_cap())
         try:
             cost_volume, lowest_cost, _, overall_mask = self.cost_volume.forward_pixel_major(
                 cur_pm, src_pm, src_cam_T_cur_cam, cur_cam_T_src_cam, src_K, cur_invK, mn, mx, None, return_mask, B, K,
