@@ -114,3 +114,18 @@ def _abi_bytes(K):
     from implicit_depth_b200 import _abi
 
     return _abi.load().b200_fv_tc_wimage_bytes(K)
+
+
+def test_product_never_touches_the_oracle():
+    """`oracle/` is test infrastructure: nothing under the product package may import or execute it, and the only
+    places outside tests/ that do are smoke() and bench.py's CPU-baseline legs."""
+    pkg = os.path.join(ROOT, "implicit_depth_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "oracle." not in src and "/oracle" not in src, f
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    uses = [m.start() for m in re.finditer(r"^\s*(from|import)\s+oracle\b", bench, flags=re.M)]
+    assert len(uses) == 1 and bench[:uses[0]].rfind("def cpu_reference_run") > bench[:uses[0]].rfind("def main_b200")
