@@ -161,6 +161,18 @@ class B200BDModel(nn.Module):
         # half the machine each: measured optimum on B200 (cap 148 -> 10.70 ms, 100 -> 10.16, 74 -> 9.98, 56 -> 10.27)
         return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count // 2
 
+    def _fv_schedule(self, B):
+        """Plane sweep as several launches over groups of frames, each with its own CTA cap (dev knob
+        `B200_FV_SPLIT="frames:cap,frames:cap"`): while the image encoder still runs the first frames stay on half
+        the SMs, the last ones spread over the SMs it has freed.  None = one launch under `_fv_sm_cap`."""
+        import os
+
+        spec = os.environ.get("B200_FV_SPLIT", "")
+        if not spec or not (self.native_image_encoder and self.overlap_image_encoder):
+            return None
+        sched = [tuple(int(x) for x in part.split(":")) for part in spec.split(",")]
+        return sched if sum(n for n, _ in sched) == B else None
+
     def _fv_sm_cap(self):
         """CTA cap of the plane-sweep kernel (same window as `_front_sm_cap`; separate dev knob)."""
         import os
@@ -300,6 +312,7 @@ class B200BDModel(nn.Module):
             if not hasattr(self, "_mx") or self._mx.device != cur_image.device else self._mx
         self._mn, self._mx = mn, mx
         _abi.call("b200_set_sm_cap", self._fv_sm_cap())
+        self.cost_volume.sm_schedule = self._fv_schedule(B)
         try:
             cost_volume, lowest_cost, _, overall_mask = self.cost_volume.forward_pixel_major(
                 cur_pm, src_pm, src_cam_T_cur_cam, cur_cam_T_src_cam, src_K, cur_invK, mn, mx, None, return_mask, B, K,

@@ -311,10 +311,22 @@ class B200FeatureVolumeManager(B200CostVolumeManager):
         mask = torch.empty((B, h, w), device=dev, dtype=torch.bool) if return_mask else None
         invK = _as_f32c(cur_invK)
         if self.impl in ("auto", "tc"):
-            _abi.call("b200_fv_mlp_tc", _abi.ptr(cur_pm), _abi.ptr(src_pm), _abi.ptr(cams), _abi.ptr(invK),
-                      _abi.ptr(planes), _abi.ptr(bias_eff), _abi.ptr(pk["wimage"]), _abi.ptr(pk["b2"]),
-                      _abi.ptr(pk["w3"]), _abi.ptr(pk["b3"]), _abi.ptr(vol), _abi.ptr(mask), B, K, FEAT_C, h, w, D,
-                      _abi.stream_ptr())
+            # one launch, or one per group of frames with its own CTA cap (`sm_schedule`: [(frames, cap), ...]; a
+            # caller sharing the GPU with another stream lets the later frames spread over the SMs that stream frees)
+            sched = getattr(self, "sm_schedule", None)
+            if not sched or sum(n for n, _ in sched) != B:
+                sched = [(B, None)]
+            b0 = 0
+            for nb, cap in sched:
+                if cap is not None:
+                    _abi.call("b200_set_sm_cap", int(cap))
+                sl = slice(b0, b0 + nb)
+                _abi.call("b200_fv_mlp_tc", _abi.ptr(cur_pm[sl]), _abi.ptr(src_pm[sl]), _abi.ptr(cams[sl]),
+                          _abi.ptr(invK[sl]), _abi.ptr(planes[sl]), _abi.ptr(bias_eff[sl]), _abi.ptr(pk["wimage"]),
+                          _abi.ptr(pk["b2"]), _abi.ptr(pk["w3"]), _abi.ptr(pk["b3"]), _abi.ptr(vol[sl]),
+                          _abi.ptr(mask[sl] if mask is not None else None), nb, K, FEAT_C, h, w, D,
+                          _abi.stream_ptr())
+                b0 += nb
         elif self.impl == "simt":
             _abi.call("b200_fv_mlp_simt", _abi.ptr(cur_pm), _abi.ptr(src_pm), _abi.ptr(cams), _abi.ptr(invK),
                       _abi.ptr(planes), _abi.ptr(bias_eff), _abi.ptr(pk["W1p"]), _abi.ptr(pk["W2t"]),

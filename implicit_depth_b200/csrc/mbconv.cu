@@ -5,6 +5,8 @@
 //   se_pool_kernel     squeeze: per-(frame, channel) mean over the image, deterministic two-level reduction
 //   se_fc_kernel       excitation: fc1 + SiLU + fc2 + sigmoid -> scale[b, c]  (fc2 weights transposed)
 //   se_scale_kernel    x * scale[b, c]
+//   dwconv3x3_pool_kernel / se_fc1_kernel / se_fc2_kernel   the same chain with the squeeze fused into the depthwise
+//                      conv and the excitation spread over many blocks (b200_mbconv_dw_se: what the encoder plan uses)
 // The 1x1 expand / project convolutions and the fused 3x3 convolutions run on the tensor-core conv kernels.
 #include <cuda_bf16.h>
 
@@ -227,6 +229,161 @@ extern "C" int b200_squeeze_excite(const void* in_hi, const void* in_lo, const f
   se_scale_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo, scale_ws,
                                          (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, B, HW, C);
   B200_CHECK_LAUNCH("squeeze_excite");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// MBConv middle as one chain of four short kernels: depthwise 3x3 + SiLU with the squeeze fused in, fc1, fc2, scale.
+// The separate pool pass (a second read of the expanded activation) is gone, and the excitation no longer recomputes
+// fc1 in every block: fc1 is spread over S/4 blocks per frame, fc2 over C/128, so each block streams a few KB of
+// weights instead of the whole S x C matrix (the old se_fc_kernel was pure load latency on the critical path of all
+// 30 MBConv blocks).  Every reduction has a fixed order: results are deterministic and batch-invariant.
+// ---------------------------------------------------------------------------------------
+#define DWP_PIX 32  // output pixels per block of dwconv3x3_pool_kernel = pixels per partial sum
+extern "C" int b200_mbconv_pool_block(void) { return DWP_PIX; }
+
+// Block = (32 output pixels, 64 channels, frame): thread = (pixel lane, 8 channels).  partial[b][pixel block][c] =
+// sum of the activation over the block's pixels (fixed-order tree in shared memory).
+__global__ void __launch_bounds__(256)
+dwconv3x3_pool_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                      const float* __restrict__ wt, const float* __restrict__ bias, __nv_bfloat16* __restrict__ oh,
+                      __nv_bfloat16* __restrict__ ol, float* __restrict__ partial, int H, int W, int C, int stride,
+                      int OH, int OW) {
+  __shared__ float red[DWP_PIX][65];
+  const int b = blockIdx.z, c0 = blockIdx.y * 64;
+  const int cgp = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c = c0 + cgp * 8;
+  const int p = blockIdx.x * DWP_PIX + pl;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < C && p < OH * OW) {
+    const int oy = p / OW, ox = p - oy * OW;
+    {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+      acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int y = oy * stride + dy - 1;
+      if (y < 0 || y >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int x = ox * stride + dx - 1;
+        if (x < 0 || x >= W) continue;
+        float v[8];
+        mb_load8(hi, lo, (((size_t)b * H + y) * W + x) * C + c, v);
+        const float* wp = wt + (size_t)(dy * 3 + dx) * C + c;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+        acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
+        acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
+        acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
+        acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = silu(acc[e]);
+    mb_store8(oh, ol, ((size_t)b * OH * OW + p) * C + c, acc);
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[pl][cgp * 8 + e] = acc[e];  // zeros from threads outside the image / channels
+  __syncthreads();
+  if (threadIdx.x < 64 && c0 + threadIdx.x < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < DWP_PIX; ++r) s += red[r][threadIdx.x];
+    partial[((size_t)b * gridDim.x + blockIdx.x) * C + c0 + threadIdx.x] = s;
+  }
+}
+
+// fc1 + SiLU: block = (4 rows of w1, frame), 8 warps = 4 rows x 2 interleaved halves of the channel range.  The block
+// first finishes the squeeze (mean[c] = sum of the nPB partials / HW) into shared memory.
+#define FC1_ROWS 4
+__global__ void __launch_bounds__(256)
+se_fc1_kernel(const float* __restrict__ partial, const float* __restrict__ w1, const float* __restrict__ b1,
+              float* __restrict__ s1, int C, int S, int nPB, float inv_hw) {
+  extern __shared__ float mean_s[];  // [C]
+  __shared__ float part[8];
+  const int b = blockIdx.y, j0 = blockIdx.x * FC1_ROWS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* pp = partial + (size_t)b * nPB * C;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int pb = 0; pb < nPB; ++pb) s += __ldg(pp + (size_t)pb * C + c);
+    mean_s[c] = s * inv_hw;
+  }
+  __syncthreads();
+  const int row = j0 + (warp >> 1), half = warp & 1;
+  float a = 0.f;
+  if (row < S) {
+    const float* r = w1 + (size_t)row * C;
+    int c = half * 32 + lane;
+    for (; c + 7 * 64 < C; c += 8 * 64) {
+      float wv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) wv[u] = __ldg(r + c + 64 * u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a = fmaf(wv[u], mean_s[c + 64 * u], a);
+    }
+    for (; c < C; c += 64) a = fmaf(__ldg(r + c), mean_s[c], a);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) part[warp] = a;
+  __syncthreads();
+  if (threadIdx.x < FC1_ROWS && j0 + threadIdx.x < S)
+    s1[(size_t)b * S + j0 + threadIdx.x] =
+        silu(part[2 * threadIdx.x] + part[2 * threadIdx.x + 1] + b1[j0 + threadIdx.x]);
+}
+
+// fc2 + sigmoid: block = (128 channels, frame), one channel per thread, w2t [S][C] coalesced over channels.
+__global__ void __launch_bounds__(128)
+se_fc2_kernel(const float* __restrict__ s1, const float* __restrict__ w2t, const float* __restrict__ b2,
+              float* __restrict__ scale, int C, int S) {
+  __shared__ float s1s[128];
+  const int b = blockIdx.y;
+  if (threadIdx.x < S) s1s[threadIdx.x] = s1[(size_t)b * S + threadIdx.x];
+  __syncthreads();
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c < C) {
+    float acc = b2[c];
+#pragma unroll 16
+    for (int j = 0; j < S; ++j) acc = fmaf(__ldg(w2t + (size_t)j * C + c), s1s[j], acc);
+    scale[(size_t)b * C + c] = sigmoidf_fast(acc);
+  }
+}
+
+// Depthwise 3x3 (+ folded BatchNorm bias, SiLU) followed by the squeeze-and-excitation of one MBConv block
+// (torchvision MBConv.block[1:3]): out = dw(x) * sigmoid(fc2(silu(fc1(mean_hw(dw(x)))))).
+//   wt [9][C], bias [C]; w1 [S][C], b1 [S], w2t [S][C], b2 [C] (fp32, S <= 128);
+//   workspaces: partial_ws [B][ceil(OH*OW / b200_mbconv_pool_block())][C], s1_ws [B][S], scale_ws [B][C].
+extern "C" int b200_mbconv_dw_se(const void* in_hi, const void* in_lo, const float* wt, const float* bias,
+                                 const float* w1, const float* b1, const float* w2t, const float* b2,
+                                 float* partial_ws, float* s1_ws, float* scale_ws, void* out_hi, void* out_lo, int B,
+                                 int H, int W, int C, int stride, int S, void* stream) {
+  B200_CHECK_ARG(in_hi && in_lo && wt && bias && w1 && b1 && w2t && b2 && partial_ws && s1_ws && scale_ws && out_hi &&
+                     out_lo,
+                 "mbconv_dw_se: null pointer");
+  B200_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2),
+                 "mbconv_dw_se: bad arguments (C %% 8 == 0, stride 1|2; got C=%d stride=%d)", C, stride);
+  B200_CHECK_ARG(S > 0 && S <= 128 && C <= 12288, "mbconv_dw_se: bad sizes (S <= 128, C <= 12288; got C=%d S=%d)", C, S);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int OH = (H + 2 - 3) / stride + 1, OW = (W + 2 - 3) / stride + 1;
+  const int OHW = OH * OW, nPB = (OHW + DWP_PIX - 1) / DWP_PIX;
+  dwconv3x3_pool_kernel<<<dim3(nPB, (C + 63) / 64, B), 256, 0, st>>>(
+      (const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo, wt, bias, (__nv_bfloat16*)out_hi,
+      (__nv_bfloat16*)out_lo, partial_ws, H, W, C, stride, OH, OW);
+  se_fc1_kernel<<<dim3((S + FC1_ROWS - 1) / FC1_ROWS, B), 256, (size_t)C * sizeof(float), st>>>(
+      partial_ws, w1, b1, s1_ws, C, S, nPB, 1.f / (float)OHW);
+  se_fc2_kernel<<<dim3((C + 127) / 128, B), 128, 0, st>>>(s1_ws, w2t, b2, scale_ws, C, S);
+  const size_t total = (size_t)B * OHW * (C / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  se_scale_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)out_hi, (const __nv_bfloat16*)out_lo, scale_ws,
+                                         (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, B, OHW, C);
+  B200_CHECK_LAUNCH("mbconv_dw_se");
   return 0;
 }
 

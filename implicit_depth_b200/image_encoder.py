@@ -13,6 +13,8 @@ consumers' weights are padded with zero columns (`SplitAct.Cl` = logical channel
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _abi
@@ -85,6 +87,36 @@ def _squeeze_excite(g: Plan, x, se):
     return x
 
 
+def _dwconv_se(g: Plan, x, cna, stride, se):
+    """MBConv middle: depthwise 3x3 + BN + SiLU, then SqueezeExcitation, as one chain of four short kernels with the
+    squeeze fused into the depthwise conv (`b200_mbconv_dw_se`)."""
+    conv, bn = cna[0], cna[1]
+    w, b = _fold_bn(conv.weight, bn)  # [C, 1, 3, 3]
+    C, S, cl = x.C, se.fc1.out_channels, se.fc1.in_channels
+    wt = torch.zeros((9, C), dtype=torch.float32, device=g.device)
+    wt[:, :w.shape[0]] = w.to(g.device).float().reshape(w.shape[0], 9).t()
+    bias = _padv(b.to(g.device), C)
+    w1 = torch.zeros((S, C), dtype=torch.float32, device=g.device)
+    w1[:, :cl] = se.fc1.weight.detach().to(g.device).float().reshape(S, cl)
+    b1 = se.fc1.bias.detach().to(g.device).float().contiguous()
+    w2 = torch.zeros((S, C), dtype=torch.float32, device=g.device)  # transposed: coalesced over channels
+    w2[:, :cl] = se.fc2.weight.detach().to(g.device).float().reshape(cl, S).t()
+    b2 = _padv(se.fc2.bias.to(g.device), C)
+    OH, OW = (x.H + 2 - 3) // stride + 1, (x.W + 2 - 3) // stride + 1
+    pix = _abi.load().b200_mbconv_pool_block()
+    partial = g.empty((x.B, (OH * OW + pix - 1) // pix, C))
+    s1 = g.empty((x.B, S))
+    scale = g.empty((x.B, C))
+    y = g.act(x.B, OH, OW, C)
+    y.Cl = getattr(x, "Cl", C)
+    g._keep += [wt, bias, w1, b1, w2, b2]
+    g.add(lambda: _abi.call("b200_mbconv_dw_se", _abi.ptr(x.hi), _abi.ptr(x.lo), _abi.ptr(wt), _abi.ptr(bias),
+                            _abi.ptr(w1), _abi.ptr(b1), _abi.ptr(w2), _abi.ptr(b2), _abi.ptr(partial), _abi.ptr(s1),
+                            _abi.ptr(scale), _abi.ptr(y.hi), _abi.ptr(y.lo), x.B, x.H, x.W, C, stride, S,
+                            _abi.stream_ptr()), launches=4, reads=[x], writes=[y])
+    return y
+
+
 def plan_efficientnet_v2_s(g: Plan, features, get_image, B, H, W, taps=(1, 2, 3, 5, 6)):
     """Launch plan of torchvision `efficientnet_v2_s().features[:7]` (stem + 6 stages).  Returns the SplitActs of the
     tapped stages (channels [24, 48, 64, 160, 256] at /2 .. /32; `.Cl` holds the logical channel count)."""
@@ -121,8 +153,11 @@ def plan_efficientnet_v2_s(g: Plan, features, get_image, B, H, W, taps=(1, 2, 3,
                 layers = blk.block
                 stride = layers[1][0].stride[0]
                 h = _cna(g, inp, layers[0], "silu", 1)
-                h = _dwconv(g, h, layers[1], stride)
-                h = _squeeze_excite(g, h, layers[2])
+                if os.environ.get("B200_MBCONV_FUSED", "1") != "0":  # dev knob: "0" = separate pool / fc kernels
+                    h = _dwconv_se(g, h, layers[1], stride, layers[2])
+                else:
+                    h = _dwconv(g, h, layers[1], stride)
+                    h = _squeeze_excite(g, h, layers[2])
                 x = _cna(g, h, layers[3], "none", 1, residual=res)
             else:
                 raise TypeError(f"unsupported block {type(blk).__name__}")

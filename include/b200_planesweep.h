@@ -155,6 +155,15 @@ int b200_dwconv3x3_silu(const void* in_hi, const void* in_lo, const float* wt, c
 int b200_squeeze_excite(const void* in_hi, const void* in_lo, const float* w1, const float* b1, const float* w2t,
                         const float* b2, float* mean_ws, float* scale_ws, void* out_hi, void* out_lo, int B, int HW,
                         int C, int S, void* stream);
+/* The two calls above as one chain with the squeeze fused into the depthwise conv and the excitation spread over
+ * many blocks (what the encoder plan uses): out = dw(x) * sigmoid(fc2(silu(fc1(mean_hw(dw(x)))))), torchvision
+ * MBConv.block[1:3].  Workspaces (fp32): partial_ws [B][ceil(OH*OW / b200_mbconv_pool_block())][C], s1_ws [B][S],
+ * scale_ws [B][C].  Fixed-order reductions: deterministic and batch-invariant. */
+int b200_mbconv_dw_se(const void* in_hi, const void* in_lo, const float* wt, const float* bias, const float* w1,
+                      const float* b1, const float* w2t, const float* b2, float* partial_ws, float* s1_ws,
+                      float* scale_ws, void* out_hi, void* out_lo, int B, int H, int W, int C, int stride, int S,
+                      void* stream);
+int b200_mbconv_pool_block(void);
 /* out = a + b on split activations of n elements (n % 8 == 0). */
 int b200_split_add(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* out_hi, void* out_lo,
                    long long n, void* stream);

@@ -18,8 +18,13 @@ model = B200BDModel(opts)
 synthetic.init_model_weights(model, seed=0)
 model = model.cuda().eval()
 cur, src = synthetic.make_frame_batch(2000, B, 7, 384, 512)
-cur = {k: torch.from_numpy(v).cuda() for k, v in cur.items()}
-src = {k: torch.from_numpy(v).cuda() for k, v in src.items()}
+# staged inputs (implicit_depth_b200.staging), like bench.py: the forward reads the device slot in place
+from implicit_depth_b200.staging import FrameStaging
+
+staging = FrameStaging(B, 7, 384, 512, P=8)
+frame = staging.device_frame("cuda")
+FrameStaging.upload(staging.host_frame().fill(cur, src), frame)
+cur, src = frame.cur, frame.src
 for _ in range(2):
     model("test", cur, src, return_mask=True)
 torch.cuda.synchronize()

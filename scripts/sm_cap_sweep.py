@@ -36,15 +36,18 @@ def timeit(n=15):
     ts.sort(); return ts[len(ts) // 2]
 
 
-SETTINGS = [(74, 74, 0), (74, 100, 0), (74, 124, 0), (74, 148, 0), (74, 74, -1), (74, 148, -1), (100, 148, -1),
-            (60, 100, 0), (74, 74, 0)]
+# (matching-encoder cap, plane-sweep cap, encoder stream priority, plane-sweep split "frames:cap,...")
+SETTINGS = [(74, 74, 0, ""), (74, 100, 0, ""), (74, 124, 0, ""), (74, 148, 0, ""), (74, 74, -1, ""),
+            (74, 148, -1, ""), (74, 74, 0, "2:74,2:148"), (74, 74, 0, "1:74,3:148"), (74, 74, 0, "3:74,1:148"),
+            (74, 74, 0, "2:74,1:110,1:148"), (74, 74, -1, "2:74,2:148"), (60, 60, 0, "2:60,2:148"), (74, 74, 0, "")]
 if len(sys.argv) > 1:
-    SETTINGS = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]]
-for front, fv, prio in SETTINGS:
+    SETTINGS = [tuple(a.split(";")) for a in sys.argv[1:]]
+    SETTINGS = [(int(a), int(b), int(c), d) for a, b, c, d in SETTINGS]
+for front, fv, prio, split in SETTINGS:
     os.environ["B200_FRONT_SM_CAP"], os.environ["B200_FV_SM_CAP"] = str(front), str(fv)
-    os.environ["B200_ENC_PRIORITY"] = str(prio)
+    os.environ["B200_ENC_PRIORITY"], os.environ["B200_FV_SPLIT"] = str(prio), split
     m._state, m._graphs, m._side = {}, {}, None  # plans bake the caps, the side stream its priority
     torch.cuda.synchronize()
     ms = timeit()
-    print(json.dumps({"front_cap": front, "fv_cap": fv, "enc_priority": prio, "ms_per_forward": round(ms, 3),
+    print(json.dumps({"front_cap": front, "fv_cap": fv, "enc_priority": prio, "fv_split": split, "ms_per_forward": round(ms, 3),
                       "frames_per_s": round(1000.0 * B / ms, 1)}), flush=True)
