@@ -158,8 +158,9 @@ class B200BDModel(nn.Module):
             return 0
         if "B200_FRONT_SM_CAP" in os.environ:  # dev knob
             return int(os.environ["B200_FRONT_SM_CAP"])
-        # half the machine each: measured optimum on B200 (cap 148 -> 10.70 ms, 100 -> 10.16, 74 -> 9.98, 56 -> 10.27)
-        return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count // 2
+        # a little over half the machine: measured optimum on B200 (scripts/sm_cap_sweep.py, ms per step at cfg2:
+        # cap 64 -> 9.69, 74 -> 9.10, 78 -> 8.96, 80 -> 8.92, 82 -> 9.08, 86 -> 9.07, 100 -> 9.23+)
+        return round(0.54 * torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count)
 
     def _fv_schedule(self, B):
         """Plane sweep as several launches over groups of frames, each with its own CTA cap (dev knob

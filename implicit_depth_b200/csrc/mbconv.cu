@@ -239,60 +239,68 @@ extern "C" int b200_squeeze_excite(const void* in_hi, const void* in_lo, const f
 // weights instead of the whole S x C matrix (the old se_fc_kernel was pure load latency on the critical path of all
 // 30 MBConv blocks).  Every reduction has a fixed order: results are deterministic and batch-invariant.
 // ---------------------------------------------------------------------------------------
-#define DWP_PIX 32  // output pixels per block of dwconv3x3_pool_kernel = pixels per partial sum
+#define DWP_PIX 64  // output pixels per block of dwconv3x3_pool_kernel = pixels per partial sum (2 per thread)
 extern "C" int b200_mbconv_pool_block(void) { return DWP_PIX; }
 
-// Block = (32 output pixels, 64 channels, frame): thread = (pixel lane, 8 channels).  partial[b][pixel block][c] =
-// sum of the activation over the block's pixels (fixed-order tree in shared memory).
+// Block = (64 output pixels, 64 channels, frame): thread = (pixel lane, 8 channels), two pixels per thread.
+// partial[b][pixel block][c] = sum of the activation over the block's pixels (per-thread sum in pixel order, then a
+// fixed-order tree over the 32 pixel lanes in shared memory).
 __global__ void __launch_bounds__(256)
 dwconv3x3_pool_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                       const float* __restrict__ wt, const float* __restrict__ bias, __nv_bfloat16* __restrict__ oh,
                       __nv_bfloat16* __restrict__ ol, float* __restrict__ partial, int H, int W, int C, int stride,
                       int OH, int OW) {
-  __shared__ float red[DWP_PIX][65];
+  __shared__ float red[32][65];
   const int b = blockIdx.z, c0 = blockIdx.y * 64;
   const int cgp = threadIdx.x & 7, pl = threadIdx.x >> 3;
   const int c = c0 + cgp * 8;
-  const int p = blockIdx.x * DWP_PIX + pl;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (c < C && p < OH * OW) {
-    const int oy = p / OW, ox = p - oy * OW;
-    {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
-      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
-      acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-    }
+  float pool[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int y = oy * stride + dy - 1;
-      if (y < 0 || y >= H) continue;
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int x = ox * stride + dx - 1;
-        if (x < 0 || x >= W) continue;
-        float v[8];
-        mb_load8(hi, lo, (((size_t)b * H + y) * W + x) * C + c, v);
-        const float* wp = wt + (size_t)(dy * 3 + dx) * C + c;
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
-        acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
-        acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
-        acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
-        acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+  for (int it = 0; it < DWP_PIX / 32; ++it) {
+    const int p = blockIdx.x * DWP_PIX + it * 32 + pl;
+    if (c < C && p < OH * OW) {
+      const int oy = p / OW, ox = p - oy * OW;
+      float acc[8];
+      {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+        acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+        acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
       }
-    }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = silu(acc[e]);
-    mb_store8(oh, ol, ((size_t)b * OH * OW + p) * C + c, acc);
+      for (int dy = 0; dy < 3; ++dy) {
+        const int y = oy * stride + dy - 1;
+        if (y < 0 || y >= H) continue;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int x = ox * stride + dx - 1;
+          if (x < 0 || x >= W) continue;
+          float v[8];
+          mb_load8(hi, lo, (((size_t)b * H + y) * W + x) * C + c, v);
+          const float* wp = wt + (size_t)(dy * 3 + dx) * C + c;
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+          acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
+          acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
+          acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
+          acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        acc[e] = silu(acc[e]);
+        pool[e] += acc[e];
+      }
+      mb_store8(oh, ol, ((size_t)b * OH * OW + p) * C + c, acc);
+    }
   }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) red[pl][cgp * 8 + e] = acc[e];  // zeros from threads outside the image / channels
+  for (int e = 0; e < 8; ++e) red[pl][cgp * 8 + e] = pool[e];  // zeros from threads outside the image / channels
   __syncthreads();
   if (threadIdx.x < 64 && c0 + threadIdx.x < C) {
     float s = 0.f;
 #pragma unroll
-    for (int r = 0; r < DWP_PIX; ++r) s += red[r][threadIdx.x];
+    for (int r = 0; r < 32; ++r) s += red[r][threadIdx.x];
     partial[((size_t)b * gridDim.x + blockIdx.x) * C + c0 + threadIdx.x] = s;
   }
 }
@@ -308,11 +316,27 @@ se_fc1_kernel(const float* __restrict__ partial, const float* __restrict__ w1, c
   const int b = blockIdx.y, j0 = blockIdx.x * FC1_ROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* pp = partial + (size_t)b * nPB * C;
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float s = 0.f;
-#pragma unroll 8
-    for (int pb = 0; pb < nPB; ++pb) s += __ldg(pp + (size_t)pb * C + c);
-    mean_s[c] = s * inv_hw;
+  // two channels and two partials per step, unrolled x4: 16 independent loads in flight per thread (fixed order)
+  for (int c = threadIdx.x; c < C; c += 512) {
+    const int c2 = c + 256;
+    const bool has2 = c2 < C;
+    float a0 = 0.f, a1 = 0.f, e0 = 0.f, e1 = 0.f;
+    int pb = 0;
+#pragma unroll 4
+    for (; pb + 1 < nPB; pb += 2) {
+      a0 += __ldg(pp + (size_t)pb * C + c);
+      a1 += __ldg(pp + (size_t)(pb + 1) * C + c);
+      if (has2) {
+        e0 += __ldg(pp + (size_t)pb * C + c2);
+        e1 += __ldg(pp + (size_t)(pb + 1) * C + c2);
+      }
+    }
+    if (pb < nPB) {
+      a0 += __ldg(pp + (size_t)pb * C + c);
+      if (has2) e0 += __ldg(pp + (size_t)pb * C + c2);
+    }
+    mean_s[c] = (a0 + a1) * inv_hw;
+    if (has2) mean_s[c2] = (e0 + e1) * inv_hw;
   }
   __syncthreads();
   const int row = j0 + (warp >> 1), half = warp & 1;

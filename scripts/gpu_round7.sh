@@ -1,0 +1,11 @@
+#!/bin/bash
+# Final-build check: parity suite, encoder timing, SM-cap spot check, bench line, ncu launch list of the staged step.
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -q > gpurun_out/t_gpu.log 2>&1; tail -5 gpurun_out/t_gpu.log
+timeout 100 python scripts/time_native_encoder.py > gpurun_out/time_enc2.log 2>&1; tail -2 gpurun_out/time_enc2.log
+timeout 100 python scripts/sm_cap_sweep.py "80;80;0;" "76;76;0;" "84;84;0;" "80;80;0;" > gpurun_out/mb_sweep_new4.log 2>&1; cat gpurun_out/mb_sweep_new4.log
+timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_f.json 2> gpurun_out/bench_f.err; tail -c 3000 gpurun_out/bench_f.json; tail -3 gpurun_out/bench_f.err
+timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/launches_g.csv python scripts/profile_step.py > gpurun_out/ncu_launch_g.log 2>&1; tail -2 gpurun_out/ncu_launch_g.log
+python scripts/summarize_launches.py gpurun_out/launches_g.csv 40
