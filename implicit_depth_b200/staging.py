@@ -110,6 +110,8 @@ class FrameStaging:
         return StagedFrame(self, buf.pin_memory() if pin else buf)
 
     def device_frame(self, device):
+        """A device-side slot.  Allocate a few and REUSE them (`pipeline.FramePipeline` keeps two): the forward
+        captures one CUDA graph per slot address, so a fresh slot per batch would re-capture every call."""
         return StagedFrame(self, torch.zeros(self.numel, dtype=torch.float32, device=device))
 
     @staticmethod
