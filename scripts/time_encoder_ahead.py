@@ -11,17 +11,19 @@ torch.set_grad_enabled(False)
 B, K, H, W, D = 4, 7, 384, 512, 64
 st = FrameStaging(B, K, H, W, P=8)
 hosts = []
-for i in range(3):
+for i in range(2 if os.environ.get('ONLY_AHEAD') else 3):
     cur, src = synthetic.make_frame_batch(7000 + i, B, K, H, W)
     hosts.append(st.host_frame().fill(cur, src))
 N = int(os.environ.get("STEPS", 40))
-for ahead in (False, True, False, True):
+MODES = (True,) if os.environ.get('ONLY_AHEAD') else (False, True, False, True)
+for ahead in MODES:
     m = B200BDModel(default_options(image_width=W, image_height=H, matching_num_depth_bins=D))
-    synthetic.init_model_weights(m, seed=0)
+    if not os.environ.get('NO_INIT'):
+        synthetic.init_model_weights(m, seed=0)
     m = m.cuda().eval()
     m.use_cuda_graph = True
     pipe = FramePipeline(m, "cuda", encoder_ahead=ahead, return_mask=True)
-    feed = lambda n: (hosts[i % 3] for i in range(n))
+    feed = lambda n: (hosts[i % len(hosts)] for i in range(n))
     for _ in pipe.run(feed(6)):
         pass
     torch.cuda.synchronize()
