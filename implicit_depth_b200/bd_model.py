@@ -144,9 +144,17 @@ class B200BDModel(nn.Module):
         self.encoder_strict_fp32 = True
         self._enc_fast = None
         self._side = None
+        # Encoder-ahead mode (pipeline.FramePipeline(encoder_ahead=True)): the image-prior encoder is not part of the
+        # forward's graph; `run_encoder` launches it separately (for the NEXT batch, under the back phase of the
+        # current one) and the forward starts by copying its outputs into the buffers the cost-volume encoder reads.
+        self.encoder_ahead = False
+        self._enc_graphs = {}
+        self._enc_pending = None       # data_ptr of the images the encoder last ran on and nobody consumed yet
+        self.after_encoder_handoff = None  # hook: called once the encoder outputs have been copied out
 
     def _apply(self, fn, *a, **k):
         self._state, self._graphs, self._enc_fast, self._side = {}, {}, None, None
+        self._enc_graphs, self._enc_pending = {}, None
         return super()._apply(fn, *a, **k)
 
     def _front_sm_cap(self):
@@ -154,7 +162,7 @@ class B200BDModel(nn.Module):
         (a long chain of small-grid kernels) runs beside them on its own stream; 0 = no cap."""
         import os
 
-        if not (self.native_image_encoder and self.overlap_image_encoder):
+        if not (self.native_image_encoder and self.overlap_image_encoder) or self.encoder_ahead:
             return 0
         if "B200_FRONT_SM_CAP" in os.environ:  # dev knob
             return int(os.environ["B200_FRONT_SM_CAP"])
@@ -199,6 +207,7 @@ class B200BDModel(nn.Module):
 
     def load_state_dict(self, *a, **k):
         self._state, self._graphs, self._enc_fast = {}, {}, None  # launch plans hold packed copies of the weights
+        self._enc_graphs, self._enc_pending = {}, None
         return super().load_state_dict(*a, **k)
 
     def _run_image_encoder(self, cur_image):
@@ -244,12 +253,23 @@ class B200BDModel(nn.Module):
             encp = Plan(dev)  # image-prior encoder on the conv kernels
             img_feats = plan_efficientnet_v2_s(encp, self.encoder.features, lambda: slots["cur_image"], B, H, W,
                                                taps=self.encoder.TAPS)
-            # the encoder runs on its own stream from the start of the forward; every consumer in `post` waits for
-            # the one feature map it reads, so the deep encoder stages overlap the first cost-volume-encoder levels
-            for a in img_feats:
-                ev = torch.cuda.Event()
-                post.external[id(a)] = ev
-                encp.add((lambda ev=ev: ev.record()), launches=0, reads=[a], writes=[])
+            if self.encoder_ahead:
+                # the encoder is launched apart from the forward: `post` reads copies of its outputs, so the encoder
+                # of the next batch may overwrite its own buffers while this batch is still in the back phase
+                enc_out = img_feats
+                img_feats = []
+                for a in enc_out:
+                    c = post.act(a.B, a.H, a.W, a.C)
+                    c.Cl = getattr(a, "Cl", a.C)
+                    img_feats.append(c)
+            else:
+                # the encoder runs on its own stream from the start of the forward; every consumer in `post` waits
+                # for the one feature map it reads, so the deep encoder stages overlap the first cost-volume-encoder
+                # levels
+                for a in img_feats:
+                    ev = torch.cuda.Event()
+                    post.external[id(a)] = ev
+                    encp.add((lambda ev=ev: ev.record()), launches=0, reads=[a], writes=[])
         else:
             img_feats = [post.from_f32((lambda i=i: slots["enc"][i]), B, enc_ch[i], H // 2 ** (i + 1),
                                        W // 2 ** (i + 1)) for i in range(5)]
@@ -257,8 +277,11 @@ class B200BDModel(nn.Module):
         cv_feats = self.cost_volume_net.plan(post, cv, img_feats[ms:])
         dec_in = img_feats[:ms] + cv_feats
         pred, search_depths = self._plan_head(post, dec_in, slots, P, search)
+        ahead = encp is not None and self.encoder_ahead
         return SimpleNamespace(slots=slots, pre=pre, post=post, encp=encp, feats_pm=feats_pm, h=h, w=w, pred=pred,
-                               search_depths=search_depths, feat_layout=self.cost_volume.FEAT_LAYOUT)
+                               search_depths=search_depths, feat_layout=self.cost_volume.FEAT_LAYOUT,
+                               enc_out=(enc_out if ahead else None), post_in=(img_feats if ahead else None),
+                               encoder_ahead=ahead)
 
     def _plan_head(self, post, dec_in, slots, P, search):
         """Decoder + per-pixel binary-occupancy MLP (bd_model.py:260-304).  Returns (pred, search_depths)."""
@@ -287,15 +310,14 @@ class B200BDModel(nn.Module):
         B, K = src_image.shape[:2]
         H, W = cur_image.shape[-2:]
         P = rendered_depth.shape[1]
-        key = (B, K, H, W, P, search)
-        if key not in self._state or self._state[key].feat_layout != self.cost_volume.FEAT_LAYOUT:
-            self._state = {key: self._build(B, K, H, W, P, cur_image.device, search)}
-        st = self._state[key]
+        st = self._ensure_state(B, K, H, W, P, cur_image.device, search)
         # relative poses, bd_model.py:196-204: both batched products in one launch
         src_cam_T_cur_cam, cur_cam_T_src_cam = relative_poses(src_cam_T_world, src_world_T_cam, cur_cam_T_world,
                                                               cur_world_T_cam)
         # image-prior encoder: native plan on a side stream, or the injected PyTorch module
-        if st.encp is not None:
+        if st.encoder_ahead:
+            enc_feats, join_encoder = None, (lambda: None)  # launched apart: `run_encoder` + `_encoder_handoff`
+        elif st.encp is not None:
             st.slots["cur_image"] = cur_image
             enc_feats, join_encoder = None, self._run_native_encoder(st, cur_image.device)
         else:
@@ -330,6 +352,60 @@ class B200BDModel(nn.Module):
         if st.encp is not None:
             join_encoder()  # formal join of the side stream (its last op already gates the decoder)
         return st.pred, lowest_cost, overall_mask, st.search_depths
+
+    def _ensure_state(self, B, K, H, W, P, dev, search=False):
+        key = (B, K, H, W, P, search)
+        st = self._state.get(key)
+        if st is None or st.feat_layout != self.cost_volume.FEAT_LAYOUT or \
+                st.encoder_ahead != (self.encoder_ahead and st.encp is not None):
+            self._state = {key: self._build(B, K, H, W, P, dev, search)}
+            self._graphs, self._enc_graphs, self._enc_pending = {}, {}, None  # they point into the old plans
+        return self._state[key]
+
+    # ---- encoder-ahead mode ------------------------------------------------------------------------------------
+    def run_encoder(self, cur_image, K, P, search=False):
+        """Launch the image-prior encoder for `cur_image` [B,3,H,W] (fp32, contiguous, stable address: a staging
+        slot) on the current stream, as a CUDA graph of its own when `use_cuda_graph`.  Its outputs stay in the
+        encoder plan's buffers until the forward of this batch copies them out (`_encoder_handoff`)."""
+        if not (self.encoder_ahead and self.native_image_encoder):
+            raise RuntimeError("run_encoder needs encoder_ahead mode with the built-in encoder")
+        B, _, H, W = cur_image.shape
+        st = self._ensure_state(B, K, H, W, P, cur_image.device, search)
+        if not self.use_cuda_graph:
+            st.slots["cur_image"] = cur_image
+            st.encp.run()
+        else:
+            key = (B, K, H, W, P, search, cur_image.data_ptr())
+            if key not in self._enc_graphs:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    st.slots["cur_image"] = cur_image
+                    st.encp.run()  # warm-up: packs weights, sets kernel attributes
+                torch.cuda.current_stream().wait_stream(s)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    st.encp.run()
+                while len(self._enc_graphs) >= self.MAX_STAGED_GRAPHS:
+                    self._enc_graphs.pop(next(iter(self._enc_graphs)))
+                self._enc_graphs[key] = graph
+            self._enc_graphs[key].replay()
+        self._enc_pending = cur_image.data_ptr()
+
+    def _encoder_handoff(self, cur_image, K, P, search=False):
+        """Start of a forward in encoder-ahead mode: make sure the encoder has run on these images (inline if nobody
+        launched it ahead), copy its outputs into the buffers the back phase reads, tell the pipeline."""
+        B, _, H, W = cur_image.shape
+        st = self._ensure_state(B, K, H, W, P, cur_image.device, search)
+        if not st.encoder_ahead:
+            return
+        if self._enc_pending != cur_image.data_ptr():
+            self.run_encoder(cur_image, K, P, search)
+        torch._foreach_copy_([a.hi for a in st.post_in] + [a.lo for a in st.post_in],
+                             [a.hi for a in st.enc_out] + [a.lo for a in st.enc_out])
+        self._enc_pending = None
+        if self.after_encoder_handoff is not None:
+            self.after_encoder_handoff()
 
     def sample_prior(self, rendered_depth, prior_prediction, cam_to_world, prior_world_to_cam, K, invK):
         """`BDModel.sample_prior` (bd_model.py:395-410) as one kernel; same argument order as the reference."""
@@ -385,6 +461,8 @@ class B200BDModel(nn.Module):
         # a batch staged by `staging.FrameStaging` (one buffer, images already in matching-encoder order): the
         # forward reads the staging slot in place -- no per-tensor copies, no image concatenation
         images_all = self._staged_images(cur_data, src_data, args[0])
+        if self.encoder_ahead and self.native_image_encoder:
+            self._encoder_handoff(args[0], args[1].shape[1], args[-1].shape[1], bool(infer_depth))
         if self.use_cuda_graph:
             pred, lowest, mask, search = self._forward_graphed(args, prior, return_mask, bool(infer_depth),
                                                                images_all=images_all)

@@ -63,6 +63,8 @@ class B200DepthModel(B200BDModel):
                 f(cur_data[f"invK_s{ms}_b44"]), f(src_data["cam_T_world_b44"]), f(src_data["world_T_cam_b44"]),
                 f(cur_data["cam_T_world_b44"]), f(cur_data["world_T_cam_b44"]), no_planes]
         images_all = self._staged_images(cur_data, src_data, args[0])
+        if self.encoder_ahead and self.native_image_encoder:
+            self._encoder_handoff(args[0], args[1].shape[1], 0, False)
         if self.use_cuda_graph:
             pred, lowest, mask, _ = self._forward_graphed(args, None, return_mask, False, images_all=images_all)
         else:

@@ -14,12 +14,23 @@ from .staging import FrameStaging, StagedDict, StagedFrame
 
 
 class FramePipeline:
-    def __init__(self, model, device, gather=None, **forward_kwargs):
+    def __init__(self, model, device, gather=None, encoder_ahead=False, **forward_kwargs):
         """model: B200BDModel (or anything with the reference's forward signature); gather: optional callable
-        applied to the output dict on the compute stream (e.g. `parallel.GatherPlan.run`)."""
+        applied to the output dict on the compute stream (e.g. `parallel.GatherPlan.run`).
+
+        encoder_ahead (staged batches, B200BDModel with its built-in encoder): the image-prior encoder depends only
+        on the current images, so the encoder of batch i+1 is launched on a fourth stream as soon as batch i has taken
+        its own encoder outputs, and runs under the forward of batch i; the forward itself then is matching encoder +
+        plane sweep on all SMs followed by the back phase.  Results are unchanged (same kernels, same order per
+        batch)."""
         self.model, self.device, self.gather, self.kw = model, torch.device(device), gather, forward_kwargs
         self.s_in = torch.cuda.Stream(device=self.device)
         self.s_out = torch.cuda.Stream(device=self.device)
+        self.encoder_ahead = bool(encoder_ahead)
+        if self.encoder_ahead:
+            model.encoder_ahead = True
+            self.s_enc = torch.cuda.Stream(device=self.device)
+        self.ev_enc = [None, None]         # encoder of the batch in slot s has finished (encoder_ahead)
         self.slots = [None, None]          # device input dictionaries
         self.host_out = [None, None]       # pinned output dictionaries
         self.ev_free = [None, None]        # forward that last read input slot s has finished
@@ -61,17 +72,46 @@ class FramePipeline:
             ev.record(self.s_in)
         return ev
 
-    def _forward(self, slot, ev_in):
+    def _encoder_hook(self, main, next_slot, ev_next):
+        """Called by the forward of batch i right after it copied its encoder outputs out: launch the encoder of
+        batch i+1 (already being uploaded into `next_slot`) on the encoder stream."""
+        def hook():
+            nxt = self.slots[next_slot]
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self.s_enc):
+                self.s_enc.wait_event(ev)       # the encoder plan's buffers are free again
+                self.s_enc.wait_event(ev_next)  # the next batch's images have arrived
+                self.model.run_encoder(nxt.cur["image_b3hw"], nxt.staging.K, nxt.staging.P,
+                                       bool(self.kw.get("infer_depth", False)))
+                done = torch.cuda.Event()
+                done.record(self.s_enc)
+            self.ev_enc[next_slot] = done
+        return hook
+
+    def _forward(self, slot, ev_in, next_slot=None, ev_next=None):
         main = torch.cuda.current_stream(self.device)
         main.wait_event(ev_in)
-        if isinstance(self.slots[slot], StagedFrame):
+        staged = isinstance(self.slots[slot], StagedFrame)
+        if staged:
             frame = self.slots[slot]
             dcur, dsrc = StagedDict(frame.cur), frame.src  # (the forward may add keys to cur_data)
             dcur.frame = frame
         else:
             dcur, dsrc = self.slots[slot]
             dcur = dict(dcur)
-        out = self.model("test", dcur, dsrc, **self.kw)
+        ahead = self.encoder_ahead and staged
+        if ahead:
+            if self.ev_enc[slot] is not None:   # this batch's encoder ran ahead, under the previous forward
+                main.wait_event(self.ev_enc[slot])
+                self.ev_enc[slot] = None
+            self.model.after_encoder_handoff = \
+                self._encoder_hook(main, next_slot, ev_next) if ev_next is not None else None
+        try:
+            out = self.model("test", dcur, dsrc, **self.kw)
+        finally:
+            if ahead:
+                self.model.after_encoder_handoff = None
         if self.gather is not None:
             g = self.gather(out)
             out = {k: (g[k] if k in g else v) for k, v in out.items()}
@@ -109,7 +149,7 @@ class FramePipeline:
             slot = i & 1
             following = next(it, None)
             ev_next = self._upload(slot ^ 1, *as_args(following)) if following is not None else None
-            out, ev_fwd = self._forward(slot, ev_in)
+            out, ev_fwd = self._forward(slot, ev_in, slot ^ 1, ev_next)
             ev_done = self._download(slot, out, ev_fwd)
             if pending is not None:
                 pending[1].synchronize()

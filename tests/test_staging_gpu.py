@@ -121,3 +121,35 @@ def test_staged_entry_replaced_by_the_caller_is_honoured():
     ref_cur["rendered_depth"] = planes
     want = m("test", ref_cur, {k: torch.from_numpy(v).cuda() for k, v in src.items()}, return_mask=True)
     assert torch.equal(got["pred_0"], want["pred_0"]) and not torch.equal(got["pred_0"], base["pred_0"])
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_encoder_ahead_pipeline_is_bit_identical(graph):
+    """`FramePipeline(encoder_ahead=True)`: the image-prior encoder of batch i+1 runs under the forward of batch i;
+    every batch still gets exactly the results of a direct call."""
+    from implicit_depth_b200.pipeline import FramePipeline
+
+    ref_model = _model()
+    ref_model.use_cuda_graph = graph
+    st = FrameStaging(1, 7, 192, 256, P=8)
+    hosts, direct = [], []
+    for i in range(5):
+        cur, src = synthetic.make_frame_batch(6400 + i, 1, 7, 192, 256)
+        o = ref_model("test", {k: torch.from_numpy(v).cuda() for k, v in cur.items()},
+                      {k: torch.from_numpy(v).cuda() for k, v in src.items()}, return_mask=True)
+        direct.append({k: v.cpu().clone() for k, v in o.items()})
+        hosts.append(st.host_frame().fill(cur, src))
+    m = _model()
+    m.use_cuda_graph = graph
+    pipe = FramePipeline(m, "cuda", encoder_ahead=True, return_mask=True)
+    for rep in range(2):  # second pass: all graphs already captured
+        got = [{k: v.clone() for k, v in res.items()} for res in pipe.run(iter(hosts))]
+        assert len(got) == 5
+        for g_, d_ in zip(got, direct):
+            for k in d_:
+                assert torch.equal(g_[k], d_[k]), (rep, k)
+    # a direct call on a model in encoder-ahead mode runs the encoder inline
+    cur, src = synthetic.make_frame_batch(6400, 1, 7, 192, 256)
+    o = m("test", {k: torch.from_numpy(v).cuda() for k, v in cur.items()},
+          {k: torch.from_numpy(v).cuda() for k, v in src.items()}, return_mask=True)
+    assert torch.equal(o["pred_0"].cpu(), direct[0]["pred_0"])
