@@ -285,25 +285,49 @@ def main_b200(args):
     # batches with the forward; every step still uploads its own inputs and downloads its own outputs. ----
     from implicit_depth_b200.pipeline import FramePipeline
 
-    pipe = FramePipeline(model, dev, gather=(gplan.run if gplan is not None else None), return_mask=True)
     feed = lambda n: (host_sets[i % NSETS] for i in range(n))
-    for _ in pipe.run(feed(3)):  # warm-up (allocates the slots, captures nothing new)
-        pass
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    checksum = 0.0
-    for res in pipe.run(feed(args.steps)):
-        checksum += float(res["pred_0"][0, 0, 0, 0])  # the host really reads every step's result
-    e1.record()
-    torch.cuda.synchronize()
-    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
-    et = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(et, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / (float(et.item()) / 1000.0)
+
+    def run_e2e(pipe):
+        for _ in pipe.run(feed(4)):  # warm-up (allocates the slots, captures the per-slot graphs)
+            pass
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        checksum = 0.0
+        for res in pipe.run(feed(args.steps)):
+            checksum += float(res["pred_0"][0, 0, 0, 0])  # the host really reads every step's result
+        e1.record()
+        torch.cuda.synchronize()
+        et = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        return world * B * args.steps / (float(et.item()) / 1000.0), pipe.h2d_bytes, pipe.d2h_bytes
+
+    gather = gplan.run if gplan is not None else None
+    # plain pipeline: every forward contains its own image-prior encoder (the graph `value` times)
+    e2e_plain, h2d, d2h = run_e2e(FramePipeline(model, dev, gather=gather, return_mask=True))
+    # encoder-ahead pipeline: the image-prior encoder of batch i+1 runs under the forward
+    # of batch i; same kernels, bit-identical results (tests/test_staging_gpu.py).  On its own model instance so that
+    # the plans `value`, the roofline and the stage breakdown use stay as they are.
+    e2e_value, e2e_mode = e2e_plain, "plain"
+    if not args.no_graph and os.environ.get("B200_BENCH_ENCODER_AHEAD", "1") != "0":
+        try:
+            model_e = B200BDModel(opts)
+            model_e.load_state_dict(model.state_dict())
+            model_e = model_e.to(dev).eval()
+            model_e.use_cuda_graph = True
+            v, h2d_e, d2h_e = run_e2e(FramePipeline(model_e, dev, gather=gather, encoder_ahead=True, return_mask=True))
+            if v > e2e_plain:
+                e2e_value, e2e_mode, h2d, d2h = v, "encoder_ahead", h2d_e, d2h_e
+            e2e_ahead = v
+            del model_e
+            torch.cuda.empty_cache()
+        except Exception as e:  # the plain pipeline's number stands
+            e2e_ahead = repr(e)
+    else:
+        e2e_ahead = None
 
     if rank != 0:
         if world > 1:
@@ -402,8 +426,11 @@ def main_b200(args):
                                     "fp32-grade split-bf16 like the rest of the forward (cuDNN TF32 would put pred_0 "
                                     "1.7e-2 off the fp32 reference)"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "pipeline": e2e_mode, "plain_pipeline": e2e_plain, "encoder_ahead_pipeline": e2e_ahead,
                 "how": "FramePipeline: one pinned staging buffer per batch -> one H2D copy -> forward reading the device "
-                       "slot in place -> D2H into pinned host memory every step, "
+                       "slot in place -> D2H into pinned host memory every step; 'encoder_ahead': the image-prior "
+                       "encoder of batch i+1 (it depends on the current images only) runs on its own stream under "
+                       "the forward of batch i, results bit-identical; "
                        "copies of neighbouring steps overlapped with the forward on separate streams; one CUDA-event "
                        "bracket around all steps; rotating input sets larger than L2"},
         "gpu_launches": args.steps * model.num_kernel_launches(B, K_SRC, IMAGE_H, IMAGE_W, 8),
