@@ -29,7 +29,10 @@ class FramePipeline:
         self.encoder_ahead = bool(encoder_ahead)
         if self.encoder_ahead:
             model.encoder_ahead = True
-            self.s_enc = torch.cuda.Stream(device=self.device)
+            import os
+
+            self.s_enc = torch.cuda.Stream(device=self.device,
+                                           priority=int(os.environ.get("B200_ENC_PRIORITY", "0")))  # dev knob
         self.ev_enc = [None, None]         # encoder of the batch in slot s has finished (encoder_ahead)
         self.slots = [None, None]          # device input dictionaries
         self.host_out = [None, None]       # pinned output dictionaries
