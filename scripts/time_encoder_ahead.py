@@ -15,8 +15,22 @@ for i in range(2 if os.environ.get('ONLY_AHEAD') else 3):
     cur, src = synthetic.make_frame_batch(7000 + i, B, K, H, W)
     hosts.append(st.host_frame().fill(cur, src))
 N = int(os.environ.get("STEPS", 40))
-MODES = (True,) if os.environ.get('ONLY_AHEAD') else (False, True, False, True)
-for ahead in MODES:
+# settings: "ahead;encoder stream priority;front-end CTA cap (0 = none)" on the command line, e.g.
+#   python scripts/time_encoder_ahead.py "0;0;-" "1;0;0" "1;-1;0" "1;-1;120" "1;0;120"
+# ("-" = leave the model's default cap rule alone)
+SETTINGS = [("1", "0", "-")] if os.environ.get('ONLY_AHEAD') else [("0", "0", "-"), ("1", "0", "-"), ("1", "-1", "-"),
+                                                                   ("1", "-1", "120"), ("1", "0", "120"),
+                                                                   ("0", "0", "-"), ("1", "0", "-")]
+if len(sys.argv) > 1:
+    SETTINGS = [tuple(a.split(";")) for a in sys.argv[1:]]
+for ahead_s, prio, cap in SETTINGS:
+    ahead = ahead_s == "1"
+    os.environ["B200_ENC_PRIORITY"] = prio
+    if cap == "-":
+        os.environ.pop("B200_FRONT_SM_CAP", None)
+        os.environ.pop("B200_FV_SM_CAP", None)
+    else:
+        os.environ["B200_FRONT_SM_CAP"] = os.environ["B200_FV_SM_CAP"] = cap
     m = B200BDModel(default_options(image_width=W, image_height=H, matching_num_depth_bins=D))
     if not os.environ.get('NO_INIT'):
         synthetic.init_model_weights(m, seed=0)
@@ -35,7 +49,7 @@ for ahead in MODES:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / N
-    print(json.dumps({"encoder_ahead": ahead, "ms_per_step": round(ms, 3), "frames_per_s": round(1000 * B / ms, 1),
+    print(json.dumps({"encoder_ahead": ahead, "enc_priority": prio, "front_cap": cap, "ms_per_step": round(ms, 3), "frames_per_s": round(1000 * B / ms, 1),
                       "checksum": chk}), flush=True)
     del pipe, m
     torch.cuda.empty_cache()
