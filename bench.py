@@ -385,6 +385,16 @@ def main_b200(args):
                     "traffic_source": NCU_SOURCE, "ms_per_launch": dot_ms,
                     "algorithmic_bytes_per_launch": dot_bytes, "peak_source": peak_src,
                     "secondary_gather_GBps": 4.0 * 16 * 4 * K_SRC * D_PLANES * N * B / (dot_ms * 1e-3) / 1e9}
+    # the bound that actually limits the gather: 128 B per clock per SM through the L1 data pipe
+    try:
+        sm_mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        l1_peak = n_sm * 128.0 * sm_mhz * 1e6 / 1e9
+        roofline_dot["secondary_bound"] = {"what": "gathered bytes through the L1 data pipe (128 B/clk/SM)",
+                                           "peak_GBps": l1_peak,
+                                           "frac": roofline_dot["secondary_gather_GBps"] / l1_peak}
+    except Exception:
+        pass
 
     # ---- per-stage breakdown (eager launches, CUDA events) ----
     model.use_cuda_graph = False
