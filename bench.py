@@ -32,6 +32,7 @@ WORKLOAD = "cfg2: B=4 per GPU, 512x384, 7 source views, 64 depth planes, implici
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2 (B=4) from the committed `ncu --set full` captures
 # (the cost volume written by either kernel stays in the 126 MB L2 for the consuming kernel, hence ~ the input bytes)
 NCU_SOURCE = "profiles/r01e_ncu_full_volume.md"
+NCU_FV_TC_WARP_INST = 491767150.0  # smsp__inst_executed.sum of fv_tc_kernel<7> at cfg2, B=4 (same capture)
 NCU_DRAM_BYTES = {"fv_tc_kernel": 24.3e6, "cv_dot_kernel": 23.6e6}
 
 
@@ -385,10 +386,15 @@ def main_b200(args):
                     "traffic_source": NCU_SOURCE, "ms_per_launch": dot_ms,
                     "algorithmic_bytes_per_launch": dot_bytes, "peak_source": peak_src,
                     "secondary_gather_GBps": 4.0 * 16 * 4 * K_SRC * D_PLANES * N * B / (dot_ms * 1e-3) / 1e9}
-    # the bound that actually limits the gather: 128 B per clock per SM through the L1 data pipe
+    # the bound that actually limits the gather: 128 B per clock per SM through the L1 data pipe; and the
+    # CUDA-core instruction stream of fv_tc_kernel (warp instructions per B=4 launch from the ncu capture)
     try:
         sm_mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue_floor_ms = NCU_FV_TC_WARP_INST * (B / 4.0) / (n_sm * 4.0 * sm_mhz * 1e6) * 1e3
+        roofline["secondary_bound"] = {"what": "warp-instruction issue (4 schedulers per SM), instruction count from "
+                                               + NCU_SOURCE, "floor_ms_per_launch": issue_floor_ms,
+                                       "frac": issue_floor_ms / fv_ms}
         l1_peak = n_sm * 128.0 * sm_mhz * 1e6 / 1e9
         roofline_dot["secondary_bound"] = {"what": "gathered bytes through the L1 data pipe (128 B/clk/SM)",
                                            "peak_GBps": l1_peak,
