@@ -9,8 +9,10 @@ One "step" = one `BDModel.forward("test", ...)` over one batch of synthetic inpu
 random weights).  N>1 runs one rank per GPU (torchrun) on its own 4 frames (weak scaling, config 3 at N=8)
 followed by the NCCL all_gather of the outputs.  Rank 0 prints ONE JSON line.
 
-`--impl reference` times the reference's algorithm on the host cores (the CPU oracle port under `oracle/`;
-the reference itself is Python under /root/reference and does not exist on the GPU box).
+`--impl reference` times the reference's own implementation of the path on the host cores: the UNMODIFIED reference
+`BDModel` from `baseline/_ref` (a byte-for-byte copy made by `baseline/make_ref.py` in the build container; it travels
+with the snapshot), or the oracle port under `oracle/` if that copy is absent.  The N=1 line of the b200 arm also
+carries `gpu_reference`: the same unmodified reference on the same B200 through torch/cuDNN, four modes.
 """
 import argparse
 import json
@@ -44,6 +46,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     return ap.parse_args()
 
 
@@ -129,12 +132,13 @@ def load_peaks():
 
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_run(steps, warmup, budget_s=240.0):
-    """The reference's algorithm on the host cores: oracle port, one cfg2 frame per step (bounded sample)."""
+    """The reference's own CPU implementation of the path on the host cores, one cfg2 frame per step (bounded
+    sample): the UNMODIFIED reference `BDModel` from baseline/_ref (kind "reference"; `test_bd.py` defaults: looping
+    matching encoder + per-plane FeatureVolumeManager) when the copy was shipped, else the oracle port (kind "port")."""
     import torch
 
     from implicit_depth_b200 import synthetic
     from implicit_depth_b200.bd_model import B200BDModel, default_options
-    from oracle import networks as ON  # the only place bench.py executes oracle/: the CPU baseline
 
     torch.set_grad_enabled(False)
     # all the host threads this process may use (torchrun pins OMP_NUM_THREADS=1 for its workers: undo that here)
@@ -148,11 +152,27 @@ def cpu_reference_run(steps, warmup, budget_s=240.0):
     model = B200BDModel(opts)  # parameter container only (CPU); never called
     synthetic.init_model_weights(model, seed=0)
     sd = {k: v.detach() for k, v in model.state_dict().items()}
-    enc = model.encoder.eval()
     cur, src = synthetic.make_frame_batch(2000, 1, K_SRC, IMAGE_H, IMAGE_W)
     cur = {k: torch.from_numpy(v) for k, v in cur.items()}
     src = {k: torch.from_numpy(v) for k, v in src.items()}
-    run = lambda: ON.bd_forward(sd, enc, cur, src, opts, torch_volume=True)
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_loader
+
+    if ref_loader.available():
+        kind = "reference"
+        ref = ref_loader.build_bd_model(IMAGE_W, IMAGE_H, D_PLANES, state_dict=sd)
+        how = "the unmodified reference BDModel.forward (baseline/_ref, torch CPU kernels, test_bd.py defaults)"
+
+        def run():
+            with torch.inference_mode():
+                return ref("test", dict(cur), src, unbatched_matching_encoder_forward=True, return_mask=True)
+    else:
+        from oracle import networks as ON  # the only place bench.py executes oracle/: the CPU baseline
+
+        kind = "port"
+        enc = model.encoder.eval()
+        how = "oracle.networks.bd_forward (torch CPU kernels; baseline/_ref not shipped)"
+        run = lambda: ON.bd_forward(sd, enc, cur, src, opts, torch_volume=True)
     t0 = time.perf_counter()
     run()  # first call also serves as warm-up and as the time estimate
     est = time.perf_counter() - t0
@@ -164,10 +184,70 @@ def cpu_reference_run(steps, warmup, budget_s=240.0):
     for _ in range(n):
         run()
     dt = (time.perf_counter() - t0) / n
-    return {"value": 1.0 / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{n} x 1 frame of cfg2 (512x384, K=7, D=64) through oracle.networks.bd_forward "
-                      f"(torch CPU kernels, {cores} threads), {dt:.2f} s/frame",
+    return {"value": 1.0 / dt, "unit": "frames/s", "cores": cores, "kind": kind,
+            "sample": f"{n} x 1 frame of cfg2 (512x384, K=7, D=64) through {how}, {cores} threads, {dt:.2f} s/frame",
             "steps_timed": n, "s_per_frame": dt}
+
+
+def gpu_reference_run(dev, sd, cur, src, steps=10, warmup=3):
+    """SURVEY 8d(i) / north_star ">= 4x the reference's own PyTorch/cuDNN forward on 1 x B200": the UNMODIFIED reference
+    `BDModel` (baseline/_ref; same seeded state dict, same cfg2 batch) on this GPU, CUDA events placed exactly as
+    test_bd.py:196-212, in four modes: {torch defaults (cuDNN TF32 convs, fp32 matmuls), strict fp32} x
+    {test_bd.py default: looping matching encoder + per-plane manager, --fast_cost_volume: to_fast() + batched}."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_loader
+
+    if not ref_loader.available():
+        return {"unavailable": "baseline/_ref not shipped (run baseline/make_ref.py in the build container)"}
+    res = {"modes": {}, "what": "unmodified reference BDModel.forward (baseline/_ref) via installed torch/cuDNN, "
+                                "same weights and batch, CUDA events as test_bd.py:196-212, median of "
+                                f"{steps} after {warmup} warm-ups", "frames_per_step": int(cur["image_b3hw"].shape[0])}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    B = int(cur["image_b3hw"].shape[0])
+    try:
+        for fast in (False, True):
+            ref = ref_loader.build_bd_model(IMAGE_W, IMAGE_H, D_PLANES, state_dict=sd)
+            if fast:
+                ref.cost_volume = ref.cost_volume.to_fast()  # test_bd.py:80-81
+            ref = ref.to(dev).eval()
+            for strict in (False, True):
+                torch.backends.cudnn.allow_tf32 = not strict
+                torch.backends.cuda.matmul.allow_tf32 = False  # PyTorch's default
+                name = ("fast_cost_volume" if fast else "test_default") + ("_strict_fp32" if strict else "_torch_defaults")
+                try:
+                    ts = []
+                    with torch.inference_mode():
+                        for i in range(warmup + steps):
+                            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            a.record()
+                            ref("test", dict(cur), src, unbatched_matching_encoder_forward=(not fast), return_mask=True,
+                                infer_depth=False, infer_res=None)
+                            b.record()
+                            torch.cuda.synchronize()
+                            if i >= warmup:
+                                ts.append(a.elapsed_time(b))
+                    ts.sort()
+                    ms = ts[len(ts) // 2]
+                    res["modes"][name] = {"ms_per_step": ms, "frames_per_s": B / (ms * 1e-3)}
+                except Exception as e:  # e.g. out of memory in the batched manager
+                    res["modes"][name] = {"error": repr(e)[:300]}
+            del ref
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    ok = {k: v for k, v in res["modes"].items() if "frames_per_s" in v}
+    if ok:
+        best = max(ok, key=lambda k: ok[k]["frames_per_s"])
+        res["fastest_mode"] = best
+        res["fastest_frames_per_s"] = ok[best]["frames_per_s"]
+        strict_ok = {k: v for k, v in ok.items() if k.endswith("strict_fp32")}
+        if strict_ok:
+            bs = max(strict_ok, key=lambda k: strict_ok[k]["frames_per_s"])
+            res["fastest_strict_fp32_mode"] = bs
+            res["fastest_strict_fp32_frames_per_s"] = strict_ok[bs]["frames_per_s"]
+    return res
 
 
 def main_reference(args):
@@ -178,7 +258,8 @@ def main_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "frames/s", "n_gpus": args.gpus,
             "steps": r["steps_timed"], "warmup": args.warmup, "ms_per_step": 1000.0 * r["s_per_frame"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU arm: each step is a bounded sample of 1 frame"},
+            "config": {"workload": WORKLOAD, "frames_per_gpu": FRAMES_PER_GPU, "global_batch": FRAMES_PER_GPU * args.gpus},
+            "sample_note": "CPU arm: each step is a bounded sample of 1 frame of the workload (see cpu_baseline.sample)",
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -222,8 +303,8 @@ def main_b200(args):
     model.use_cuda_graph = not args.no_graph
     B = FRAMES_PER_GPU
 
-    # three rotating input sets (227 MB) so that no step finds its inputs in the 126 MB L2; plus an explicit
-    # L2 flush (256 MB write) between steps, outside the per-step CUDA-event brackets
+    # three rotating input sets (227 MB) so that no step finds its inputs in the 126 MB L2 (the stand-alone kernel
+    # timings below additionally flush L2 with a 256 MB write before every call)
     # Batches are staged (implicit_depth_b200.staging): one pinned host buffer per batch in the order
     # the kernels read it, one H2D copy, and the forward's CUDA graph reads the device copy in place.
     from implicit_depth_b200.staging import FrameStaging
@@ -245,12 +326,20 @@ def main_b200(args):
         return model("test", cur, src, unbatched_matching_encoder_forward=False, return_mask=True)
 
     out = step(0)
-    gplan = GatherPlan(out, world) if world > 1 else None
+    # the only exchange is the final gather of outputs.  The forward writes its results straight into the
+    # plan's packed send buffer; ONE NCCL gather to rank 0 per step runs on the plan's own stream under the next step.
+    gplan = GatherPlan(out, world, mode="root") if world > 1 else None
 
     def full_step(i):
-        o = step(i)
-        if gplan is not None:
-            gplan.run(o)  # final gather of outputs over NCCL/NVLink
+        if gplan is None:
+            return step(i)
+        slot = i & 1
+        model.output_views = gplan.send_views(slot)
+        try:
+            o = step(i)
+        finally:
+            model.output_views = None
+        gplan.run(slot)
         return o
 
     for i in range(max(args.warmup, 3)):
@@ -259,20 +348,24 @@ def main_b200(args):
     if world > 1:
         dist.barrier()
 
+    # EXACTLY `steps` steps inside ONE CUDA-event bracket on the compute stream; the bracket closes after the compute
+    # stream has waited for the last gathers, so every collective is inside it.  L2: the three rotating input sets are
+    # larger than L2, and every step streams ~1.7 GB of activations through it.
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    t_wall0 = time.time()
+    e0.record()
     for i in range(args.steps):
-        flush.zero_()
-        evs[i][0].record()
         full_step(i)
-        evs[i][1].record()
+    if gplan is not None:
+        for ev in gplan.done:
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+    e1.record()
     torch.cuda.synchronize()
-    t_wall1 = time.time()
     if world > 1:
         dist.barrier()
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    total_ms = e0.elapsed_time(e1)
     tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -298,7 +391,8 @@ def main_b200(args):
         e0.record()
         checksum = 0.0
         for res in pipe.run(feed(args.steps)):
-            checksum += float(res["pred_0"][0, 0, 0, 0])  # the host really reads every step's result
+            if "pred_0" in res:  # (with the gather to rank 0 only the root holds results)
+                checksum += float(res["pred_0"][0, 0, 0, 0])  # the host really reads every step's result
         e1.record()
         torch.cuda.synchronize()
         et = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -306,9 +400,11 @@ def main_b200(args):
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
         return world * B * args.steps / (float(et.item()) / 1000.0), pipe.h2d_bytes, pipe.d2h_bytes
 
-    gather = gplan.run if gplan is not None else None
+    # packed outputs at every N (at N=1 the "gather" is the send buffer itself): one D2H copy per step on the rank that
+    # holds the gathered batch
+    mk_plan = lambda: GatherPlan(out, world, mode="root")
     # plain pipeline: every forward contains its own image-prior encoder (the graph `value` times)
-    e2e_plain, h2d, d2h = run_e2e(FramePipeline(model, dev, gather=gather, return_mask=True))
+    e2e_plain, h2d, d2h = run_e2e(FramePipeline(model, dev, gather=mk_plan(), return_mask=True))
     # encoder-ahead pipeline: the image-prior encoder of batch i+1 runs under the forward
     # of batch i; same kernels, bit-identical results (tests/test_staging_gpu.py).  On its own model instance so that
     # the plans `value`, the roofline and the stage breakdown use stay as they are.
@@ -319,7 +415,8 @@ def main_b200(args):
             model_e.load_state_dict(model.state_dict())
             model_e = model_e.to(dev).eval()
             model_e.use_cuda_graph = True
-            v, h2d_e, d2h_e = run_e2e(FramePipeline(model_e, dev, gather=gather, encoder_ahead=True, return_mask=True))
+            v, h2d_e, d2h_e = run_e2e(FramePipeline(model_e, dev, gather=mk_plan(), encoder_ahead=True,
+                                                    return_mask=True))
             if v > e2e_plain:
                 e2e_value, e2e_mode, h2d, d2h = v, "encoder_ahead", h2d_e, d2h_e
             e2e_ahead = v
@@ -421,6 +518,23 @@ def main_b200(args):
         stage_ms["error"] = repr(e)
     model.use_cuda_graph = not args.no_graph
 
+    n_launches = model.num_kernel_launches(B, K_SRC, IMAGE_H, IMAGE_W, 8)
+    gpu_reference = None
+    if world == 1 and not args.no_gpu_reference:
+        try:
+            model._state, model._graphs = {}, {}  # free the plans' activations before the reference allocates
+            torch.cuda.empty_cache()
+            sd_ref = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+            gpu_reference = gpu_reference_run(dev, sd_ref, dev_sets[0][0], dev_sets[0][1])
+            if "fastest_frames_per_s" in gpu_reference:
+                gpu_reference["value_over_fastest_mode"] = value / gpu_reference["fastest_frames_per_s"]
+                gpu_reference["e2e_over_fastest_mode"] = e2e_value / gpu_reference["fastest_frames_per_s"]
+            if "fastest_strict_fp32_frames_per_s" in gpu_reference:
+                gpu_reference["value_over_fastest_strict_fp32_mode"] = \
+                    value / gpu_reference["fastest_strict_fp32_frames_per_s"]
+        except Exception as e:
+            gpu_reference = {"error": repr(e)[:300]}
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:  # rank 0 at N=1 only
         try:
@@ -434,9 +548,10 @@ def main_b200(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (split-bf16 tcgen05 MMAs, fp32 accumulate)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_gpu": B, "global_batch": world * B,
-                   "l2": "3 rotating input sets (227 MB > 126 MB L2) + 256 MB flush write between steps, outside "
-                         "the per-step CUDA-event brackets",
-                   "timing": "sum of per-step CUDA-event durations, max over ranks",
+                   "l2": "3 rotating input sets (227 MB > 126 MB L2); every step also streams ~1.7 GB of activations "
+                         "through L2 (no explicit flush inside the bracket)",
+                   "timing": "one CUDA-event bracket around all steps on the compute stream, closed after the last "
+                             "NCCL gathers; max over ranks",
                    "cuda_graph": not args.no_graph,
                    "image_encoder": "EfficientNetV2-S (torchvision layout) on the hand-written conv / MBConv kernels, "
                                     "fp32-grade split-bf16 like the rest of the forward (cuDNN TF32 would put pred_0 "
@@ -449,10 +564,9 @@ def main_b200(args):
                        "the forward of batch i, results bit-identical; "
                        "copies of neighbouring steps overlapped with the forward on separate streams; one CUDA-event "
                        "bracket around all steps; rotating input sets larger than L2"},
-        "gpu_launches": args.steps * model.num_kernel_launches(B, K_SRC, IMAGE_H, IMAGE_W, 8),
-        "gpu_launches_per_step": model.num_kernel_launches(B, K_SRC, IMAGE_H, IMAGE_W, 8),
+        "gpu_launches": args.steps * n_launches, "gpu_launches_per_step": n_launches,
         "roofline": roofline, "roofline_warp_dot": roofline_dot, "stage_ms": stage_ms, "clocks": clocks,
-        "cpu_baseline": cpu_baseline,
+        "cpu_baseline": cpu_baseline, "gpu_reference": gpu_reference,
     }
     if saved_stdout is not None:
         sys.stdout.flush()

@@ -151,6 +151,9 @@ class B200BDModel(nn.Module):
         self._enc_graphs = {}
         self._enc_pending = None       # data_ptr of the images the encoder last ran on and nobody consumed yet
         self.after_encoder_handoff = None  # hook: called once the encoder outputs have been copied out
+        # Optional destination views {output key: tensor} (e.g. `parallel.GatherPlan.send_views`): the forward writes
+        # its results there instead of into fresh tensors, so a packed gather / download buffer costs no extra copy.
+        self.output_views = None
 
     def _apply(self, fn, *a, **k):
         self._state, self._graphs, self._enc_fast, self._side = {}, {}, None, None
@@ -471,13 +474,22 @@ class B200BDModel(nn.Module):
         else:
             pred, lowest, mask, search = self._forward_impl(*args, prior, return_mask, bool(infer_depth),
                                                             images_all=images_all)
-            pred, search = _clone(pred), _clone(search)
-        out = {"pred_0": pred}
+        # results leave the plans' / the graph's static buffers here (one copy each, into `output_views` if given)
+        out = {"pred_0": self._emit("pred_0", pred)}
         if infer_depth:
-            out["search_depths"] = search  # bd_model.py:292
-        out["lowest_cost_bhw"] = lowest
-        out["overall_mask_bhw"] = mask
+            out["search_depths"] = self._emit("search_depths", search)  # bd_model.py:292
+        out["lowest_cost_bhw"] = self._emit("lowest_cost_bhw", lowest)
+        out["overall_mask_bhw"] = self._emit("overall_mask_bhw", mask)
         return out
+
+    def _emit(self, name, t):
+        if t is None:
+            return None
+        ov = self.output_views
+        if ov is not None and name in ov:
+            ov[name].copy_(t)
+            return ov[name]
+        return t.clone()
 
     # ------------------------------------------------------------------------------------
     MAX_STAGED_GRAPHS = 8  # one graph per staging slot in use (FramePipeline has two)
@@ -514,4 +526,4 @@ class B200BDModel(nn.Module):
         if prior is not None:
             sprior.copy_(prior)
         graph.replay()
-        return tuple(_clone(o) for o in outs)
+        return outs

@@ -69,11 +69,10 @@ class B200DepthModel(B200BDModel):
             pred, lowest, mask, _ = self._forward_graphed(args, None, return_mask, False, images_all=images_all)
         else:
             pred, lowest, mask, _ = self._forward_impl(*args, None, return_mask, False, images_all=images_all)
-            pred = tuple(p.clone() for p in pred)
         out = {}
         for i in range(4):
-            out[f"log_depth_pred_s{i}_b1hw"] = pred[2 * i]
-            out[f"depth_pred_s{i}_b1hw"] = pred[2 * i + 1]
-        out["lowest_cost_bhw"] = lowest
-        out["overall_mask_bhw"] = mask
+            out[f"log_depth_pred_s{i}_b1hw"] = self._emit(f"log_depth_pred_s{i}_b1hw", pred[2 * i])
+            out[f"depth_pred_s{i}_b1hw"] = self._emit(f"depth_pred_s{i}_b1hw", pred[2 * i + 1])
+        out["lowest_cost_bhw"] = self._emit("lowest_cost_bhw", lowest)
+        out["overall_mask_bhw"] = self._emit("overall_mask_bhw", mask)
         return out

@@ -86,3 +86,20 @@ def feature_volume_mlp(cur_feats, src_feats, src_extr, src_poses, src_Ks, cur_in
     vol = torch.cat(vols, 1)
     idx = torch.argmax(vol, 1)
     return vol, idx, planes[idx], mask_out
+
+
+def mask_edge_distance(src_extr, src_Ks, cur_invK, z_last, h, w):
+    """Arbiter for `overall_mask_bhw` (`get_mask`, cost_volume.py:75-96, taken at the last plane :603-615): per pixel
+    the distance, in pixels of the source image, from the nearest view's projection to the nearest edge of the open
+    window 2 < px < w-2, 2 < py < h-2 -- a pixel whose mask bit differs from the reference's is a rounding flip only
+    if this distance is ~0.  Pass fp64 tensors.  Returns [B,h,w]."""
+    B, K = src_extr.shape[:2]
+    pix = _pix(h, w, cur_invK.dtype, cur_invK.device)
+    X = z_last * (cur_invK[:, :3, :3] @ pix)
+    Xh = torch.cat([X, torch.ones_like(X[:, :1])], 1).repeat_interleave(K, 0)
+    P = (src_Ks.reshape(-1, 4, 4) @ src_extr.reshape(-1, 4, 4))[:, :3]
+    c = P @ Xh
+    xy = (c[:, :2] / torch.clamp(c[:, 2:], min=1e-5)).view(B, K, 2, h, w)
+    px, py = xy[:, :, 0], xy[:, :, 1]
+    d = torch.stack([(px - 2).abs(), (px - (w - 2)).abs(), (py - 2).abs(), (py - (h - 2)).abs()], 0).amin(0)
+    return d.amin(1)
