@@ -18,12 +18,12 @@ c_ll = ctypes.c_longlong
 
 # name -> argument types (return type is always int, 0 = ok)
 SIGNATURES = {
-    "b200_volume_prepare": [c_f] * 12 + [c_i] * 4 + [ctypes.c_void_p],
+    "b200_volume_prepare": [c_f] * 12 + [c_i] * 5 + [ctypes.c_void_p],
     "b200_feats_to_pixel_major": [c_f, c_f, c_i, c_i, c_i, c_ll, c_ll, c_i, ctypes.c_void_p],
     "b200_volume_argmax": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
     "b200_cv_dot": [c_f] * 7 + [c_i] * 6 + [ctypes.c_void_p],
     "b200_fv_mlp_simt": [c_f] * 13 + [c_i] * 7 + [ctypes.c_void_p],
-    "b200_fv_mlp_tc": [c_f] * 12 + [c_i] * 6 + [ctypes.c_void_p],
+    "b200_fv_mlp_tc": [c_f] * 12 + [c_i] * 7 + [ctypes.c_void_p],
     "b200_fv_tc_wimage_bytes": [c_i],
     "b200_fv_tc_layout": [c_i, ctypes.c_void_p],
     "b200_conv_create": [ctypes.c_void_p, ctypes.c_void_p],
@@ -39,7 +39,7 @@ SIGNATURES = {
     "b200_instance_norm": [c_f] * 7 + [c_i] * 6 + [ctypes.c_float, ctypes.c_float, c_i, ctypes.c_void_p],
     "b200_instance_norm_ws_bytes": [c_i, c_i, ctypes.c_void_p, ctypes.c_void_p],
     "b200_stem_conv7": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
-    "b200_stem_conv7_tc": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
+    "b200_stem_conv7_tc": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, ctypes.c_void_p],
     "b200_maxblurpool": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, ctypes.c_void_p],
     "b200_dwconv3x3_silu": [c_f] * 6 + [c_i] * 5 + [ctypes.c_void_p],
     "b200_squeeze_excite": [c_f] * 10 + [c_i] * 4 + [ctypes.c_void_p],
@@ -48,8 +48,6 @@ SIGNATURES = {
     "b200_split_add": [c_f] * 6 + [c_ll, ctypes.c_void_p],
     "b200_channel_dot_exp": [c_f] * 6 + [c_ll, c_i, ctypes.c_void_p],
     "b200_sigmoid_resize": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, ctypes.c_float, c_i, c_i, ctypes.c_void_p],
-    "b200_set_sm_cap": [c_i],
-    "b200_sm_cap": [],
     "b200_sample_prior": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
     "b200_relative_poses": [c_f] * 6 + [c_i, c_i, ctypes.c_void_p],
     "b200_intrinsics_pyramid": [c_f, c_f, c_f, c_i, c_i, ctypes.c_void_p],
@@ -58,7 +56,11 @@ SIGNATURES = {
     "b200_binary_mlp_search": [ctypes.c_void_p, c_f, c_i, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_f, c_f,
                                ctypes.c_void_p],
     "b200_binary_mlp_destroy": [ctypes.c_void_p],
+}
+# dev-probe library (csrc/dev/, `build.build_dev()`): tcgen05 self-test + MMA issue-rate probe
+DEV_SIGNATURES = {
     "b200_umma_probe": [c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
+    "b200_mma_rate": [ctypes.c_void_p, c_i, c_i, c_i, c_i, ctypes.c_void_p],
 }
 
 _lib = None
@@ -77,6 +79,7 @@ def load():
             f"{LIB_PATH} not found: build it with `python -m implicit_depth_b200.build` "
             "(there is no CPU/PyTorch fallback for this path)")
     lib = ctypes.CDLL(LIB_PATH)
+    _check_digest(lib)
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.argtypes = argtypes
@@ -88,6 +91,51 @@ def load():
     lib.b200_fv_tc_layout.restype = ctypes.c_int
     _lib = lib
     return lib
+
+
+def _check_digest(lib):
+    """A library built from other sources than the ones next to it must not be called through these signatures."""
+    from . import build
+
+    if not os.path.isdir(build.CSRC):
+        return  # binary-only deployment: nothing to compare with
+    try:
+        fn = lib.b200_source_digest
+    except AttributeError:
+        raise B200Error(f"{LIB_PATH} predates the source-digest check: rebuild with `python -m implicit_depth_b200.build`")
+    fn.restype = ctypes.c_char_p
+    have, want = fn().decode(), build.source_digest()
+    if have != want:
+        raise B200Error(f"{LIB_PATH} was built from different sources (library {have[:12]}, csrc {want[:12]}): "
+                        "rebuild with `python -m implicit_depth_b200.build`")
+
+
+_dev = None
+
+
+def load_dev():
+    """The dev-probe library (tests/test_umma_probe_gpu.py, scripts/mma_rate.py)."""
+    global _dev
+    if _dev is None:
+        from . import build
+
+        if not os.path.exists(build.DEV_LIB):
+            raise B200Error(f"{build.DEV_LIB} not found: build it with `python -m implicit_depth_b200.build`")
+        lib = ctypes.CDLL(build.DEV_LIB)
+        for name, argtypes in DEV_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_int
+        lib.b200_last_error.restype = ctypes.c_char_p
+        _dev = lib
+    return _dev
+
+
+def call_dev(name, *args):
+    lib = load_dev()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise B200Error(f"{name} failed ({rc}): {lib.b200_last_error().decode()}")
 
 
 def ptr(t):

@@ -133,12 +133,11 @@ class B200BDModel(nn.Module):
         self.bce_loss.register_buffer("pos_weight", torch.ones(1))
         self._state = {}
         self._graphs = {}
+        self._versioned = None
         self.use_cuda_graph = False
         # the image encoder is independent of the matching encoder + plane sweep until the cost-volume encoder:
-        # run it (BatchNorm folded) on a side stream so its many small cuDNN launches overlap our kernels
-        import os
-
-        self.overlap_image_encoder = os.environ.get("B200_ENC_OVERLAP", "1") != "0"  # dev knob
+        # run it on a side stream so its many small launches overlap the matching encoder and the plane sweep
+        self.overlap_image_encoder = True
         # cuDNN's default TF32 convolutions in the image encoder alone push pred_0 to 1.7e-2 of the fp32 reference
         # (scripts/tf32_encoder_check.py; strict fp32: 9e-5), far outside the 1e-3 parity budget: keep it in fp32
         self.encoder_strict_fp32 = True
@@ -156,44 +155,23 @@ class B200BDModel(nn.Module):
         self.output_views = None
 
     def _apply(self, fn, *a, **k):
-        self._state, self._graphs, self._enc_fast, self._side = {}, {}, None, None
+        self._state, self._graphs, self._enc_fast, self._side, self._versioned = {}, {}, None, None, None
         self._enc_graphs, self._enc_pending = {}, None
         return super()._apply(fn, *a, **k)
+
+    FRONT_SM_FRACTION = 0.54  # see _front_sm_cap
 
     def _front_sm_cap(self):
         """CTA cap for the persistent kernels of the matching encoder and the plane sweep while the image encoder
         (a long chain of small-grid kernels) runs beside them on its own stream; 0 = no cap."""
-        import os
-
         if not (self.native_image_encoder and self.overlap_image_encoder):
             return 0
-        if "B200_FRONT_SM_CAP" in os.environ:  # dev knob
-            return int(os.environ["B200_FRONT_SM_CAP"])
         if self.encoder_ahead:  # the encoder is not inside this forward
             return 0
-        # a little over half the machine: measured optimum on B200 (scripts/sm_cap_sweep.py, ms per step at cfg2:
+        # a little over half the machine: measured optimum on B200 (profiles/r01f_sm_cap_sweep.md, ms per step at cfg2:
         # cap 64 -> 9.69, 74 -> 9.10, 78 -> 8.96, 80 -> 8.92, 82 -> 9.08, 86 -> 9.07, 100 -> 9.23+)
-        return round(0.54 * torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count)
-
-    def _fv_schedule(self, B):
-        """Plane sweep as several launches over groups of frames, each with its own CTA cap (dev knob
-        `B200_FV_SPLIT="frames:cap,frames:cap"`): while the image encoder still runs the first frames stay on half
-        the SMs, the last ones spread over the SMs it has freed.  None = one launch under `_fv_sm_cap`."""
-        import os
-
-        spec = os.environ.get("B200_FV_SPLIT", "")
-        if not spec or not (self.native_image_encoder and self.overlap_image_encoder):
-            return None
-        sched = [tuple(int(x) for x in part.split(":")) for part in spec.split(",")]
-        return sched if sum(n for n, _ in sched) == B else None
-
-    def _fv_sm_cap(self):
-        """CTA cap of the plane-sweep kernel (same window as `_front_sm_cap`; separate dev knob)."""
-        import os
-
-        if "B200_FV_SM_CAP" in os.environ and self.native_image_encoder and self.overlap_image_encoder:
-            return int(os.environ["B200_FV_SM_CAP"])
-        return self._front_sm_cap()
+        return round(self.FRONT_SM_FRACTION *
+                     torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count)
 
     def _run_native_encoder(self, st, dev):
         """Launches the native encoder plan (side stream when `overlap_image_encoder`); returns join()."""
@@ -201,9 +179,7 @@ class B200BDModel(nn.Module):
             st.encp.run()
             return lambda: None
         if self._side is None:
-            import os
-
-            self._side = torch.cuda.Stream(device=dev, priority=int(os.environ.get("B200_ENC_PRIORITY", "0")))
+            self._side = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
@@ -242,13 +218,10 @@ class B200BDModel(nn.Module):
         ms = self.run_opts.matching_scale
         D = self.run_opts.matching_num_depth_bins
         slots = {}
-        pre = Plan(dev)  # matching encoder
-        _abi.call("b200_set_sm_cap", self._front_sm_cap())
-        try:
-            feats_pm, h, w = self.matching_model.plan(pre, lambda: slots["images"], B * (K + 1), H, W,
-                                                      feat_layout=self.cost_volume.FEAT_LAYOUT)
-        finally:
-            _abi.call("b200_set_sm_cap", 0)
+        cap = self._front_sm_cap()
+        pre = Plan(dev, max_ctas=cap)  # matching encoder (shares the GPU with the image encoder's stream)
+        feats_pm, h, w = self.matching_model.plan(pre, lambda: slots["images"], B * (K + 1), H, W,
+                                                  feat_layout=self.cost_volume.FEAT_LAYOUT)
         post = Plan(dev)  # cost-volume encoder, decoder, binary MLP
         enc_ch = list(self.encoder.num_ch_enc)
         encp = None
@@ -284,6 +257,7 @@ class B200BDModel(nn.Module):
         pred, search_depths = self._plan_head(post, dec_in, slots, P, search)
         ahead = encp is not None and self.encoder_ahead
         return SimpleNamespace(slots=slots, pre=pre, post=post, encp=encp, feats_pm=feats_pm, h=h, w=w, pred=pred,
+                               front_cap=cap,
                                search_depths=search_depths, feat_layout=self.cost_volume.FEAT_LAYOUT,
                                enc_out=(enc_out if ahead else None), post_in=(img_feats if ahead else None),
                                encoder_ahead=ahead)
@@ -339,14 +313,13 @@ class B200BDModel(nn.Module):
         mx = torch.tensor(self.run_opts.max_matching_depth, device=cur_image.device).view(1, 1, 1, 1) \
             if not hasattr(self, "_mx") or self._mx.device != cur_image.device else self._mx
         self._mn, self._mx = mn, mx
-        _abi.call("b200_set_sm_cap", self._fv_sm_cap())
-        self.cost_volume.sm_schedule = self._fv_schedule(B)
+        self.cost_volume.max_ctas = st.front_cap
         try:
             cost_volume, lowest_cost, _, overall_mask = self.cost_volume.forward_pixel_major(
                 cur_pm, src_pm, src_cam_T_cur_cam, cur_cam_T_src_cam, src_K, cur_invK, mn, mx, None, return_mask, B, K,
                 st.h, st.w)
         finally:
-            _abi.call("b200_set_sm_cap", 0)
+            self.cost_volume.max_ctas = 0
         if st.encp is None:
             join_encoder()
         st.slots["enc"] = enc_feats
@@ -358,12 +331,30 @@ class B200BDModel(nn.Module):
             join_encoder()  # formal join of the side stream (its last op already gates the decoder)
         return st.pred, lowest_cost, overall_mask, st.search_depths
 
+    def _weights_version(self):
+        """Changes whenever any parameter / buffer of the model is modified in place (sub-module `load_state_dict`,
+        `init_model_weights`, an optimiser step): the launch plans and captured graphs hold packed, BatchNorm-folded
+        copies of the weights and must be rebuilt then.  (Tensor versions only grow, so their sum identifies the
+        state; re-allocations go through `_apply`.)"""
+        if self._versioned is None:
+            self._versioned = list(self.parameters()) + list(self.buffers())
+        return sum(t._version for t in self._versioned)
+
+    def _sync_weights(self):
+        """Drop plans and graphs built from weights that have since been modified (called at the top of forward)."""
+        if self._state and next(iter(self._state.values())).weights_version != self._weights_version():
+            self._state, self._graphs, self._enc_graphs, self._enc_pending = {}, {}, {}, None
+
     def _ensure_state(self, B, K, H, W, P, dev, search=False):
         key = (B, K, H, W, P, search)
         st = self._state.get(key)
+        wv = self._weights_version()
+        if st is not None and st.weights_version != wv:
+            st = None
         if st is None or st.feat_layout != self.cost_volume.FEAT_LAYOUT or \
                 st.encoder_ahead != (self.encoder_ahead and st.encp is not None):
             self._state = {key: self._build(B, K, H, W, P, dev, search)}
+            self._state[key].weights_version = wv
             self._graphs, self._enc_graphs, self._enc_pending = {}, {}, None  # they point into the old plans
         return self._state[key]
 
@@ -375,6 +366,7 @@ class B200BDModel(nn.Module):
         if not (self.encoder_ahead and self.native_image_encoder):
             raise RuntimeError("run_encoder needs encoder_ahead mode with the built-in encoder")
         B, _, H, W = cur_image.shape
+        self._sync_weights()
         st = self._ensure_state(B, K, H, W, P, cur_image.device, search)
         if not self.use_cuda_graph:
             st.slots["cur_image"] = cur_image
@@ -448,6 +440,7 @@ class B200BDModel(nn.Module):
         ms = self.run_opts.matching_scale
         cur_image = cur_data["image_b3hw"]
         _abi.require_cuda(cur_image)
+        self._sync_weights()
         f = lambda t: t if t.dtype == torch.float32 else t.float()
         args = [f(cur_image).contiguous(), f(src_data["image_b3hw"]), f(src_data[f"K_s{ms}_b44"]),
                 f(cur_data[f"invK_s{ms}_b44"]), f(src_data["cam_T_world_b44"]), f(src_data["world_T_cam_b44"]),

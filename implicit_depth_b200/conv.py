@@ -22,7 +22,7 @@ class _Desc(ctypes.Structure):
                 ("bias", ctypes.c_void_p), ("res_hi", ctypes.c_void_p), ("res_lo", ctypes.c_void_p),
                 ("out_hi", ctypes.c_void_p), ("out_lo", ctypes.c_void_p), ("out_f32", ctypes.c_void_p),
                 ("B", ctypes.c_int), ("OH", ctypes.c_int), ("OW", ctypes.c_int), ("Cout", ctypes.c_int),
-                ("act", ctypes.c_int), ("slope", ctypes.c_float)]
+                ("act", ctypes.c_int), ("slope", ctypes.c_float), ("max_ctas", ctypes.c_int)]
 
 
 class SplitAct:
@@ -111,9 +111,10 @@ def pack_conv_weights(weights, seg_channels, cout, halo=False, nt=None):
 class ConvPlan:
     """One convolution launch with everything (tensor maps, weight image, buffers) fixed at plan time."""
 
-    def __init__(self, segs, weights, bias, out, B, cout, act="none", slope=0.2, residual=None, out_f32=None):
+    def __init__(self, segs, weights, bias, out, B, cout, act="none", slope=0.2, residual=None, out_f32=None,
+                 max_ctas=0):
         """segs: list of (SplitAct, ksize, stride, pad); weights: one [Cout, C, k, k] fp32 tensor per segment;
-        out: SplitAct or None; residual: SplitAct or None."""
+        out: SplitAct or None; residual: SplitAct or None; max_ctas: CTA cap of the persistent launch (0 = all SMs)."""
         d = _Desc()
         d.nseg = len(segs)
         for i, (a, k, s, p) in enumerate(segs):
@@ -133,6 +134,7 @@ class ConvPlan:
         d.B, d.OH, d.OW, d.Cout = B, OH, OW, cout
         d.act = ACT[act]
         d.slope = slope
+        d.max_ctas = int(max_ctas)
         lib = _abi.load()
         self.halo = bool(lib.b200_conv_uses_halo(ctypes.byref(d)))  # decides the weight-image layout
         self.nt = int(lib.b200_conv_ntile_for(ctypes.byref(d)))  # N tile of this conv (weight-image layout)

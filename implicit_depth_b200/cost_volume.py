@@ -114,6 +114,7 @@ class B200CostVolumeManager(nn.Module):
         self.register_buffer("linear_ramp_1d11", torch.linspace(0, 1, num_depth_bins).view(1, num_depth_bins, 1, 1))
         self.backprojector = _PixGrid(matching_height, matching_width)
         self.projector = _Eps()
+        self.max_ctas = 0  # CTA cap of the persistent feature-volume kernel (0 = all SMs); see B200BDModel
 
     # ---- helpers -----------------------------------------------------------------------
     def _check_shapes(self, cur_feats, src_feats):
@@ -151,12 +152,18 @@ class B200CostVolumeManager(nn.Module):
         cams = torch.empty((B, K, 32), device=dev, dtype=torch.float32)
         planes = torch.empty((B, D), device=dev, dtype=torch.float32)
         bias_eff = torch.empty((B, MLP_HID), device=dev, dtype=torch.float32) if W1 is not None else None
-        mn = _as_f32c(min_depth.reshape(-1)) if planes_in is None else None
-        mx = _as_f32c(max_depth.reshape(-1)) if planes_in is None else None
+        mn = mx = None
+        per_frame = 0
+        if planes_in is None:
+            # the reference broadcasts min/max over the batch (cost_volume.py:117-126): one range or one per frame
+            mn, mx = _as_f32c(min_depth.reshape(-1)), _as_f32c(max_depth.reshape(-1))
+            if mn.numel() != mx.numel() or mn.numel() not in (1, B):
+                raise ValueError(f"min_depth / max_depth must hold 1 or B={B} values, got {mn.numel()} / {mx.numel()}")
+            per_frame = 1 if (mn.numel() == B and B > 1) else 0
         _abi.call("b200_volume_prepare", _abi.ptr(_as_f32c(src_Ks)), _abi.ptr(_as_f32c(src_extrinsics)),
                   _abi.ptr(_as_f32c(src_poses)), _abi.ptr(_as_f32c(cur_invK)), _abi.ptr(mn), _abi.ptr(mx),
                   _abi.ptr(planes_in), _abi.ptr(W1), _abi.ptr(b1), _abi.ptr(cams), _abi.ptr(planes),
-                  _abi.ptr(bias_eff), B, K, D, FEAT_C, _abi.stream_ptr())
+                  _abi.ptr(bias_eff), B, K, D, FEAT_C, per_frame, _abi.stream_ptr())
         return cams, planes, bias_eff
 
     # ---- reference API -----------------------------------------------------------------
@@ -311,22 +318,10 @@ class B200FeatureVolumeManager(B200CostVolumeManager):
         mask = torch.empty((B, h, w), device=dev, dtype=torch.bool) if return_mask else None
         invK = _as_f32c(cur_invK)
         if self.impl in ("auto", "tc"):
-            # one launch, or one per group of frames with its own CTA cap (`sm_schedule`: [(frames, cap), ...]; a
-            # caller sharing the GPU with another stream lets the later frames spread over the SMs that stream frees)
-            sched = getattr(self, "sm_schedule", None)
-            if not sched or sum(n for n, _ in sched) != B:
-                sched = [(B, None)]
-            b0 = 0
-            for nb, cap in sched:
-                if cap is not None:
-                    _abi.call("b200_set_sm_cap", int(cap))
-                sl = slice(b0, b0 + nb)
-                _abi.call("b200_fv_mlp_tc", _abi.ptr(cur_pm[sl]), _abi.ptr(src_pm[sl]), _abi.ptr(cams[sl]),
-                          _abi.ptr(invK[sl]), _abi.ptr(planes[sl]), _abi.ptr(bias_eff[sl]), _abi.ptr(pk["wimage"]),
-                          _abi.ptr(pk["b2"]), _abi.ptr(pk["w3"]), _abi.ptr(pk["b3"]), _abi.ptr(vol[sl]),
-                          _abi.ptr(mask[sl] if mask is not None else None), nb, K, FEAT_C, h, w, D,
-                          _abi.stream_ptr())
-                b0 += nb
+            _abi.call("b200_fv_mlp_tc", _abi.ptr(cur_pm), _abi.ptr(src_pm), _abi.ptr(cams), _abi.ptr(invK),
+                      _abi.ptr(planes), _abi.ptr(bias_eff), _abi.ptr(pk["wimage"]), _abi.ptr(pk["b2"]),
+                      _abi.ptr(pk["w3"]), _abi.ptr(pk["b3"]), _abi.ptr(vol), _abi.ptr(mask), B, K, FEAT_C, h, w, D,
+                      int(self.max_ctas), _abi.stream_ptr())
         elif self.impl == "simt":
             _abi.call("b200_fv_mlp_simt", _abi.ptr(cur_pm), _abi.ptr(src_pm), _abi.ptr(cams), _abi.ptr(invK),
                       _abi.ptr(planes), _abi.ptr(bias_eff), _abi.ptr(pk["W1p"]), _abi.ptr(pk["W2t"]),

@@ -34,10 +34,6 @@
 extern "C" const char* b200_last_error(void);
 void b200_set_error(const char* fmt, ...);
 
-// Upper bound on the CTAs of the persistent kernels launched / planned from now on (0 = all SMs): lets a caller keep
-// some SMs free for work on another stream (b200_set_sm_cap).
-extern "C" int b200_sm_cap(void);
-
 #define B200_CHECK_ARG(cond, ...)            \
   do {                                       \
     if (!(cond)) {                           \

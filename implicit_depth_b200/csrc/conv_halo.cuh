@@ -20,9 +20,9 @@
 #define CVH_ROWS 16
 #define CVH_EPI_THREADS 256
 
-template <int SUB, int NTC /* NT / 64: 1 or 2 */, bool PROF /* dev: per-role clock64 accounting */>
+template <int SUB, int NT /* N tile: 128, 64, or 16 (direct-store epilogue, no residual) */>
 __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvKParams prm) {
-  constexpr int NT = 64 * NTC;
+  constexpr int NTC = NT / 64;  // 64-channel store boxes per N tile (0 for the 16-wide tile)
   constexpr int PW = 8 * SUB + 2;
   constexpr uint32_t PATCH_PLANE = (18u * PW * 64u + 1023u) & ~1023u;  // one bf16 plane of a 32-channel patch
   constexpr uint32_t B_BYTES = NT * 128u;                              // [hi NT x 32 | lo NT x 32] bf16
@@ -48,18 +48,16 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + S);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_t0 = 0;
-  const long long k_t0 = clock64();
-#define PROF_T0 if (PROF) prof_t0 = clock64()
-#define PROF_ADD(i) if (PROF) prof_acc[i] += clock64() - prof_t0
   const int items = prm.B * prm.tiles_y * prm.tiles_x * prm.n_ntiles;
 
   for (int i = tid; i < prm.n_ntiles * NT; i += CVH_THREADS)
     bias_s[i] = (prm.bias != nullptr && i < prm.Cout) ? prm.bias[i] : 0.f;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < 2 * prm.nseg; ++s) tc::prefetch_tmap(&prm.maps[s]);
-    tc::prefetch_tmap(&prm.out_maps[0]);
-    tc::prefetch_tmap(&prm.out_maps[1]);
+    if (NT != 16) {
+      tc::prefetch_tmap(&prm.out_maps[0]);
+      tc::prefetch_tmap(&prm.out_maps[1]);
+    }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&p_full[i], 1);
       tc::mbar_init(&p_empty[i], 1);
@@ -99,16 +97,12 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
         const int x0 = tx * 8 * SUB + org, y0 = ty * CVH_ROWS + org;
         for (int cb = 0; cb < cblocks; ++cb, ++pit) {
           const uint32_t pb = pit & 1u, round = pit >> 1;
-          if (round > 0) { PROF_T0; tc::mbar_wait(&p_empty[pb], (round - 1) & 1u); PROF_ADD(0); }
+          if (round > 0) tc::mbar_wait(&p_empty[pb], (round - 1) & 1u);
           uint8_t* pa = patch0 + (size_t)pb * 2u * PATCH_PLANE;
           if (tc::elect_one()) {
-            if (prm.debug & 2) {
-              tc::mbar_arrive(&p_full[pb]);
-            } else {
-              tc::mbar_expect_tx(&p_full[pb], 2u * (uint32_t)(18 * PW * 64));
-              tc::tma_load_4d(pa, &prm.maps[2 * s], cb * 32, x0, y0, b, &p_full[pb]);
-              tc::tma_load_4d(pa + PATCH_PLANE, &prm.maps[2 * s + 1], cb * 32, x0, y0, b, &p_full[pb]);
-            }
+            tc::mbar_expect_tx(&p_full[pb], 2u * (uint32_t)(18 * PW * 64));
+            tc::tma_load_4d(pa, &prm.maps[2 * s], cb * 32, x0, y0, b, &p_full[pb]);
+            tc::tma_load_4d(pa + PATCH_PLANE, &prm.maps[2 * s + 1], cb * 32, x0, y0, b, &p_full[pb]);
           }
           __syncwarp();
           // weights: TPS taps per stage (a kernel row of a 3x3 segment when TPS = 3), chunks ordered (seg, cb, tap)
@@ -117,16 +111,12 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
             const int nt_g = min(TPS, ntaps - tap);
             const uint32_t st = bst, r2 = bround;
             if (++bst == (uint32_t)S) { bst = 0; ++bround; }
-            if (r2 > 0) { PROF_T0; tc::mbar_wait(&b_empty[st], (r2 - 1) & 1u); PROF_ADD(1); }
+            if (r2 > 0) tc::mbar_wait(&b_empty[st], (r2 - 1) & 1u);
             if (tc::elect_one()) {
-              if (prm.debug & 2) {
-                tc::mbar_arrive(&b_full[st]);
-              } else {
-                tc::mbar_expect_tx(&b_full[st], nt_g * B_BYTES);
-                tc::bulk_load(bring + (size_t)st * (TPS * B_BYTES),
-                              wbase + (size_t)(prm.seg_chunk0[s] + cb * ntaps + tap) * B_BYTES, nt_g * B_BYTES,
-                              &b_full[st]);
-              }
+              tc::mbar_expect_tx(&b_full[st], nt_g * B_BYTES);
+              tc::bulk_load(bring + (size_t)st * (TPS * B_BYTES),
+                            wbase + (size_t)(prm.seg_chunk0[s] + cb * ntaps + tap) * B_BYTES, nt_g * B_BYTES,
+                            &b_full[st]);
             }
             __syncwarp();
           }
@@ -142,7 +132,7 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
     uint32_t bst = 0, bround = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
       const uint32_t a = tile_i & 1u, use = tile_i >> 1;
-      if (use > 0) { PROF_T0; tc::mbar_wait(&acc_empty[a], (use - 1) & 1u); PROF_ADD(2); }
+      if (use > 0) tc::mbar_wait(&acc_empty[a], (use - 1) & 1u);
       tc::fence_after_sync();
       const uint32_t acc = tmem + a * ACC_COLS;
       uint32_t first = 1;
@@ -151,7 +141,7 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
         const int cblocks = (C + 31) >> 5;
         for (int cb = 0; cb < cblocks; ++cb, ++pit) {
           const uint32_t pb = pit & 1u;
-          { PROF_T0; tc::mbar_wait(&p_full[pb], (pit >> 1) & 1u); PROF_ADD(3); }
+          tc::mbar_wait(&p_full[pb], (pit >> 1) & 1u);
           tc::fence_after_sync();
           const uint32_t pa = tc::smem_u32(patch0 + (size_t)pb * 2u * PATCH_PLANE);
           const int ksteps = (min(32, C - cb * 32) + 15) >> 4;
@@ -160,7 +150,7 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
           for (int tap = 0; tap < ntaps; tap += TPS) {
             const int nt_g = min(TPS, ntaps - tap);
             const uint32_t st = bst;
-            { PROF_T0; tc::mbar_wait(&b_full[st], bround & 1u); PROF_ADD(4); }
+            tc::mbar_wait(&b_full[st], bround & 1u);
             if (++bst == (uint32_t)S) { bst = 0; ++bround; }
             tc::fence_after_sync();
             const uint32_t sb = tc::smem_u32(bring) + st * (TPS * B_BYTES);
@@ -173,7 +163,6 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
                   const uint64_t a_hi = tc::smem_desc_sw64(pa + row0 + sub * 512u, SBO);
                   const uint64_t a_lo = a_hi + (PATCH_PLANE >> 4);
                   const uint32_t d = acc + sub * 2 * NT;
-                  if (prm.debug & 4) continue;  // dev: no MMAs
                   // hi*hi -> columns [0,NT), hi*lo -> columns [NT,2NT): one N = 2*NT instruction per k-step
                   tc::mma_ss(d, a_hi, b_m, IDESC_MERGED, (first && t == 0) ? 0u : 1u);
                   if (ksteps > 1) tc::mma_ss(d, a_hi + 2, b_m + 2, IDESC_MERGED, 1u);
@@ -208,6 +197,45 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
     constexpr int COLS = NT / 2;              // columns per thread: 32 (NT = 64) or 64 (NT = 128)
     const uint32_t swz = (uint32_t)(row & 7);
     uint32_t tile_i = 0;
+    if constexpr (NT == 16) {
+      // 16-wide N tile (the 3x3 128 -> 16 head of the matching encoder): warp group `half` drains sub-tile `half`;
+      // a thread holds all 16 channels of its pixel and stores them directly (32 B per plane, image border by test)
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
+        const int mt = item;  // n_ntiles == 1
+        const int tx = mt % prm.tiles_x;
+        const int ty = (mt / prm.tiles_x) % prm.tiles_y;
+        const int b = mt / (prm.tiles_x * prm.tiles_y);
+        const uint32_t a = tile_i & 1u;
+        tc::mbar_wait(&acc_full[a], (tile_i >> 1) & 1u);
+        tc::fence_after_sync();
+        if (half < SUB) {
+          uint32_t rm[16], rc[16];
+          const uint32_t t_main = tmem + lane_base + a * ACC_COLS + half * 2 * NT;
+          tc::tmem_ld16(t_main, rm);
+          tc::tmem_ld16(t_main + NT, rc);
+          tc::wait_ld();
+          const int oy = ty * CVH_ROWS + (row >> 3), ox = tx * 8 * SUB + half * 8 + (row & 7);
+          if (oy < prm.OH && ox < prm.OW) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              v[j] = apply_act((__uint_as_float(rm[j]) + __uint_as_float(rc[j])) + bias_s[j], prm.act, prm.slope);
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tc::split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+            const size_t o = (((size_t)b * prm.OH + oy) * prm.OW + ox) * 16;
+            uint4* oh = reinterpret_cast<uint4*>(prm.out_hi + o);
+            uint4* ol = reinterpret_cast<uint4*>(prm.out_lo + o);
+            oh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            oh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          }
+        }
+        tc::fence_before_sync();
+        tc::mbar_arrive(&acc_empty[a]);
+      }
+    } else
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
       const int nt = item % prm.n_ntiles;
       const int mt = item / prm.n_ntiles;
@@ -233,15 +261,13 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
         }
       }
       tc::named_sync(1, CVH_EPI_THREADS);
-      { PROF_T0; tc::mbar_wait(&acc_full[a], (tile_i >> 1) & 1u); PROF_ADD(5); }
+      tc::mbar_wait(&acc_full[a], (tile_i >> 1) & 1u);
       tc::fence_after_sync();
-      const long long ep0 = PROF ? clock64() : 0;
       const float* bias_t = bias_s + nt * NT + half * COLS;
 #pragma unroll
       for (int sub = 0; sub < SUB; ++sub) {
         uint8_t* sg = staging + sub * STAGING;
         if (has_res) tc::mbar_wait(&res_full[sub], tile_i & 1u);
-        if (prm.debug & 1) continue;  // dev: skip the TMEM drain / staging writes
         const uint32_t t_main = tmem + lane_base + a * ACC_COLS + sub * 2 * NT + half * COLS;
 #pragma unroll
         for (int c0 = 0; c0 < COLS; c0 += 32) {
@@ -290,7 +316,7 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
       tc::mbar_arrive(&acc_empty[a]);
       tc::fence_async_smem();
       tc::named_sync(1, CVH_EPI_THREADS);
-      if (leader && !(prm.debug & 1)) {
+      if (leader) {
 #pragma unroll
         for (int sub = 0; sub < SUB; ++sub)
 #pragma unroll
@@ -301,18 +327,9 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
                                nt * NT + blk * 64, tx * 8 * SUB + sub * 8, ty * CVH_ROWS, b);
         tc::tma_store_commit();
       }
-      if (PROF) prof_acc[6] += clock64() - ep0;
     }
-    if (leader) tc::tma_store_wait_all<0>();
+    if (NT != 16 && leader) tc::tma_store_wait_all<0>();
   }
-  if (PROF && prm.prof && lane == 0 && (warp <= 2)) {
-    long long* o = prm.prof + (size_t)blockIdx.x * 8;
-    if (warp == 0) { o[0] = prof_acc[0]; o[1] = prof_acc[1]; }
-    if (warp == 1) { o[2] = prof_acc[2]; o[3] = prof_acc[3]; o[4] = prof_acc[4]; o[7] = clock64() - k_t0; }
-    if (warp == 2) { o[5] = prof_acc[5]; o[6] = prof_acc[6]; }
-  }
-#undef PROF_T0
-#undef PROF_ADD
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem, 512);

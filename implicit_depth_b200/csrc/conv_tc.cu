@@ -49,8 +49,6 @@ struct ConvKParams {
   float slope;
   int halo, sub, has_res, tps;
   int seg_chunk0[CV_MAX_SEG];  // index of each segment's first chunk in the weight image
-  long long* prof;             // dev only: per-CTA role timings [grid][8] (clock64 ticks) or null
-  int debug;                   // dev only (B200_CONV_DEBUG): 1 = no epilogue body, 2 = no TMA loads, 4 = no MMAs
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -276,6 +274,8 @@ struct b200_conv_desc {
   float* out_f32;
   int B, OH, OW, Cout, act;
   float slope;
+  int max_ctas;  // upper bound on the CTAs of this (persistent) launch, 0 = all SMs: lets the caller keep SMs free
+                 // for work on another stream
 };
 
 extern "C" int b200_conv_ntile(int Cout) { return Cout <= 128 ? Cout : 128; }
@@ -288,7 +288,7 @@ extern "C" int b200_conv_uses_halo(const b200_conv_desc* d);
 // 1536 -> 256 project convs of the image encoder at 12x16: 16 CTAs x 24 chunks -> 32 CTAs).
 extern "C" int b200_conv_ntile_for(const b200_conv_desc* d) {
   const int nt = b200_conv_ntile(d->Cout);
-  if (nt < 128 || b200_conv_uses_halo(d) || getenv("B200_CONV_NT128") != nullptr) return nt;
+  if (nt < 128 || b200_conv_uses_halo(d)) return nt;
   const int m_tiles = d->B * ((d->OW + CV_TW - 1) / CV_TW) * ((d->OH + CV_TH - 1) / CV_TH);
   return (m_tiles * (d->Cout / 128) <= 74) ? 64 : 128;
 }
@@ -296,18 +296,20 @@ extern "C" int b200_conv_ntile_for(const b200_conv_desc* d) {
 // 1 if this conv runs on the halo kernel (weight image in 32-channel chunks, 64-byte swizzle, [hi | lo] per
 // chunk), 0 for the plain kernel (64-channel chunks, 128-byte swizzle).  Pure function of the geometry.
 extern "C" int b200_conv_uses_halo(const b200_conv_desc* d) {
-  if (!d || getenv("B200_CONV_NO_HALO") != nullptr) return 0;
-  if (d->Cout % 64 != 0 || d->out_f32 != nullptr || d->out_hi == nullptr) return 0;
+  if (!d) return 0;
+  const bool n16 = d->Cout == 16;  // 16-wide N tile: 3x3 stride-1 segments only, no residual (matching-encoder head)
+  if ((d->Cout % 64 != 0 && !n16) || d->out_f32 != nullptr || d->out_hi == nullptr) return 0;
+  if (n16 && d->res_hi != nullptr) return 0;
   // a pure 1x1 conv uses every halo patch for a single tap, so the halo kernel's 2-deep patch ring exposes the TMA
   // latency of each 32-channel block (51 us for the 1536->256 project conv of the image encoder); the plain kernel
   // streams 64-channel boxes through a 3..6-stage ring instead
   bool all_1x1 = true;
   for (int s = 0; s < d->nseg; ++s) all_1x1 = all_1x1 && d->seg[s].ksize == 1;
-  if (all_1x1 && getenv("B200_CONV_1X1_HALO") == nullptr) return 0;
+  if (all_1x1) return 0;
   for (int s = 0; s < d->nseg; ++s) {
     const b200_conv_seg& sg = d->seg[s];
     const bool ok = sg.stride == 1 && ((sg.ksize == 3 && (sg.pad == 0 || sg.pad == 1)) || (sg.ksize == 1 && sg.pad == 0));
-    if (!ok) return 0;
+    if (!ok || (n16 && sg.ksize != 3)) return 0;
   }
   return 1;
 }
@@ -353,11 +355,10 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   k.n_ntiles = (d->Cout + k.NT - 1) / k.NT;
   const bool halo = b200_conv_uses_halo(d) != 0;
   k.halo = halo ? 1 : 0;
-  k.debug = getenv("B200_CONV_DEBUG") ? atoi(getenv("B200_CONV_DEBUG")) : 0;
   k.sub = 1;
   if (halo) {
     // two M=128 sub-tiles per item share every weight chunk when the N tile is 64 wide and there is enough work
-    k.sub = (k.NT == 64) ? 2 : 1;
+    k.sub = (k.NT <= 64) ? 2 : 1;
     if (k.sub == 2) {
       // wave quantisation on the persistent grid: an item of two sub-tiles costs ~1.7x an item of one (shared weight
       // chunks), so e.g. 192 double items on 148 SMs (2 waves = 3.4 units) lose to 384 single items (3 waves)
@@ -366,9 +367,6 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
       const int items1 = d->B * ((d->OW + 7) / 8) * rows * k.n_ntiles;
       const int waves2 = (items2 + n_sm - 1) / n_sm, waves1 = (items1 + n_sm - 1) / n_sm;
       if (items2 < n_sm || 10 * waves1 < 17 * waves2) k.sub = 1;
-      const char* e = getenv("B200_CONV_SUB");  // dev override
-      if (e != nullptr && atoi(e) == 2) k.sub = 2;
-      if (e != nullptr && atoi(e) == 1) k.sub = 1;
     }
   }
   const int cw = halo ? 32 : 64;  // channels per K chunk
@@ -411,7 +409,7 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
       }
     }
   }
-  if (halo) {
+  if (halo && k.NT != 16) {
     const cuuint32_t obox[4] = {64, 8, CVH_ROWS, 1};
     for (int part = 0; part < 2; ++part) {
       int r = encode_nhwc(enc, &k.out_maps[part], part ? d->out_lo : d->out_hi, d->Cout, d->OW, d->OH, d->B, obox, 1,
@@ -445,7 +443,7 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
     k.tiles_y = (d->OH + CVH_ROWS - 1) / CVH_ROWS;
     // weight stages: a whole kernel row (3 taps) per barrier round for the 64-wide N tile (halves the issue-loop
     // overhead per MMA); single taps for the 128-wide tile whose stages would otherwise be 48 KB
-    k.tps = (k.NT == 64) ? 3 : 1;
+    k.tps = (k.NT <= 64) ? 3 : 1;
     int S = 12 / k.tps;
     while (S > 2 && conv_halo_smem(k.sub, k.NT, S, k.tps, k.n_ntiles) > 227 * 1024) --S;
     k.stages = S;
@@ -462,22 +460,20 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   }
   const int items = k.B * k.tiles_x * k.tiles_y * k.n_ntiles;
   p->grid = items < n_sm ? items : n_sm;
-  if (b200_sm_cap() > 0 && p->grid > b200_sm_cap()) p->grid = b200_sm_cap();
+  if (d->max_ctas > 0 && p->grid > d->max_ctas) p->grid = d->max_ctas;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_halo_kernel<2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(conv_halo_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_halo_kernel<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(conv_halo_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_halo_kernel<1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(conv_halo_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_halo_kernel<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(conv_halo_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_halo_kernel<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_halo_kernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(conv_halo_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       delete p;
       b200_set_error("conv_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -496,11 +492,6 @@ extern "C" int b200_conv_run(void* plan, void* stream) {
   // Programmatic dependent launch: the kernels call griddepcontrol.wait after their prologue (barrier init, TMEM
   // allocation, tensor-map prefetch, bias staging), so on SMs the previous kernel has already left, the prologue
   // of this one overlaps the previous kernel's tail.  Captured into CUDA graphs as programmatic edges.
-  static int use_pdl = -1;
-  if (use_pdl < 0) {
-    const char* e = getenv("B200_PDL");
-    use_pdl = (e == nullptr || atoi(e) != 0) ? 1 : 0;
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p->grid);
   cfg.blockDim = dim3(p->k.halo ? CVH_THREADS : CV_THREADS);
@@ -510,32 +501,21 @@ extern "C" int b200_conv_run(void* plan, void* stream) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
+  cfg.numAttrs = 1;
   cudaError_t le;
   if (!p->k.halo)
     le = cudaLaunchKernelEx(&cfg, conv_tc_kernel, p->k);
-  else if (p->k.prof == nullptr) {
-    if (p->k.NT == 128) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 2, false>, p->k);
-    else if (p->k.sub == 2) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<2, 1, false>, p->k);
-    else le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 1, false>, p->k);
-  } else {
-    if (p->k.NT == 128) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 2, true>, p->k);
-    else if (p->k.sub == 2) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<2, 1, true>, p->k);
-    else le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 1, true>, p->k);
-  }
+  else if (p->k.NT == 128) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 128>, p->k);
+  else if (p->k.NT == 16 && p->k.sub == 2) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<2, 16>, p->k);
+  else if (p->k.NT == 16) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 16>, p->k);
+  else if (p->k.sub == 2) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<2, 64>, p->k);
+  else le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 64>, p->k);
   if (le != cudaSuccess) {
     b200_set_error("conv_run: launch failed: %s", cudaGetErrorString(le));
     return -2;
   }
   B200_CHECK_LAUNCH("conv_run");
   return 0;
-}
-
-// dev only: attach a [grid][8] int64 buffer for per-CTA role timings (halo kernel); returns the grid size
-extern "C" int b200_conv_set_prof(void* plan, long long* buf) {
-  ConvPlan* p = (ConvPlan*)plan;
-  p->k.prof = buf;
-  return p->grid;
 }
 
 extern "C" int b200_conv_destroy(void* plan) {

@@ -192,25 +192,17 @@ extern "C" int b200_cv_dot(const float* cur, const float* src, const float* cams
   B200_CHECK_ARG(C == B200_FEAT_C, "cv_dot: only %d feature channels supported (got %d)", B200_FEAT_C, C);
   B200_CHECK_ARG(B > 0 && K > 0 && K <= B200_MAX_VIEWS && D > 0 && h > 0 && w > 0,
                  "cv_dot: bad sizes B=%d K=%d D=%d h=%d w=%d", B, K, D, h, w);
-  B200_CHECK_ARG(D <= 4096, "cv_dot: at most 4096 depth planes (got %d)", D);
+  // static shared memory (~42 KB for K > 4) + D floats of plane depths must fit the 48 KB default carve-out
+  B200_CHECK_ARG(D <= 1024, "cv_dot: at most 1024 depth planes (got %d)", D);
   B200_CHECK_ARG((long long)h * w * B200_FEAT_C < (1ll << 30), "cv_dot: feature map too large (%d x %d)", h, w);
   B200_CHECK_ARG(cur && src && cams && planes && cost, "cv_dot: null pointer");
   B200_CHECK_ARG((((uintptr_t)cur | (uintptr_t)src) & 15) == 0, "cv_dot: feature pointers must be 16-byte aligned");
   const int N = h * w;
   dim3 grid(((w + 7) / 8) * ((h + CVD_WARPS - 1) / CVD_WARPS), B);
   cudaStream_t st = (cudaStream_t)stream;
-  static int mb = 0;  // tuning knob (dev): resident blocks per SM
-  if (mb == 0) {
-    const char* e = getenv("B200_CVD_MB");
-    mb = e ? atoi(e) : 3;
-  }
 #define CVD_LAUNCH(NR, MB) \
   cv_dot_kernel<NR, MB><<<grid, CVD_THREADS, D * sizeof(float), st>>>(cur, src, cams, planes, cost, lowest, best_idx, K, D, h, w)
-  if (K <= 4) {
-    if (mb == 2) CVD_LAUNCH(1, 2); else if (mb == 3) CVD_LAUNCH(1, 3); else if (mb == 5) CVD_LAUNCH(1, 5); else CVD_LAUNCH(1, 4);
-  } else {
-    if (mb == 2) CVD_LAUNCH(2, 2); else if (mb == 3) CVD_LAUNCH(2, 3); else if (mb == 5) CVD_LAUNCH(2, 5); else CVD_LAUNCH(2, 4);
-  }
+  if (K <= 4) CVD_LAUNCH(1, 3); else CVD_LAUNCH(2, 3);  // 3 resident blocks per SM: measured optimum
   B200_CHECK_LAUNCH("cv_dot");
   return 0;
 }

@@ -2,8 +2,8 @@
 // (A from shared memory vs tensor memory) and accumulator pattern.  One thread per CTA issues `iters`
 // groups of 12 MMAs (the split-bf16 K=64 chunk pattern of the conv / feature-volume kernels) over
 // uninitialised shared-memory tiles and reports elapsed SM clocks.  Not part of the product path.
-#include "common.cuh"
-#include "tc.cuh"
+#include "../common.cuh"
+#include "../tc.cuh"
 
 __global__ void __launch_bounds__(128) mma_rate_kernel(long long* out, int N, int mode, int iters) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];

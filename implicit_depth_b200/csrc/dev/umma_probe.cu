@@ -12,8 +12,8 @@
 //           the 32-channel-block conv kernel
 // The GPU tests compare D against a host matmul, so a layout mistake shows up as a numeric error
 // in a 30-line kernel instead of inside the fused ones.
-#include "common.cuh"
-#include "tc.cuh"
+#include "../common.cuh"
+#include "../tc.cuh"
 
 #define PROBE_MAX_K 192
 #define PROBE_MAX_N 128

@@ -348,69 +348,148 @@ extern "C" int b200_stem_conv7(const float* img, const float* wt, const float* b
 
 // MaxPool2d(kernel 2, stride 1) followed by BlurPool(filt 4 = [1,3,3,1]^2/64, stride 2, reflect pad
 // (1,2,1,2)) -- the anti-aliased "maxpool" of antialiased-cnns 0.3 -- fused; H,W -> H/2,W/2 for even sizes.
-__global__ void maxblurpool_kernel(const __nv_bfloat16* __restrict__ ih, const __nv_bfloat16* __restrict__ il,
-                                   __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, int B, int H, int W,
-                                   int C, int OH, int OW) {
+//   M[my][mx]  = max of the 2x2 input block at (my, mx)                 (max-pooled map, (H-1) x (W-1))
+//   out[oy][ox] = sum_{a,q} f[a] f[q] / 64 * M[refl(2oy+a-1)][refl(2ox+q-1)],  f = [1,3,3,1]
+// Two kernels: interior output rows slide down the image (below), the one or two rows whose window reflects at the
+// top / bottom edge take the direct form.
+__device__ __forceinline__ int mbp_reflect(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
+
+// direct form, one thread = one output pixel x 8 channels; rows = the output rows to compute (n_rows of them)
+__global__ void maxblurpool_rows_kernel(const __nv_bfloat16* __restrict__ ih, const __nv_bfloat16* __restrict__ il,
+                                        __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, int B, int H, int W,
+                                        int C, int OH, int OW, int row_a, int row_b_first, int n_rows) {
   const int cg = C >> 3;
-  const int MH = H - 1, MW = W - 1;  // max-pooled size
-  const size_t total = (size_t)B * OH * OW * cg;
+  const int MH = H - 1, MW = W - 1;
+  const size_t total = (size_t)B * n_rows * OW * cg;
   const float f[4] = {1.f, 3.f, 3.f, 1.f};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % cg);
     size_t r = i / cg;
     const int ox = (int)(r % OW);
     r /= OW;
-    const int oy = (int)(r % OH);
-    const int b = (int)(r / OH);
+    const int ri = (int)(r % n_rows);
+    const int b = (int)(r / n_rows);
+    const int oy = ri == 0 ? row_a : row_b_first + ri - 1;  // row_a (the top row), then row_b_first, row_b_first+1, ...
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    if (oy >= 1 && 2 * oy + 2 < MH && ox >= 1 && 2 * ox + 2 < MW) {
-      // interior: the 4x4 max-pooled window needs a 5x5 window of inputs; load each once, slide row by row
-      const size_t base = (((size_t)b * H + 2 * oy - 1) * W + 2 * ox - 1) * C + c8 * 8;
-      float prev[5][8], cur[5][8];
+    for (int a = 0; a < 4; ++a) {
+      const int my = mbp_reflect(2 * oy + a - 1, MH);
+      float hb[8];
 #pragma unroll
-      for (int q = 0; q < 5; ++q) load8(ih, il, base + (size_t)q * C, prev[q]);
+      for (int e = 0; e < 8; ++e) hb[e] = 0.f;
+      for (int q = 0; q < 4; ++q) {
+        const int mx = mbp_reflect(2 * ox + q - 1, MW);
+        float m[8], t[8];
+        const size_t base = ((size_t)b * H + my) * W + mx;
+        load8(ih, il, base * C + c8 * 8, m);
+        load8(ih, il, (base + 1) * C + c8 * 8, t);
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], t[e]);
+        load8(ih, il, (base + W) * C + c8 * 8, t);
 #pragma unroll
-        for (int q = 0; q < 5; ++q) load8(ih, il, base + ((size_t)(a + 1) * W + q) * C, cur[q]);
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], t[e]);
+        load8(ih, il, (base + W + 1) * C + c8 * 8, t);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float wgt = f[a] * f[q] * (1.f / 64.f);
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            acc[e] = fmaf(wgt, fmaxf(fmaxf(prev[q][e], prev[q + 1][e]), fmaxf(cur[q][e], cur[q + 1][e])), acc[e]);
-        }
-#pragma unroll
-        for (int q = 0; q < 5; ++q)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) prev[q][e] = cur[q][e];
+        for (int e = 0; e < 8; ++e) hb[e] = fmaf(f[q], fmaxf(m[e], t[e]), hb[e]);
       }
-    } else {
-      for (int a = 0; a < 4; ++a) {
-        int my = 2 * oy + a - 1;  // index into the reflect-padded max-pooled map (pad top 1)
-        my = my < 0 ? -my : (my >= MH ? 2 * (MH - 1) - my : my);
-        for (int q = 0; q < 4; ++q) {
-          int mx = 2 * ox + q - 1;
-          mx = mx < 0 ? -mx : (mx >= MW ? 2 * (MW - 1) - mx : mx);
-          float m[8], t[8];
-          const size_t base = ((size_t)b * H + my) * W + mx;
-          load8(ih, il, base * C + c8 * 8, m);
-          load8(ih, il, (base + 1) * C + c8 * 8, t);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], t[e]);
-          load8(ih, il, (base + W) * C + c8 * 8, t);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], t[e]);
-          load8(ih, il, (base + W + 1) * C + c8 * 8, t);
-          const float wgt = f[a] * f[q] * (1.f / 64.f);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, fmaxf(m[e], t[e]), acc[e]);
-        }
-      }
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(f[a], hb[e], acc[e]);
     }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= (1.f / 64.f);
     store8(oh, ol, (((size_t)b * OH + oy) * OW + ox) * C + c8 * 8, acc);
+  }
+}
+
+// Interior rows [oy_lo, oy_hi): one thread = one output column x 8 channels x MBP_SEG output rows, sliding down the
+// image.  Per input row it loads the 5 (8 at a reflecting column) pixels of its window once, keeps the horizontal
+// pair-maxima of the previous row and the horizontally blurred last four max-pooled rows in registers, and emits an
+// output every second row: 2 x 5 pixel loads per output instead of 25, every reduction in a fixed order.
+#define MBP_SEG 16
+struct MbpRow { float v[4][8]; };
+__device__ __forceinline__ void mbp_load_row(const __nv_bfloat16* ih, const __nv_bfloat16* il, size_t row_base, int C,
+                                             int c8, bool fast, int x0, const int mc[4], MbpRow& hm) {
+  if (fast) {  // columns x0 .. x0+4, neighbours share pixels
+    float px[5][8];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) load8(ih, il, (row_base + x0 + q) * C + c8 * 8, px[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) hm.v[q][e] = fmaxf(px[q][e], px[q + 1][e]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float a[8], t[8];
+      load8(ih, il, (row_base + mc[q]) * C + c8 * 8, a);
+      load8(ih, il, (row_base + mc[q] + 1) * C + c8 * 8, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) hm.v[q][e] = fmaxf(a[e], t[e]);
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+maxblurpool_slide_kernel(const __nv_bfloat16* __restrict__ ih, const __nv_bfloat16* __restrict__ il,
+                         __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, int B, int H, int W, int C,
+                         int OH, int OW, int oy_lo, int oy_hi) {
+  const int cg = C >> 3;
+  const int MW = W - 1;
+  const int nseg = (oy_hi - oy_lo + MBP_SEG - 1) / MBP_SEG;
+  const size_t total = (size_t)B * nseg * OW * cg;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg);
+    size_t r = i / cg;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int seg = (int)(r % nseg);
+    const int b = (int)(r / nseg);
+    const int oy0 = oy_lo + seg * MBP_SEG, oy1 = min(oy0 + MBP_SEG, oy_hi);
+    int mc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) mc[q] = mbp_reflect(2 * ox + q - 1, MW);
+    const bool fast = ox >= 1 && 2 * ox + 2 < MW;
+    const int x0 = 2 * ox - 1;
+    const int m0 = 2 * oy0 - 1;              // first max-pooled row of the segment (>= 1: interior rows only)
+    const int jmax = 2 * (oy1 - oy0) + 1;    // last max-pooled row counter (row m0 + jmax)
+    const size_t img = (size_t)b * H;
+    MbpRow prev, cur;
+    float hb[4][8];
+    mbp_load_row(ih, il, (img + m0) * W, C, c8, fast, x0, mc, prev);
+    // step(S): consume input row m0 + j + 1 -> max-pooled row j -> horizontally blurred row into slot S = j & 3
+#define MBP_STEP(S)                                                                           \
+    {                                                                                         \
+      mbp_load_row(ih, il, (img + m0 + j + 1) * W, C, c8, fast, x0, mc, cur);                 \
+      _Pragma("unroll") for (int e = 0; e < 8; ++e) {                                         \
+        const float t0 = fmaxf(prev.v[0][e], cur.v[0][e]), t1 = fmaxf(prev.v[1][e], cur.v[1][e]); \
+        const float t2 = fmaxf(prev.v[2][e], cur.v[2][e]), t3 = fmaxf(prev.v[3][e], cur.v[3][e]); \
+        hb[S][e] = (t0 + t3) + 3.f * (t1 + t2);                                               \
+      }                                                                                       \
+      prev = cur;                                                                             \
+    }
+#define MBP_EMIT(S0, S1, S2, S3)                                                              \
+    {                                                                                         \
+      float o[8];                                                                             \
+      _Pragma("unroll") for (int e = 0; e < 8; ++e)                                           \
+        o[e] = ((hb[S0][e] + hb[S3][e]) + 3.f * (hb[S1][e] + hb[S2][e])) * (1.f / 64.f);      \
+      const int oy = oy0 + ((j - 3) >> 1);                                                    \
+      store8(oh, ol, (((size_t)b * OH + oy) * OW + ox) * C + c8 * 8, o);                      \
+    }
+    for (int j = 0; j <= jmax;) {  // four max-pooled rows per trip: slots 0..3, outputs after slots 1 (j >= 5) and 3
+      MBP_STEP(0); ++j;
+      if (j > jmax) break;
+      MBP_STEP(1);
+      if (j >= 5) MBP_EMIT(2, 3, 0, 1);
+      ++j;
+      if (j > jmax) break;
+      MBP_STEP(2); ++j;
+      if (j > jmax) break;
+      MBP_STEP(3);
+      MBP_EMIT(0, 1, 2, 3);
+      ++j;
+    }
+#undef MBP_STEP
+#undef MBP_EMIT
   }
 }
 
@@ -419,12 +498,27 @@ extern "C" int b200_maxblurpool(const void* in_hi, const void* in_lo, void* out_
   B200_CHECK_ARG(in_hi && in_lo && out_hi && out_lo && B > 0 && H > 2 && W > 2, "maxblurpool: bad arguments");
   B200_CHECK_ARG(C % 8 == 0, "maxblurpool: C must be a multiple of 8");
   const int OH = (H - 1 + 3 - 4) / 2 + 1, OW = (W - 1 + 3 - 4) / 2 + 1;
-  const size_t total = (size_t)B * OH * OW * (C / 8);
+  const int MH = H - 1;
+  // interior output rows: the 4-row window 2oy-1 .. 2oy+2 of the max-pooled map needs no reflection
+  int oy_hi = OH;
+  while (oy_hi > 1 && 2 * (oy_hi - 1) + 2 >= MH) --oy_hi;
+  const int oy_lo = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16 *ih = (const __nv_bfloat16*)in_hi, *il = (const __nv_bfloat16*)in_lo;
+  __nv_bfloat16 *oh = (__nv_bfloat16*)out_hi, *ol = (__nv_bfloat16*)out_lo;
+  if (oy_hi > oy_lo) {
+    const int nseg = (oy_hi - oy_lo + MBP_SEG - 1) / MBP_SEG;
+    const size_t total = (size_t)B * nseg * OW * (C / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    maxblurpool_slide_kernel<<<blocks, 256, 0, st>>>(ih, il, oh, ol, B, H, W, C, OH, OW, oy_lo, oy_hi);
+  }
+  const int row_b_first = oy_hi > oy_lo ? oy_hi : 1;      // rows [row_b_first, OH) reflect at the bottom edge
+  const int n_rows = 1 + (OH - row_b_first);              // + row 0 (top edge)
+  const size_t total = (size_t)B * n_rows * OW * (C / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  maxblurpool_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo,
-                                                              (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, B, H, W,
-                                                              C, OH, OW);
+  maxblurpool_rows_kernel<<<blocks, 256, 0, st>>>(ih, il, oh, ol, B, H, W, C, OH, OW, 0, row_b_first, n_rows);
   B200_CHECK_LAUNCH("maxblurpool");
   return 0;
 }

@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(FVT_THREADS, 1) fv_tc_kernel(const FvTcParams 
 }
 
 template <int K>
-static int launch_fv_tc(const FvTcParams& prm, int n_sm, cudaStream_t stream) {
+static int launch_fv_tc(const FvTcParams& prm, int n_sm, int max_ctas, cudaStream_t stream) {
   using Cfg = FvCfg<K>;
   const size_t smem = 1024 + Cfg::W_BYTES + sizeof(float) * (128 * 4 + 2 * B200_MAX_VIEWS * B200_CAM_STRIDE + 24) +
                       sizeof(float2) * 2 * 2 * FVT_ROWS + 2 * sizeof(GroupSync) + 16;
@@ -384,7 +384,7 @@ static int launch_fv_tc(const FvTcParams& prm, int n_sm, cudaStream_t stream) {
   const int N = prm.h * prm.w;
   const long long total_tiles = (long long)prm.B * ((N + FVT_ROWS - 1) / FVT_ROWS) * prm.D;
   int grid = n_sm;
-  if (b200_sm_cap() > 0 && grid > b200_sm_cap()) grid = b200_sm_cap();
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if ((long long)grid * 2 > total_tiles) grid = (int)((total_tiles + 1) / 2);
   fv_tc_kernel<K><<<grid, FVT_THREADS, smem, stream>>>(prm);
   B200_CHECK_LAUNCH("fv_mlp_tc");
@@ -394,7 +394,7 @@ static int launch_fv_tc(const FvTcParams& prm, int n_sm, cudaStream_t stream) {
 extern "C" int b200_fv_mlp_tc(const float* cur, const float* src, const float* cams, const float* cur_invK,
                               const float* planes, const float* bias_eff, const void* wimage, const float* b2,
                               const float* w3, const float* b3, float* vol, unsigned char* mask_out, int B, int K,
-                              int C, int h, int w, int D, void* stream) {
+                              int C, int h, int w, int D, int max_ctas, void* stream) {
   B200_CHECK_ARG(C == B200_FEAT_C, "fv_mlp_tc: only %d feature channels supported (got %d)", B200_FEAT_C, C);
   B200_CHECK_ARG(B > 0 && K > 0 && K <= B200_MAX_VIEWS && D > 0 && h > 0 && w > 0,
                  "fv_mlp_tc: bad sizes B=%d K=%d D=%d h=%d w=%d", B, K, D, h, w);
@@ -411,14 +411,14 @@ extern "C" int b200_fv_mlp_tc(const float* cur, const float* src, const float* c
                  B, D, h, w};
   cudaStream_t st = (cudaStream_t)stream;
   switch (K) {
-    case 1: return launch_fv_tc<1>(prm, n_sm, st);
-    case 2: return launch_fv_tc<2>(prm, n_sm, st);
-    case 3: return launch_fv_tc<3>(prm, n_sm, st);
-    case 4: return launch_fv_tc<4>(prm, n_sm, st);
-    case 5: return launch_fv_tc<5>(prm, n_sm, st);
-    case 6: return launch_fv_tc<6>(prm, n_sm, st);
-    case 7: return launch_fv_tc<7>(prm, n_sm, st);
-    default: return launch_fv_tc<8>(prm, n_sm, st);
+    case 1: return launch_fv_tc<1>(prm, n_sm, max_ctas, st);
+    case 2: return launch_fv_tc<2>(prm, n_sm, max_ctas, st);
+    case 3: return launch_fv_tc<3>(prm, n_sm, max_ctas, st);
+    case 4: return launch_fv_tc<4>(prm, n_sm, max_ctas, st);
+    case 5: return launch_fv_tc<5>(prm, n_sm, max_ctas, st);
+    case 6: return launch_fv_tc<6>(prm, n_sm, max_ctas, st);
+    case 7: return launch_fv_tc<7>(prm, n_sm, max_ctas, st);
+    default: return launch_fv_tc<8>(prm, n_sm, max_ctas, st);
   }
 }
 

@@ -243,7 +243,7 @@ static const size_t ST_SMEM = 1024 + 49152 + 65536 + sizeof(float) * (2 * 3 * ST
 // img fp32 NCHW [n,3,H,W]; wimage: 48 KB from the packer (3 chunks x [hi 64x64 | lo 64x64] bf16, SW128,
 // k = (c*7 + dy)*8 + dx, BatchNorm folded); bias [64]; out NHWC split [n, OH, OW, 64], OH = (H-1)/2+1.
 extern "C" int b200_stem_conv7_tc(const float* img, const void* wimage, const float* bias, void* out_hi, void* out_lo,
-                                  int n_img, int H, int W, void* stream) {
+                                  int n_img, int H, int W, int max_ctas, void* stream) {
   B200_CHECK_ARG(img && wimage && bias && out_hi && out_lo && n_img > 0 && H > 0 && W > 0, "stem_conv7_tc: bad arguments");
   B200_CHECK_ARG((((uintptr_t)wimage | (uintptr_t)out_hi | (uintptr_t)out_lo) & 15) == 0,
                  "stem_conv7_tc: buffers must be 16-byte aligned");
@@ -283,7 +283,7 @@ extern "C" int b200_stem_conv7_tc(const float* img, const void* wimage, const fl
   }
   const long long total_tiles = (long long)n_img * p.tiles_x * p.tiles_y;
   int grid = n_sm;
-  if (b200_sm_cap() > 0 && grid > b200_sm_cap()) grid = b200_sm_cap();
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if ((long long)grid * 2 > total_tiles) grid = (int)((total_tiles + 1) / 2);
   stem_tc_kernel<<<grid, ST_THREADS, ST_SMEM, (cudaStream_t)stream>>>(p);
   B200_CHECK_LAUNCH("stem_conv7_tc");

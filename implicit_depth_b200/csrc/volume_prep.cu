@@ -12,14 +12,13 @@ void b200_set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-extern "C" int b200_abi_version(void) { return 1; }
-
-static int g_sm_cap = 0;
-extern "C" int b200_sm_cap(void) { return g_sm_cap; }
-extern "C" int b200_set_sm_cap(int n) {
-  g_sm_cap = n < 0 ? 0 : n;
-  return 0;
-}
+extern "C" int b200_abi_version(void) { return 2; }
+// sha256 of the sources this library was built from (passed by build.py as -DB200_SRC_DIGEST): `_abi.load()` compares
+// it with the digest of the csrc/ it sits next to, so a stale binary is never loaded against newer ctypes signatures
+#ifndef B200_SRC_DIGEST
+#define B200_SRC_DIGEST "unknown"
+#endif
+extern "C" const char* b200_source_digest(void) { return B200_SRC_DIGEST; }
 
 // ---------------------------------------------------------------------------------------
 // One thread per (b, k): P = (K @ T)[:3], M = P3 @ invK3, t, pose distances.
@@ -35,7 +34,7 @@ __global__ void volume_prepare_kernel(const float* __restrict__ src_Ks, const fl
                                       const float* __restrict__ planes_in, const float* __restrict__ W1,
                                       const float* __restrict__ b1, float* __restrict__ cams,
                                       float* __restrict__ planes, float* __restrict__ bias_eff, int B, int K, int D,
-                                      int C) {
+                                      int C, int range_stride) {
   int tid = blockIdx.x * blockDim.x + threadIdx.x;
   int nthreads = gridDim.x * blockDim.x;
   for (int i = tid; i < B * K; i += nthreads) {
@@ -72,11 +71,12 @@ __global__ void volume_prepare_kernel(const float* __restrict__ src_Ks, const fl
     for (int j = 27; j < B200_CAM_STRIDE; ++j) cam[j] = 0.f;
   }
   for (int i = tid; i < B * D; i += nthreads) {
-    int d = i % D;
+    int d = i % D, b = i / D;
     if (planes_in) {
       planes[i] = planes_in[i];
     } else {
-      float zmin = min_depth[0], zmax = max_depth[0];
+      // the reference broadcasts its min/max tensors over the batch (cost_volume.py:117-126): one range, or one per frame
+      float zmin = min_depth[b * range_stride], zmax = max_depth[b * range_stride];
       float ramp = (D > 1) ? (float)d / (float)(D - 1) : 0.f;
       planes[i] = expf(logf(zmin) + logf(zmax / zmin) * ramp);
     }
@@ -109,7 +109,8 @@ __global__ void volume_prepare_kernel(const float* __restrict__ src_Ks, const fl
 extern "C" int b200_volume_prepare(const float* src_Ks, const float* src_extrinsics, const float* src_poses,
                                    const float* cur_invK, const float* min_depth, const float* max_depth,
                                    const float* planes_in, const float* W1, const float* b1, float* cams,
-                                   float* planes, float* bias_eff, int B, int K, int D, int C, void* stream) {
+                                   float* planes, float* bias_eff, int B, int K, int D, int C, int range_per_frame,
+                                   void* stream) {
   B200_CHECK_ARG(B > 0 && K > 0 && K <= B200_MAX_VIEWS && D > 0, "volume_prepare: bad sizes B=%d K=%d D=%d", B, K, D);
   B200_CHECK_ARG(C == B200_FEAT_C, "volume_prepare: only %d feature channels supported (got %d)", B200_FEAT_C, C);
   B200_CHECK_ARG(src_Ks && src_extrinsics && src_poses && cur_invK && cams && planes, "volume_prepare: null pointer");
@@ -117,7 +118,7 @@ extern "C" int b200_volume_prepare(const float* src_Ks, const float* src_extrins
   B200_CHECK_ARG(!W1 || (b1 && bias_eff), "volume_prepare: W1 given without b1/bias_eff");
   volume_prepare_kernel<<<4, 256, 0, (cudaStream_t)stream>>>(src_Ks, src_extrinsics, src_poses, cur_invK, min_depth,
                                                             max_depth, planes_in, W1, b1, cams, planes, bias_eff, B,
-                                                            K, D, C);
+                                                            K, D, C, range_per_frame ? 1 : 0);
   B200_CHECK_LAUNCH("volume_prepare");
   return 0;
 }

@@ -56,6 +56,7 @@ class B200DepthModel(B200BDModel):
         ms = self.run_opts.matching_scale
         cur_image = cur_data["image_b3hw"]
         _abi.require_cuda(cur_image)
+        self._sync_weights()
         f = lambda t: t if t.dtype == torch.float32 else t.float()
         B = cur_image.shape[0]
         no_planes = torch.empty((B, 0, 1, 1), device=cur_image.device, dtype=torch.float32)

@@ -13,12 +13,13 @@ consumers' weights are padded with zero columns (`SplitAct.Cl` = logical channel
 """
 from __future__ import annotations
 
-import os
 
 import torch
 
 from . import _abi
 from .networks import Plan, _fold_bn
+
+FUSED_DW_SE = True  # False = separate depthwise / pool / fc kernels (kept for the kernel-level tests)
 
 
 def pad_ch(c):
@@ -153,7 +154,7 @@ def plan_efficientnet_v2_s(g: Plan, features, get_image, B, H, W, taps=(1, 2, 3,
                 layers = blk.block
                 stride = layers[1][0].stride[0]
                 h = _cna(g, inp, layers[0], "silu", 1)
-                if os.environ.get("B200_MBCONV_FUSED", "1") != "0":  # dev knob: "0" = separate pool / fc kernels
+                if FUSED_DW_SE:
                     h = _dwconv_se(g, h, layers[1], stride, layers[2])
                 else:
                     h = _dwconv(g, h, layers[1], stride)

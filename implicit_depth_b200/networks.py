@@ -32,15 +32,17 @@ LRELU = 0.2  # nn.LeakyReLU(0.2) of BasicBlock (layers.py:60) and the matching h
 class Plan:
     """Preallocated buffers + an ordered list of kernel launches (CUDA-graph capturable)."""
 
-    def __init__(self, device):
+    DAG = True       # False = strictly sequential launches on the caller's stream (the bit-identity tests compare both)
+    N_STREAMS = 3    # extra streams of the dependency scheduler
+
+    def __init__(self, device, max_ctas=0):
         self.device = torch.device(device)
         self.ops = []  # (fn, reads | None, writes | None)
         self.n_launches = 0
         self._keep = []
-        import os
-
-        self.dag = os.environ.get("B200_PLAN_DAG", "1") != "0"  # dev knob: 0 = strictly sequential launches
-        self.n_streams = int(os.environ.get("B200_PLAN_STREAMS", "3"))
+        self.dag = Plan.DAG
+        self.n_streams = Plan.N_STREAMS
+        self.max_ctas = int(max_ctas)  # CTA cap of this plan's persistent kernels (0 = all SMs)
         self._pool = None
         self.external = {}  # id(buffer produced outside this plan, possibly on another stream) -> event to wait on
 
@@ -166,7 +168,7 @@ class Plan:
             out_f32 = self.empty((B, OH, OW, cout))
         b = None if bias is None else bias.detach().to(self.device, torch.float32).contiguous()
         plan = ConvPlan([(a, w.shape[-1], s, p) for a, w, s, p in segs], [w for _, w, _, _ in segs], b, out, B, cout, act=act,
-                        slope=slope, residual=residual, out_f32=out_f32)
+                        slope=slope, residual=residual, out_f32=out_f32, max_ctas=self.max_ctas)
         self.add(plan.run, reads=[a for a, _, _, _ in segs] + [residual], writes=[out, out_f32])
         return out, out_f32
 
@@ -642,7 +644,7 @@ class ResnetMatchingEncoder(_PlannedModule):
             img = get_images()
             assert tuple(img.shape) == (n, 3, H, W) and img.is_contiguous() and img.dtype == torch.float32
             _abi.call("b200_stem_conv7_tc", _abi.ptr(img), _abi.ptr(wimage), _abi.ptr(b7), _abi.ptr(s1.hi),
-                      _abi.ptr(s1.lo), n, H, W, _abi.stream_ptr())
+                      _abi.ptr(s1.lo), n, H, W, g.max_ctas, _abi.stream_ptr())
 
         g.add(stem)
         H4, W4 = (H2 - 2) // 2 + 1, (W2 - 2) // 2 + 1

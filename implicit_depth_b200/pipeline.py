@@ -17,7 +17,7 @@ from .staging import FrameStaging, StagedDict, StagedFrame
 
 
 class FramePipeline:
-    def __init__(self, model, device, gather=None, encoder_ahead=False, **forward_kwargs):
+    def __init__(self, model, device, gather=None, encoder_ahead=False, encoder_priority=0, **forward_kwargs):
         """model: B200BDModel (or anything with the reference's forward signature); gather: optional
         `parallel.GatherPlan` (packed outputs, one collective per step, root-only download), or a plain callable
         applied to the output dict on the compute stream (e.g. `parallel.gather_outputs`).
@@ -33,10 +33,7 @@ class FramePipeline:
         self.encoder_ahead = bool(encoder_ahead)
         if self.encoder_ahead:
             model.encoder_ahead = True
-            import os
-
-            self.s_enc = torch.cuda.Stream(device=self.device,
-                                           priority=int(os.environ.get("B200_ENC_PRIORITY", "0")))  # dev knob
+            self.s_enc = torch.cuda.Stream(device=self.device, priority=int(encoder_priority))
         self.ev_enc = [None, None]         # encoder of the batch in slot s has finished (encoder_ahead)
         self.slots = [None, None]          # device input dictionaries
         self.HOST_SLOTS = 3                # a yielded dictionary stays valid while the next batch is being produced

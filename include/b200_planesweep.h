@@ -20,12 +20,11 @@
 extern "C" {
 #endif
 
-/* Upper bound on the CTAs of the persistent kernels planned / launched from now on (0 = all SMs): keeps SMs free for
- * work the caller runs concurrently on another stream. */
-int b200_set_sm_cap(int n);
-int b200_sm_cap(void);
-int b200_abi_version(void);
-const char* b200_last_error(void);
+int b200_abi_version(void);           /* 2: CTA caps are per-call arguments (`max_ctas`), no process-global state */
+const char* b200_last_error(void);    /* message of the last failing call on this thread */
+const char* b200_source_digest(void); /* sha256 of the sources the library was built from (checked by the loader) */
+/* `max_ctas` (b200_conv_desc, b200_fv_mlp_tc, b200_stem_conv7_tc): upper bound on the CTAs of that persistent launch,
+ * 0 = all SMs -- keeps SMs free for work the caller runs concurrently on another stream. */
 
 /* Per-batch set-up, replaces the tensor algebra at the top of every manager's
  * build_cost_volume: P = (K_src @ T_src<-cur)[:3] (utils/geometry_utils.py:82-84) folded with
@@ -34,13 +33,14 @@ const char* b200_last_error(void);
  * (modules/cost_volume.py:98-132) and, when W1/b1 are given, the part of the first MLP layer
  * that is constant over (pixel, plane): mask (==1) and pose channels (:684, :690-692).
  *   src_Ks, src_extrinsics, src_poses [B,K,4,4]; cur_invK [B,4,4];
- *   min_depth, max_depth: device scalars (used when planes_in == NULL); planes_in [B,D] or NULL;
+ *   min_depth, max_depth: device scalars, or [B] values when range_per_frame != 0 (the reference broadcasts its
+ *   [1,1,1,1] or [B,1,1,1] tensors, modules/cost_volume.py:117-126); used when planes_in == NULL; planes_in [B,D] or NULL;
  *   W1 [128, 26K+20] and b1 [128] in the reference's channel order, or NULL;
  *   out: cams [B,K,32], planes [B,D], bias_eff [B,128] (only with W1). */
 int b200_volume_prepare(const float* src_Ks, const float* src_extrinsics, const float* src_poses,
                         const float* cur_invK, const float* min_depth, const float* max_depth,
                         const float* planes_in, const float* W1, const float* b1, float* cams, float* planes,
-                        float* bias_eff, int B, int K, int D, int C, void* stream);
+                        float* bias_eff, int B, int K, int D, int C, int range_per_frame, void* stream);
 
 /* [n_img, C=16, HW] planes (image stride / channel stride in elements) -> pixel-major, layout 0 | 1 (see top). */
 int b200_feats_to_pixel_major(const float* in, float* out, int n_img, int C, int HW, long long img_stride,
@@ -81,7 +81,7 @@ int b200_fv_mlp_simt(const float* cur, const float* src, const float* cams, cons
 int b200_fv_mlp_tc(const float* cur, const float* src, const float* cams, const float* cur_invK,
                    const float* planes, const float* bias_eff, const void* wimage, const float* b2,
                    const float* w3, const float* b3, float* vol, unsigned char* mask_out, int B, int K, int C,
-                   int h, int w, int D, void* stream);
+                   int h, int w, int D, int max_ctas, void* stream);
 int b200_fv_tc_wimage_bytes(int K);
 /* K-dimension layout of that image: out[0] = views built by role A (the rest by role B), out[1] / out[2] =
  * 32-channel halves of role A / B, out[3] = 64-channel chunks; returns the image size in bytes
@@ -114,13 +114,15 @@ typedef struct {
   float* out_f32;       /* optional NHWC fp32 copy of the output */
   int B, OH, OW, Cout /* %16==0; >128 => %128==0 */, act /*0 none,1 leaky(slope),2 ELU,3 ReLU*/;
   float slope;
+  int max_ctas;         /* CTA cap of this persistent launch, 0 = all SMs */
 } b200_conv_desc;
 int b200_conv_ntile(int Cout);
 /* N tile of this particular conv (64 instead of 128 for ring-kernel convs with few M tiles); the weight image must be
  * packed for it. */
 int b200_conv_ntile_for(const b200_conv_desc* d);
-/* which kernel (and weight-image layout) a conv gets: 1 = halo-patch kernel (all segments stride 1, Cout % 64 == 0,
- * no fp32 copy), 0 = per-tap kernel.  Depends only on the geometry fields of the descriptor. */
+/* which kernel (and weight-image layout) a conv gets: 1 = halo-patch kernel (all segments stride 1, no fp32 copy,
+ * Cout % 64 == 0 -- or Cout == 16 with 3x3 segments and no residual: the replicate-pad head of the matching encoder,
+ * modules/networks.py:279-282), 0 = per-tap kernel.  Depends only on the geometry fields of the descriptor. */
 int b200_conv_uses_halo(const b200_conv_desc* desc);
 long long b200_conv_wimage_bytes(const int* seg_C, const int* seg_ksize, int nseg, int Cout, int halo);
 int b200_conv_create(const b200_conv_desc* desc, void** plan_out);
@@ -188,7 +190,7 @@ int b200_stem_conv7(const float* img, const float* wt, const float* bias, void* 
  * tensor memory.  wimage: 48 KB = 3 K-chunks x [W_hi 64x64 | W_lo 64x64] bf16 in the 128-byte-swizzled K-major
  * layout (BatchNorm folded, k >= 168 and dx == 7 zero). */
 int b200_stem_conv7_tc(const float* img, const void* wimage, const float* bias, void* out_hi, void* out_lo,
-                       int n_img, int H, int W, void* stream);
+                       int n_img, int H, int W, int max_ctas, void* stream);
 /* MaxPool2d(2, stride 1) + BlurPool(4x4 binomial, stride 2, reflect pad) of antialiased-cnns 0.3
  * (call site modules/networks.py:267); [B,H,W,C] -> [B,H/2,W/2,C]. */
 int b200_maxblurpool(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int B, int H, int W, int C,
@@ -232,11 +234,6 @@ int b200_relative_poses(const float* src_cam_T_world, const float* src_world_T_c
  * 2^i, invK_s[i] = inverse(K_s[i]) (fp64 adjugate rounded to fp32; the reference inverts with fp32 LAPACK).
  *   K_s0 [n,4,4]; out: K_s, invK_s [levels,n,4,4]. */
 int b200_intrinsics_pyramid(const float* K_s0, float* K_s, float* invK_s, int n, int levels, void* stream);
-
-/* Self-test of the tcgen05/TMEM building blocks: D[128,N] = A[128,K] * Bm[N,K]^T on one CTA.
- *   mode 0: bf16 operands from shared memory; 1: A from tensor memory; 2/3: split-bf16 (fp32-grade)
- *   with A from tensor / shared memory.  K in {64,128,192}, N multiple of 16 up to 128. */
-int b200_umma_probe(const float* A, const float* Bm, float* D, int K, int N, int mode, void* stream);
 
 #ifdef __cplusplus
 }

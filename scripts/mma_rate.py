@@ -3,8 +3,7 @@ import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from implicit_depth_b200 import _abi
-lib = _abi.load()
-lib.b200_mma_rate.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+lib = _abi.load_dev()
 names = {0: "SS split (hi/lo pattern)", 1: "TS split (A in TMEM)", 2: "SS plain, 3 A chunks", 3: "SS same slice",
          4: "SS split, 2 accumulators", 5: "TS split, 2 accumulators", 8: "SW64 halo: merged N + lo N/2 (avg)",
          16: "SW128 merged N + lo N/2 (avg)"}

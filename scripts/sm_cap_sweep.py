@@ -1,6 +1,6 @@
 """SM split between the image-prior encoder (side stream) and the matching encoder / plane sweep (dev tool).
-Sweeps the CTA caps of the two front-end stages and the priority of the encoder stream; cfg2, CUDA-graph replay,
-L2 flushed, staged inputs.  One JSON line per setting."""
+Sweeps the CTA cap of the front-end stages (`B200BDModel.FRONT_SM_FRACTION`); cfg2, CUDA-graph replay, L2 flushed,
+staged inputs.  One JSON line per setting."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -36,18 +36,13 @@ def timeit(n=15):
     ts.sort(); return ts[len(ts) // 2]
 
 
-# (matching-encoder cap, plane-sweep cap, encoder stream priority, plane-sweep split "frames:cap,...")
-SETTINGS = [(74, 74, 0, ""), (74, 100, 0, ""), (74, 124, 0, ""), (74, 148, 0, ""), (74, 74, -1, ""),
-            (74, 148, -1, ""), (74, 74, 0, "2:74,2:148"), (74, 74, 0, "1:74,3:148"), (74, 74, 0, "3:74,1:148"),
-            (74, 74, 0, "2:74,1:110,1:148"), (74, 74, -1, "2:74,2:148"), (60, 60, 0, "2:60,2:148"), (74, 74, 0, "")]
-if len(sys.argv) > 1:
-    SETTINGS = [tuple(a.split(";")) for a in sys.argv[1:]]
-    SETTINGS = [(int(a), int(b), int(c), d) for a, b, c, d in SETTINGS]
-for front, fv, prio, split in SETTINGS:
-    os.environ["B200_FRONT_SM_CAP"], os.environ["B200_FV_SM_CAP"] = str(front), str(fv)
-    os.environ["B200_ENC_PRIORITY"], os.environ["B200_FV_SPLIT"] = str(prio), split
-    m._state, m._graphs, m._side = {}, {}, None  # plans bake the caps, the side stream its priority
+# front-end CTA cap (matching encoder + plane sweep while the image encoder runs beside them; 0 = no cap)
+CAPS = [int(a) for a in sys.argv[1:]] or [0, 64, 74, 80, 86, 96, 110, 124]
+n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+for cap in CAPS:
+    m.FRONT_SM_FRACTION = cap / n_sm
+    m._state, m._graphs = {}, {}  # the plans bake the cap
     torch.cuda.synchronize()
     ms = timeit()
-    print(json.dumps({"front_cap": front, "fv_cap": fv, "enc_priority": prio, "fv_split": split, "ms_per_forward": round(ms, 3),
-                      "frames_per_s": round(1000.0 * B / ms, 1)}), flush=True)
+    print(json.dumps({"front_cap": cap, "ms_per_forward": round(ms, 3), "frames_per_s": round(1000.0 * B / ms, 1)}),
+          flush=True)

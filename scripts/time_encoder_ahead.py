@@ -25,18 +25,15 @@ if len(sys.argv) > 1:
     SETTINGS = [tuple(a.split(";")) for a in sys.argv[1:]]
 for ahead_s, prio, cap in SETTINGS:
     ahead = ahead_s == "1"
-    os.environ["B200_ENC_PRIORITY"] = prio
-    if cap == "-":
-        os.environ.pop("B200_FRONT_SM_CAP", None)
-        os.environ.pop("B200_FV_SM_CAP", None)
-    else:
-        os.environ["B200_FRONT_SM_CAP"] = os.environ["B200_FV_SM_CAP"] = cap
     m = B200BDModel(default_options(image_width=W, image_height=H, matching_num_depth_bins=D))
     if not os.environ.get('NO_INIT'):
         synthetic.init_model_weights(m, seed=0)
     m = m.cuda().eval()
     m.use_cuda_graph = True
-    pipe = FramePipeline(m, "cuda", encoder_ahead=ahead, return_mask=True)
+    if cap != "-":  # (in encoder-ahead mode the model applies no cap by default)
+        frac = int(cap) / torch.cuda.get_device_properties(0).multi_processor_count
+        m._front_sm_cap = lambda frac=frac: round(frac * torch.cuda.get_device_properties(0).multi_processor_count)
+    pipe = FramePipeline(m, "cuda", encoder_ahead=ahead, encoder_priority=int(prio), return_mask=True)
     feed = lambda n: (hosts[i % len(hosts)] for i in range(n))
     for _ in pipe.run(feed(6)):
         pass

@@ -34,5 +34,5 @@ torch.cuda.current_stream().wait_stream(s)
 cg = torch.cuda.CUDAGraph()
 with torch.cuda.graph(cg):
     g.run()
-print(json.dumps({"fused_mbconv": os.environ.get("B200_MBCONV_FUSED", "1"), "launches": g.n_launches,
+print(json.dumps({"launches": g.n_launches,
                   "eager_ms": round(eager, 3), "graph_ms": round(timeit(cg.replay), 3)}))

@@ -34,9 +34,40 @@ def test_library_exports_every_declared_symbol(lib):
 def test_python_binding_covers_header(lib):
     from implicit_depth_b200 import _abi
 
-    bound = set(_abi.SIGNATURES) | {"b200_last_error", "b200_abi_version"}
+    bound = set(_abi.SIGNATURES) | {"b200_last_error", "b200_abi_version", "b200_source_digest"}
     assert set(declared_symbols()) <= bound
-    assert lib.b200_abi_version() == 1
+    assert lib.b200_abi_version() == 2
+
+
+def test_library_carries_the_digest_of_its_sources(lib, tmp_path, monkeypatch):
+    """A library built from other sources than the csrc/ next to it is refused (no stale binary behind new ctypes
+    signatures), and the product library holds no process-global tuning state or dev probes."""
+    from implicit_depth_b200 import _abi, build
+
+    lib.b200_source_digest.restype = ctypes.c_char_p
+    assert lib.b200_source_digest().decode() == build.source_digest() == build.library_digest()
+    monkeypatch.setattr(build, "source_digest", lambda sub="": "0" * 64)
+    with pytest.raises(_abi.B200Error, match="different sources"):
+        _abi._check_digest(lib)
+    for gone in ("b200_set_sm_cap", "b200_sm_cap", "b200_umma_probe", "b200_mma_rate", "b200_conv_set_prof"):
+        assert not hasattr(lib, gone), gone
+    srcs = "".join(open(f).read() for f in build.sources())
+    assert "getenv" not in srcs
+
+
+def test_to_b200_and_packed_outputs_need_no_gpu():
+    """`to_b200` on anything with the reference managers' attributes (the real reference classes are exercised in
+    tests/test_reference_seam_cpu.py)."""
+    from types import SimpleNamespace
+
+    from implicit_depth_b200 import B200CostVolumeManager, B200FeatureVolumeManager, to_b200
+    from implicit_depth_b200.cost_volume import MLP
+
+    dot = to_b200(SimpleNamespace(matching_height=6, matching_width=8, num_depth_bins=4, buffers=lambda: iter(())))
+    assert type(dot) is B200CostVolumeManager
+    mlp = MLP([26 * 3 + 20, 128, 128, 1], disable_final_activation=True)
+    fv = to_b200(SimpleNamespace(matching_height=6, matching_width=8, num_depth_bins=4, mlp=mlp, buffers=lambda: iter(())))
+    assert type(fv) is B200FeatureVolumeManager and fv.num_source_views == 3 and fv.mlp is mlp
 
 
 def test_bad_arguments_return_error_codes(lib):

@@ -30,6 +30,8 @@ CASES = [
     (1, 24, 32, [160, 256], 256, 3, 1, "lrelu", False),  # two N tiles
     (1, 8, 16, [128], 16, 3, 1, "none", False),       # narrow N (matching head)
     (3, 6, 8, [384, 256], 384, 3, 1, "relu", False),  # coarsest level, three N tiles
+    (2, 37, 45, [128], 16, 3, 1, "lrelu", False),     # narrow N, ragged size, several items per CTA
+    (5, 96, 128, [128], 16, 3, 1, "none", False),     # narrow N, M=256 double tiles on a full grid
 ]
 
 
@@ -54,7 +56,8 @@ def test_conv_matches_fp64(case, with_f32):
         res = SplitAct.from_nchw_torch(rx)
     plan = ConvPlan([(a, k, stride, pad) for a in acts], ws, bias, out, B, Cout, act=act, slope=0.2,
                     residual=res, out_f32=out_f32)
-    assert plan.halo == (not with_f32 and stride == 1 and Cout % 64 == 0 and k == 3)  # pure 1x1 convs: plain kernel
+    # pure 1x1 convs and fp32 copies: per-tap kernel; Cout == 16 without residual: the 16-wide halo variant
+    assert plan.halo == (not with_f32 and stride == 1 and k == 3 and (Cout % 64 == 0 or (Cout == 16 and not use_res)))
     plan.run()
     plan.run()  # a second launch must give the same answer (persistent state fully re-initialised)
     torch.cuda.synchronize()
@@ -142,3 +145,29 @@ def test_stem_conv7_tensor_core_matches_fp64(shape):
     ref = F.relu(ref)
     assert got.shape == ref.shape
     assert (got - ref).abs().max().item() < 3e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("shape", [(2, 48, 64, 64), (1, 31, 45, 16), (3, 20, 18, 64), (1, 192, 256, 64), (1, 5, 7, 8)])
+def test_maxblurpool_matches_torch(shape):
+    """MaxPool2d(2, stride 1) + BlurPool(filt 4, stride 2, reflect pad (1,2,1,2)) of antialiased-cnns 0.3 (call site
+    modules/networks.py:267): sliding interior kernel + direct border rows against torch ops in fp64."""
+    from implicit_depth_b200 import _abi
+
+    B, H, W, C = shape
+    torch.manual_seed(H * W + C)
+    x = torch.randn(B, C, H, W, device="cuda")
+    a = SplitAct.from_nchw_torch(x)
+    xd = a.float_nchw().double()
+    m = F.max_pool2d(xd, 2, 1)
+    f = torch.tensor([1.0, 3.0, 3.0, 1.0], dtype=torch.float64, device="cuda")
+    filt = (f[:, None] * f[None, :] / 64.0)[None, None].repeat(C, 1, 1, 1)
+    ref = F.conv2d(F.pad(m, [1, 2, 1, 2], mode="reflect"), filt, stride=2, groups=C)
+    OH, OW = ref.shape[-2:]
+    out = SplitAct(B, OH, OW, C, "cuda")
+    out.hi.fill_(float("nan")); out.lo.fill_(float("nan"))
+    _abi.call("b200_maxblurpool", _abi.ptr(a.hi), _abi.ptr(a.lo), _abi.ptr(out.hi), _abi.ptr(out.lo), B, H, W, C,
+              _abi.stream_ptr())
+    torch.cuda.synchronize()
+    got = out.float_nchw().double()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() < 2e-5 * ref.abs().max().item()

@@ -424,10 +424,12 @@ def test_scheduled_plan_is_bit_identical_to_sequential_launches(monkeypatch):
     c = {k: torch.from_numpy(v).cuda() for k, v in cur.items()}
     s = {k: torch.from_numpy(v).cuda() for k, v in src.items()}
 
+    from implicit_depth_b200.networks import Plan
+
     def run(dag, overlap, graph, n):
-        monkeypatch.setenv("B200_PLAN_DAG", dag)
-        monkeypatch.setenv("B200_ENC_OVERLAP", overlap)
+        monkeypatch.setattr(Plan, "DAG", dag == "1")
         m, _, _ = seeded(image_width=256, image_height=192, matching_num_depth_bins=16)
+        m.overlap_image_encoder = overlap == "1"
         m.use_cuda_graph = graph
         outs = [m("test", c, s, return_mask=True) for _ in range(n)]
         torch.cuda.synchronize()
@@ -456,3 +458,24 @@ def test_sigmoid_upsample_matches_torch(mode):
             assert got.shape == ref.shape and (got - ref).abs().max().item() < 2e-6
         ref = F.interpolate(x, size=(H, W), mode=mode)
         assert (postprocess.resize(x, (H, W), mode=mode) - ref).abs().max().item() < 2e-6
+
+
+def test_in_place_weight_updates_rebuild_plans_and_graphs():
+    """Plans and captured graphs hold packed copies of the weights: any in-place parameter change (sub-module
+    load_state_dict, re-initialisation) must be picked up by the next forward, eager or graphed."""
+    cur, src = synthetic.make_frame_batch(4200, 1, 7, 192, 256)
+    c = {k: torch.from_numpy(v).cuda() for k, v in cur.items()}
+    s = {k: torch.from_numpy(v).cuda() for k, v in src.items()}
+    for graph in (False, True):
+        m, _, _ = seeded(image_width=256, image_height=192, matching_num_depth_bins=16)
+        m.use_cuda_graph = graph
+        a = m("test", c, s, return_mask=True)["pred_0"].clone()
+        other = B200BDModel(m.run_opts)
+        synthetic.init_model_weights(other, seed=1)
+        m.binary_mlp.load_state_dict(other.binary_mlp.state_dict())  # sub-module load: no top-level hook sees it
+        b = m("test", c, s, return_mask=True)["pred_0"].clone()
+        assert not torch.equal(a, b)
+        fresh = B200BDModel(m.run_opts)
+        fresh.load_state_dict(m.state_dict())
+        want = fresh.cuda().eval()("test", c, s, return_mask=True)["pred_0"]
+        assert torch.equal(b, want)

@@ -1,4 +1,4 @@
-"""tcgen05 / TMEM building-block self-test (see csrc/umma_probe.cu)."""
+"""tcgen05 / TMEM building-block self-test (csrc/dev/umma_probe.cu, in the dev-probe library libb200probe.so)."""
 import pytest
 import torch
 
@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 def run_probe(A, Bm, mode):
     D = torch.full((128, Bm.shape[0]), float("nan"), device="cuda")
-    _abi.call("b200_umma_probe", _abi.ptr(A), _abi.ptr(Bm), _abi.ptr(D), A.shape[1], Bm.shape[0], mode,
+    _abi.call_dev("b200_umma_probe", _abi.ptr(A), _abi.ptr(Bm), _abi.ptr(D), A.shape[1], Bm.shape[0], mode,
               _abi.stream_ptr())
     torch.cuda.synchronize()
     return D

@@ -236,3 +236,23 @@ def test_plane_count_sweep_vs_oracle(D):
                                              inp["src_poses"], inp["src_Ks"], inp["cur_invK"], planes, W)
     assert rel_err(vol.cpu().numpy(), rvol) < TOL
     np.testing.assert_array_equal(planes_to_idx(flow.cpu().numpy(), planes), np.argmax(vol.cpu().numpy(), 1))
+
+
+def test_per_frame_depth_range_like_the_reference_broadcast():
+    """min_depth / max_depth may be [B,1,1,1] tensors (the reference broadcasts them, cost_volume.py:117-126): every
+    frame gets its own planes; a wrong element count is an argument error, not a silent first-frame range."""
+    B, K, C, h, w, D = 3, 2, 16, 12, 20, 8
+    t = dev(synthetic.make_volume_inputs(91, B, K, C, h, w))
+    mn = torch.tensor([0.25, 0.5, 1.0], device="cuda").view(B, 1, 1, 1)
+    mx = torch.tensor([5.0, 4.0, 8.0], device="cuda").view(B, 1, 1, 1)
+    mgr = B200CostVolumeManager(h, w, num_depth_bins=D).cuda()
+    cost, lowest, planes_bdhw, _ = mgr(min_depth=mn, max_depth=mx, **t)
+    for b in range(B):
+        one = {k: v[b:b + 1].contiguous() for k, v in t.items()}
+        c1, l1, p1, _ = mgr(min_depth=mn[b:b + 1], max_depth=mx[b:b + 1], **one)
+        assert torch.equal(cost[b:b + 1], c1) and torch.equal(lowest[b:b + 1], l1)
+        assert torch.equal(planes_bdhw[b, :, 0, 0], p1[0, :, 0, 0])
+        np.testing.assert_allclose(p1[0, :, 0, 0].cpu().numpy(),
+                                   O.generate_depth_planes(float(mn[b]), float(mx[b]), D), rtol=1e-6)
+    with pytest.raises(ValueError):
+        mgr(min_depth=mn[:2], max_depth=mx[:2], **t)
