@@ -53,8 +53,8 @@ SIGNATURES = {
     "b200_intrinsics_pyramid": [c_f, c_f, c_f, c_i, c_i, ctypes.c_void_p],
     "b200_binary_mlp_create": [ctypes.c_void_p, ctypes.c_void_p],
     "b200_binary_mlp_planes": [ctypes.c_void_p, c_f, c_i, c_f, c_f, ctypes.c_void_p],
-    "b200_binary_mlp_search": [ctypes.c_void_p, c_f, c_i, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_f, c_f,
-                               ctypes.c_void_p],
+    "b200_binary_mlp_search": [ctypes.c_void_p, c_f, c_i, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_f, c_f, c_i,
+                               c_f, c_f, ctypes.c_void_p],
     "b200_binary_mlp_destroy": [ctypes.c_void_p],
 }
 # dev-probe library (csrc/dev/, `build.build_dev()`): tcgen05 self-test + MMA issue-rate probe

@@ -127,6 +127,8 @@ class B200BDModel(nn.Module):
             # temporal checkpoints load strictly; `sample_prior` computes the same grid in-kernel for any size
             self.backprojector = _PixGrid(192, 256)
             self.projector = _Eps()
+        # `model.thresholder = Thresholder(planes, thresholds)` (test_bd.py:91-102): anything with `.bins` and
+        # `.thresholds` vectors; None = the fixed 0.5 of bd_model.py:284-285
         self.thresholder = None
         # training-only buffer of the reference (bd_model.py:100-101), kept so its checkpoints load strictly
         self.bce_loss = nn.Module()
@@ -134,6 +136,7 @@ class B200BDModel(nn.Module):
         self._state = {}
         self._graphs = {}
         self._versioned = None
+        self._thr = None
         self.use_cuda_graph = False
         # the image encoder is independent of the matching encoder + plane sweep until the cost-volume encoder:
         # run it on a side stream so its many small launches overlap the matching encoder and the plane sweep
@@ -156,10 +159,11 @@ class B200BDModel(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._state, self._graphs, self._enc_fast, self._side, self._versioned = {}, {}, None, None, None
+        self._thr = None
         self._enc_graphs, self._enc_pending = {}, None
         return super()._apply(fn, *a, **k)
 
-    FRONT_SM_FRACTION = 0.54  # see _front_sm_cap
+    FRONT_SM_FRACTION = 0.61  # see _front_sm_cap
 
     def _front_sm_cap(self):
         """CTA cap for the persistent kernels of the matching encoder and the plane sweep while the image encoder
@@ -168,8 +172,8 @@ class B200BDModel(nn.Module):
             return 0
         if self.encoder_ahead:  # the encoder is not inside this forward
             return 0
-        # a little over half the machine: measured optimum on B200 (profiles/r01f_sm_cap_sweep.md, ms per step at cfg2:
-        # cap 64 -> 9.69, 74 -> 9.10, 78 -> 8.96, 80 -> 8.92, 82 -> 9.08, 86 -> 9.07, 100 -> 9.23+)
+        # a little over half the machine: measured optimum on B200 (scripts/sm_cap_sweep.py, ms per step at cfg2, round 2
+        # kernels: no cap -> 8.98, 70 -> 8.96, 80 -> 8.77, 90 -> 8.73, 100 -> 8.74; round 1: profiles/r01f_sm_cap_sweep.md)
         return round(self.FRONT_SM_FRACTION *
                      torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count)
 
@@ -266,7 +270,8 @@ class B200BDModel(nn.Module):
         """Decoder + per-pixel binary-occupancy MLP (bd_model.py:260-304).  Returns (pred, search_depths)."""
         res, _ = self.depth_decoder.plan(post, dec_in, outputs=(0,))
         if search:
-            search_depths, pred = self.binary_mlp.plan_search(post, res[0], get_prior=(lambda: slots.get("prior")))
+            search_depths, pred = self.binary_mlp.plan_search(post, res[0], get_prior=(lambda: slots.get("prior")),
+                                                              get_thresholds=(lambda: slots.get("thresholds")))
             return pred, search_depths
         pred = self.binary_mlp.plan_val(post, res[0], lambda: slots["rendered_depth"], P,
                                         get_prior=(lambda: slots.get("prior")))
@@ -326,6 +331,7 @@ class B200BDModel(nn.Module):
         st.slots["cv"] = cost_volume
         st.slots["rendered_depth"] = rendered_depth
         st.slots["prior"] = prior
+        st.slots["thresholds"] = self._thr if (search and self.thresholder is not None) else None
         st.post.run()
         if st.encp is not None:
             join_encoder()  # formal join of the side stream (its last op already gates the decoder)
@@ -435,8 +441,6 @@ class B200BDModel(nn.Module):
         irrelevant: the matching-encoder kernels are batch-invariant.  Only the inference branch exists."""
         if phase == "train":
             raise NotImplementedError("B200BDModel implements the inference path only")
-        if infer_depth and getattr(self, "thresholder", None) is not None:
-            raise NotImplementedError("infer_depth with a depth-dependent Thresholder is not built (threshold 0.5 only)")
         ms = self.run_opts.matching_scale
         cur_image = cur_data["image_b3hw"]
         _abi.require_cuda(cur_image)
@@ -459,6 +463,16 @@ class B200BDModel(nn.Module):
         # a batch staged by `staging.FrameStaging` (one buffer, images already in matching-encoder order): the
         # forward reads the staging slot in place -- no per-tensor copies, no image concatenation
         images_all = self._staged_images(cur_data, src_data, args[0])
+        if infer_depth and self.thresholder is not None:
+            # static device copies of the Thresholder's vectors (a captured graph keeps reading these addresses)
+            bins, vals = f(self.thresholder.bins).reshape(-1), f(self.thresholder.thresholds).reshape(-1)
+            if bins.numel() != vals.numel() or bins.numel() == 0:
+                raise ValueError("thresholder.bins and thresholder.thresholds must be vectors of equal length")
+            if self._thr is None or self._thr[0].numel() != bins.numel() or self._thr[0].device != args[0].device:
+                self._thr = (torch.empty(bins.numel(), device=args[0].device),
+                             torch.empty(bins.numel(), device=args[0].device))
+            self._thr[0].copy_(bins)
+            self._thr[1].copy_(vals)
         if self.encoder_ahead and self.native_image_encoder:
             self._encoder_handoff(args[0], args[1].shape[1], args[-1].shape[1], bool(infer_depth))
         if self.use_cuda_graph:
@@ -491,7 +505,9 @@ class B200BDModel(nn.Module):
         """Whole forward captured once per input signature into a CUDA graph and replayed.  Ordinary inputs are
         copied into the graph's static tensors every call; a staged batch (`images_all` given) is read in place:
         the graph is captured on the staging slot itself, one graph per slot, all sharing the launch plans."""
-        sig = tuple(tuple(a.shape) for a in args) + (prior is not None, return_mask, search)
+        thr = self._thr if (search and self.thresholder is not None) else None
+        sig = tuple(tuple(a.shape) for a in args) + (prior is not None, return_mask, search,
+                                                     None if thr is None else thr[0].data_ptr())
         key = sig + ((images_all.data_ptr(),) if images_all is not None else ())
         if key not in self._graphs:
             static = list(args) if images_all is not None else [a.clone() for a in args]

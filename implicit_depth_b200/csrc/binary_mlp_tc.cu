@@ -33,6 +33,9 @@ struct BmParams {
   long long npix;
   int HW, P, use_prior;
   float lo0, hi0, z0;          // search mode: initial bounds and first query depth
+  const float* thr_bins;       // search mode: depth-dependent thresholds (Thresholder, binary_metrics_utils.py:42-52):
+  const float* thr_vals;       //   threshold = thr_vals[#{i : thr_bins[i] < z}] (torch.bucketize); null = 0.5
+  int n_thr;
 };
 
 struct BmSync {
@@ -150,8 +153,14 @@ __global__ void __launch_bounds__(BM_THREADS, 1) binary_mlp_tc_kernel(const __gr
         tc::mbar_arrive(&gs->acc_free);
         logit = o + b3v;
         if (SEARCH) {
-          // bd_model.py:281-291: visible = sigmoid(pred) < 0.5; max_bound[visible] = z; min_bound[~visible] = z
-          const bool visible = (1.f / (1.f + expf(-logit))) < 0.5f;
+          // bd_model.py:281-291: visible = sigmoid(pred) < threshold(z); max_bound[visible] = z; min_bound[~visible] = z
+          float thr = 0.5f;
+          if (prm.thr_bins != nullptr) {  // Thresholder.get_thresholds: torch.bucketize(z, bins), right = False
+            int idx = 0;
+            for (int i = 0; i < prm.n_thr; ++i) idx += (__ldg(prm.thr_bins + i) < z) ? 1 : 0;
+            thr = __ldg(prm.thr_vals + min(idx, prm.n_thr - 1));
+          }
+          const bool visible = (1.f / (1.f + expf(-logit))) < thr;
           if (visible) hi = z; else lo = z;
           z = (hi + lo) / 2.f;
         } else if (live) {
@@ -326,8 +335,11 @@ extern "C" int b200_binary_mlp_planes(void* plan, const float* depth, int P, con
 }
 
 extern "C" int b200_binary_mlp_search(void* plan, const float* prior, int iters, float min_bound, float max_bound,
-                                      float first_depth, float* search_out, float* pred_out, void* stream) {
+                                      float first_depth, const float* thr_bins, const float* thr_vals, int n_thr,
+                                      float* search_out, float* pred_out, void* stream) {
   B200_CHECK_ARG(plan && search_out && pred_out && iters > 0, "binary_mlp_search: bad arguments");
+  B200_CHECK_ARG((thr_bins == nullptr) == (thr_vals == nullptr) && (thr_bins == nullptr || n_thr > 0),
+                 "binary_mlp_search: thr_bins / thr_vals come together with n_thr > 0");
   BmPlan* p = (BmPlan*)plan;
   BmParams k = p->k;
   k.prior = prior;
@@ -337,6 +349,9 @@ extern "C" int b200_binary_mlp_search(void* plan, const float* prior, int iters,
   k.lo0 = min_bound;
   k.hi0 = max_bound;
   k.z0 = first_depth;
+  k.thr_bins = thr_bins;
+  k.thr_vals = thr_vals;
+  k.n_thr = thr_bins ? n_thr : 0;
   binary_mlp_tc_kernel<true><<<p->grid, BM_THREADS, BM_SMEM, (cudaStream_t)stream>>>(k);
   B200_CHECK_LAUNCH("binary_mlp_search");
   return 0;

@@ -459,8 +459,14 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
     p->smem = 1024 + S * stage_bytes + (2 * S + 4) * 8 + 16;
   }
   const int items = k.B * k.tiles_x * k.tiles_y * k.n_ntiles;
-  p->grid = items < n_sm ? items : n_sm;
-  if (d->max_ctas > 0 && p->grid > d->max_ctas) p->grid = d->max_ctas;
+  // Balanced persistent grid: with `rounds` = ceil(items / SMs) items per CTA anyway, ceil(items / rounds) CTAs finish
+  // at the same time as a full grid would (e.g. 768 items: 128 CTAs x 6 instead of 148 CTAs of which 28 do 6 and 120
+  // do 5) and leave the other SMs to kernels of concurrent streams (the launch plans run independent layers side by
+  // side).
+  int cap = n_sm;
+  if (d->max_ctas > 0 && cap > d->max_ctas) cap = d->max_ctas;
+  const int rounds = (items + cap - 1) / cap;
+  p->grid = (items + rounds - 1) / rounds;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -643,8 +643,10 @@ class ResnetMatchingEncoder(_PlannedModule):
         def stem():
             img = get_images()
             assert tuple(img.shape) == (n, 3, H, W) and img.is_contiguous() and img.dtype == torch.float32
+            # (not capped by g.max_ctas: the first kernel of the forward runs before the image encoder's stream has
+            # anything to share the SMs with)
             _abi.call("b200_stem_conv7_tc", _abi.ptr(img), _abi.ptr(wimage), _abi.ptr(b7), _abi.ptr(s1.hi),
-                      _abi.ptr(s1.lo), n, H, W, g.max_ctas, _abi.stream_ptr())
+                      _abi.ptr(s1.lo), n, H, W, 0, _abi.stream_ptr())
 
         g.add(stem)
         H4, W4 = (H2 - 2) // 2 + 1, (W2 - 2) // 2 + 1
@@ -761,10 +763,12 @@ class BinaryMLPNetwork(nn.Module):
         return pred
 
     def plan_search(self, g: Plan, feat: SplitAct, get_prior=None, iters=12, min_bound=0.5, max_bound=8.0,
-                    first_depth=7.5 / 2.0):
+                    first_depth=7.5 / 2.0, get_thresholds=None):
         """The `infer_depth` bisection of BDModel.forward (bd_model.py:273-292) in the same fused kernel: per pixel
-        12 evaluations of the MLP at the running query depth, bounds kept in registers.  Returns (search_depths,
-        pred of the last evaluation), both [B, 1, H, W] fp32."""
+        12 evaluations of the MLP at the running query depth, bounds kept in registers.  `get_thresholds()` ->
+        (bins, thresholds) fp32 CUDA vectors of equal length (the evaluation's `Thresholder`,
+        binary_metrics_utils.py:42-52) or None for the fixed 0.5.  Returns (search_depths, pred of the last
+        evaluation), both [B, 1, H, W] fp32."""
         B, H, W, _ = feat.shape
         handle = self._fused_plan(g, feat)
         search = g.empty((B, 1, H, W))
@@ -774,8 +778,14 @@ class BinaryMLPNetwork(nn.Module):
             pr = get_prior() if (self.use_prior and get_prior is not None) else None
             if pr is not None:
                 assert tuple(pr.shape) == (B, 1, H, W) and pr.is_contiguous() and pr.dtype == torch.float32
+            thr = get_thresholds() if get_thresholds is not None else None
+            bins, vals = thr if thr is not None else (None, None)
+            if bins is not None:
+                assert bins.is_cuda and vals.is_cuda and bins.dtype == vals.dtype == torch.float32
+                assert bins.is_contiguous() and vals.is_contiguous() and bins.numel() == vals.numel()
             _abi.call("b200_binary_mlp_search", handle, _abi.ptr(pr), iters, min_bound, max_bound, first_depth,
-                      _abi.ptr(search), _abi.ptr(pred), _abi.stream_ptr())
+                      _abi.ptr(bins), _abi.ptr(vals), 0 if bins is None else bins.numel(), _abi.ptr(search),
+                      _abi.ptr(pred), _abi.stream_ptr())
 
         g.add(op)
         return search, pred

@@ -211,10 +211,14 @@ typedef struct {
 int b200_binary_mlp_create(const b200_binary_mlp_desc* desc, void** plan_out);
 /* depth [B,P,H,W] fp32; prior [B,1,H,W] fp32 or NULL (-1 everywhere if the model uses a prior); pred [B,P,H,W]. */
 int b200_binary_mlp_planes(void* plan, const float* depth, int P, const float* prior, float* pred, void* stream);
-/* per-pixel bisection: `iters` evaluations starting at first_depth inside [min_bound, max_bound];
- * search_out [B,1,H,W] = final query depth, pred_out [B,1,H,W] = logit of the last evaluation. */
+/* per-pixel bisection: `iters` evaluations starting at first_depth inside [min_bound, max_bound]; a pixel is "visible"
+ * at query depth z when sigmoid(logit) < threshold(z): 0.5, or -- with the evaluation's depth-dependent Thresholder
+ * (utils/binary_metrics_utils.py:42-52, set by test_bd.py:91-102) -- thr_vals[bucketize(z, thr_bins)] (device arrays
+ * of n_thr floats, or NULL); search_out [B,1,H,W] = final query depth, pred_out [B,1,H,W] = logit of the last
+ * evaluation. */
 int b200_binary_mlp_search(void* plan, const float* prior, int iters, float min_bound, float max_bound,
-                           float first_depth, float* search_out, float* pred_out, void* stream);
+                           float first_depth, const float* thr_bins, const float* thr_vals, int n_thr,
+                           float* search_out, float* pred_out, void* stream);
 int b200_binary_mlp_destroy(void* plan);
 /* BDModel.sample_prior (experiment_modules/bd_model.py:395-410): warp the previous frame's prediction into the
  * current frame through the rendered depth, nearest sampling, -1 where the rendered depth is not positive.

@@ -191,7 +191,7 @@ def binary_mlp_val(sd, p, feat, rendered_depth, prior=None):
 
 
 def bd_forward(sd, encoder, cur, src, opts, feature_volume="mlp_feature_volume", decoder="unet_pp", return_mask=True,
-               torch_volume=False, infer_depth=False):
+               torch_volume=False, infer_depth=False, thresholder=None):
     """`BDModel.forward(phase="test")`, bd_model.py:175-311.  cur/src: dicts of CPU float tensors; `encoder`:
     the image-prior module (same instance the product uses, on CPU)."""
     ms = opts.matching_scale
@@ -248,7 +248,7 @@ def bd_forward(sd, encoder, cur, src, opts, feature_volume="mlp_feature_volume",
             W = [(sd[f"binary_mlp.mlps.s0.{i}.weight"].numpy(), sd[f"binary_mlp.mlps.s0.{i}.bias"].numpy())
                  for i in (0, 2, 4)]
             z, pred = planesweep.binary_search_depth(dec["feature_s0_b1hw"].numpy(), W,
-                                                     None if prior is None else prior.numpy())
+                                                     None if prior is None else prior.numpy(), thresholder=thresholder)
             search, pred = torch.from_numpy(z), torch.from_numpy(pred)
         else:
             pred = binary_mlp_val(sd, "binary_mlp", dec["feature_s0_b1hw"], cur["rendered_depth"], prior)

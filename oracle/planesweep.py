@@ -265,9 +265,20 @@ def sigmoid(x):
     return 1.0 / (1.0 + np.exp(-x))
 
 
-def binary_search_depth(feature_s0, weights, prior=None, iters=12, min_bound=0.5, max_bound=8.0):
-    """`infer_depth` branch of `BDModel.forward`, `experiment_modules/bd_model.py:273-292` (thresholder None):
-    per-pixel bisection on the occupancy logit.  Returns (search_depths, pred of the last evaluation)."""
+def thresholder_bins(planes):
+    """`Thresholder.__init__`, `utils/binary_metrics_utils.py:42-47`: bin edges halfway between the planes, last 100."""
+    bins = np.zeros_like(planes)
+    bins[:-1] = (planes[1:] + planes[:-1]) / 2
+    bins[-1] = 100.0
+    return bins
+
+
+def binary_search_depth(feature_s0, weights, prior=None, iters=12, min_bound=0.5, max_bound=8.0, thresholder=None):
+    """`infer_depth` branch of `BDModel.forward`, `experiment_modules/bd_model.py:273-292`: per-pixel bisection on
+    the occupancy logit.  `thresholder` = (bins, thresholds) of the evaluation's depth-dependent `Thresholder`
+    (`get_thresholds`: thresholds[torch.bucketize(z, bins)], `binary_metrics_utils.py:50-52`; bucketize with
+    right=False = numpy searchsorted side="left") or None for the fixed 0.5.  Returns (search_depths, pred of the
+    last evaluation)."""
     B, _, H, W = feature_s0.shape
     dt = feature_s0.dtype
     lo = np.full((B, 1, H, W), min_bound, dt)
@@ -276,7 +287,8 @@ def binary_search_depth(feature_s0, weights, prior=None, iters=12, min_bound=0.5
     pred = None
     for _ in range(iters):
         pred = binary_mlp(feature_s0, z, weights, prior)
-        visible = sigmoid(pred) < 0.5
+        thr = 0.5 if thresholder is None else thresholder[1][np.searchsorted(thresholder[0], z, side="left")]
+        visible = sigmoid(pred) < thr
         hi = np.where(visible, z, hi)
         lo = np.where(visible, lo, z)
         z = (hi + lo) / dt.type(2)

@@ -260,6 +260,23 @@ def temporal_goldens():
                         infer_depth=True)
                 g["search_depths"] = o["search_depths"].numpy()
                 g["search_pred_0"] = o["pred_0"].numpy()
+                # the same search with the evaluation's depth-dependent thresholds (test_bd.py:91-102)
+                from utils.binary_metrics_utils import Thresholder  # reference
+
+                real_tcuda = torch.Tensor.cuda
+                torch.Tensor.cuda = lambda self, *a, **k: self  # Thresholder.__init__ calls thresholds.cuda()
+                try:
+                    ref.thresholder = Thresholder(planes=torch.linspace(1.5, 5.0, 8).float(), thresholds=torch.tensor(
+                        [0.5, 0.400, 0.3000, 0.3000, 0.3000, 0.3000, 0.300, 0.300]).float())
+                finally:
+                    torch.Tensor.cuda = real_tcuda
+                o = ref("test", cur_t, src_t, unbatched_matching_encoder_forward=True, return_mask=True,
+                        infer_depth=True)
+                g["thr_bins"] = ref.thresholder.bins.numpy()
+                g["thr_vals"] = ref.thresholder.thresholds.numpy()
+                g["search_depths_thr"] = o["search_depths"].numpy()
+                g["search_pred_0_thr"] = o["pred_0"].numpy()
+                ref.thresholder = None
         np.savez_compressed(os.path.join(HERE, "temporal_256x192.npz"), **g)
         print("temporal", {k: v.shape for k, v in g.items()})
     finally:

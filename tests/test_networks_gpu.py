@@ -256,6 +256,18 @@ def test_fused_binary_mlp_kernel_vs_oracle(use_prior):
     z_ref, pred_ref = O.binary_search_depth(feat, Wt, prior)
     assert np.abs(search.cpu().numpy() - z_ref).max() <= 2 * 7.5 / 2**12 + 1e-6
     assert (search.cpu().numpy() != z_ref).mean() < 1e-2
+    # depth-dependent thresholds (Thresholder, binary_metrics_utils.py:42-52; test_bd.py:91-102)
+    bins = O.thresholder_bins(np.linspace(1.5, 5.0, 8, dtype=np.float32))
+    vals = np.array([0.5, 0.4, 0.3, 0.3, 0.3, 0.3, 0.3, 0.3], np.float32)
+    thr_c = (torch.from_numpy(bins).cuda(), torch.from_numpy(vals).cuda())
+    g3 = Plan("cuda")
+    search_t, _ = net.plan_search(g3, fa, get_prior=(lambda: p_c), get_thresholds=(lambda: thr_c))
+    g3.run()
+    torch.cuda.synchronize()
+    z_thr, _ = O.binary_search_depth(feat, Wt, prior, thresholder=(bins, vals))
+    assert (z_thr != z_ref).mean() > 0.02  # the thresholds do change the answer on this data
+    assert np.abs(search_t.cpu().numpy() - z_thr).max() <= 2 * 7.5 / 2**12 + 1e-6
+    assert (search_t.cpu().numpy() != z_thr).mean() < 1e-2
 
 
 def test_sample_prior_kernel_vs_reference_golden():
@@ -274,26 +286,32 @@ def test_sample_prior_kernel_vs_reference_golden():
     assert ((got == -1) >= (g["cfg4_rendered_depth"] <= 0)).all()
 
 
-@pytest.mark.parametrize("mode", ["prior", "noprior", "search"])
+@pytest.mark.parametrize("mode", ["prior", "noprior", "search", "search_thr"])
 def test_temporal_and_infer_depth_forward_vs_reference_golden(mode):
     """implicit_depth_temporal.yaml path (use_prior: prior warp + 66-input MLP) and the
     infer_depth bisection through B200BDModel.forward, against the reference goldens."""
     g = np.load(f"{GOLDEN}/temporal_256x192.npz")
-    use_prior = mode != "search"
+    use_prior = not mode.startswith("search")
     m, checksum, sd = seeded(image_width=256, image_height=192, matching_num_depth_bins=16, use_prior=use_prior)
+    if mode == "search_thr":  # `model.thresholder = Thresholder(...)` of test_bd.py:91-102: anything with these two vectors
+        from types import SimpleNamespace
+
+        m.thresholder = SimpleNamespace(bins=torch.from_numpy(g["thr_bins"]).cuda(),
+                                        thresholds=torch.from_numpy(g["thr_vals"]).cuda())
     cur, src = synthetic.make_frame_batch(5000, 1, 7, 192, 256, num_rendered=1, temporal=True)
     cur_c = {k: torch.from_numpy(v).cuda() for k, v in cur.items() if mode == "prior" or not k.startswith("prior_")}
     src_c = {k: torch.from_numpy(v).cuda() for k, v in src.items()}
     for graph in (False, True):
         m.use_cuda_graph = graph
-        out = m("test", dict(cur_c), src_c, return_mask=True, infer_depth=(mode == "search"))
+        out = m("test", dict(cur_c), src_c, return_mask=True, infer_depth=mode.startswith("search"))
         assert abs(checksum - float(g["checksum_prior" if use_prior else "checksum_search"])) <= 1e-6 * checksum, \
             "seeded weights differ from the ones the reference goldens were generated with"
-        if mode == "search":
+        if mode.startswith("search"):
+            want = g["search_depths_thr" if mode == "search_thr" else "search_depths"]
             assert set(out) == {"pred_0", "search_depths", "lowest_cost_bhw", "overall_mask_bhw"}
             sd_got = out["search_depths"].cpu().numpy()
-            assert np.abs(sd_got - g["search_depths"]).max() <= 4 * 7.5 / 2**12
-            assert (np.abs(sd_got - g["search_depths"]) > 1e-6).mean() < 2e-2
+            assert np.abs(sd_got - want).max() <= 4 * 7.5 / 2**12
+            assert (np.abs(sd_got - want) > 1e-6).mean() < 2e-2
         else:
             assert rel_err(out["pred_0"].cpu().numpy(), g[f"{mode}_pred_0"]) < TOL
 
