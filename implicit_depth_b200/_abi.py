@@ -41,9 +41,9 @@ SIGNATURES = {
     "b200_stem_conv7": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
     "b200_stem_conv7_tc": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, ctypes.c_void_p],
     "b200_maxblurpool": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, ctypes.c_void_p],
-    "b200_dwconv3x3_silu": [c_f] * 6 + [c_i] * 5 + [ctypes.c_void_p],
+    "b200_dwconv3x3_silu": [c_f] * 6 + [c_i] * 6 + [ctypes.c_void_p],
     "b200_squeeze_excite": [c_f] * 10 + [c_i] * 4 + [ctypes.c_void_p],
-    "b200_mbconv_dw_se": [c_f] * 13 + [c_i] * 6 + [ctypes.c_void_p],
+    "b200_mbconv_dw_se": [c_f] * 13 + [c_i] * 7 + [ctypes.c_void_p],
     "b200_mbconv_pool_block": [],
     "b200_split_add": [c_f] * 6 + [c_ll, ctypes.c_void_p],
     "b200_channel_dot_exp": [c_f] * 6 + [c_ll, c_i, ctypes.c_void_p],

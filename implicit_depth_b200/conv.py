@@ -14,7 +14,8 @@ MAX_SEG = 4
 
 class _Seg(ctypes.Structure):
     _fields_ = [("in_hi", ctypes.c_void_p), ("in_lo", ctypes.c_void_p), ("H", ctypes.c_int), ("W", ctypes.c_int),
-                ("C", ctypes.c_int), ("ksize", ctypes.c_int), ("stride", ctypes.c_int), ("pad", ctypes.c_int)]
+                ("C", ctypes.c_int), ("ksize", ctypes.c_int), ("stride", ctypes.c_int), ("pad", ctypes.c_int),
+                ("pad_hi", ctypes.c_int)]
 
 
 class _Desc(ctypes.Structure):
@@ -51,6 +52,29 @@ class SplitAct:
         a.hi.copy_(xh.to(torch.bfloat16))
         a.lo.copy_((xh - a.hi.float()).to(torch.bfloat16))
         return a
+
+
+def pad_pair(p):
+    """int (symmetric) or (lo, hi) -> (lo, hi)."""
+    return (p, p) if isinstance(p, int) else (int(p[0]), int(p[1]))
+
+
+def out_size(H, W, k, stride, pad):
+    lo, hi = pad_pair(pad)
+    return (H + lo + hi - k) // stride + 1, (W + lo + hi - k) // stride + 1
+
+
+def same_pad(H, W, k, stride):
+    """TF "SAME" padding (timm `Conv2dSame`) of a k x k conv: total = max((ceil(n / s) - 1) s + k - n, 0) per axis,
+    split (total // 2, total - total // 2).  The kernels take one pair for both axes."""
+    def one(n):
+        total = max((-(-n // stride) - 1) * stride + k - n, 0)
+        return total // 2, total - total // 2
+    py, px = one(H), one(W)
+    if py != px:
+        raise NotImplementedError(f"'SAME' padding differs between the axes for a {H}x{W} map (stride {stride}): "
+                                  "mixed even/odd sizes are not supported by the conv kernels")
+    return py
 
 
 def ntile(cout):
@@ -113,18 +137,20 @@ class ConvPlan:
 
     def __init__(self, segs, weights, bias, out, B, cout, act="none", slope=0.2, residual=None, out_f32=None,
                  max_ctas=0):
-        """segs: list of (SplitAct, ksize, stride, pad); weights: one [Cout, C, k, k] fp32 tensor per segment;
-        out: SplitAct or None; residual: SplitAct or None; max_ctas: CTA cap of the persistent launch (0 = all SMs)."""
+        """segs: list of (SplitAct, ksize, stride, pad); `pad` is an int (torch-style symmetric padding) or a pair
+        (top/left, bottom/right) -- (0, 1) is the TF "SAME" padding of a stride-2 3x3 conv on an even-sized map;
+        weights: one [Cout, C, k, k] fp32 tensor per segment; out: SplitAct or None; residual: SplitAct or None;
+        max_ctas: CTA cap of the persistent launch (0 = all SMs)."""
         d = _Desc()
         d.nseg = len(segs)
         for i, (a, k, s, p) in enumerate(segs):
+            p_lo, p_hi = pad_pair(p)
             d.seg[i].in_hi = a.hi.data_ptr()
             d.seg[i].in_lo = a.lo.data_ptr()
             d.seg[i].H, d.seg[i].W, d.seg[i].C = a.H, a.W, a.C
-            d.seg[i].ksize, d.seg[i].stride, d.seg[i].pad = k, s, p
+            d.seg[i].ksize, d.seg[i].stride, d.seg[i].pad, d.seg[i].pad_hi = k, s, p_lo, p_hi
         a0, k0, s0, p0 = segs[0]
-        OH = (a0.H + 2 * p0 - k0) // s0 + 1
-        OW = (a0.W + 2 * p0 - k0) // s0 + 1
+        OH, OW = out_size(a0.H, a0.W, k0, s0, p0)
         d.bias = bias.data_ptr() if bias is not None else None
         d.res_hi = residual.hi.data_ptr() if residual is not None else None
         d.res_lo = residual.lo.data_ptr() if residual is not None else None

@@ -20,8 +20,15 @@
 #define CVH_ROWS 16
 #define CVH_EPI_THREADS 256
 
-template <int SUB, int NT /* N tile: 128, 64, or 16 (direct-store epilogue, no residual) */>
+// KSPLIT (SUB = 1, NT >= 64; low-resolution layers whose item count leaves most SMs idle): a thread-block cluster of
+// prm.ksplit CTAs shares ONE item.  CTA r accumulates a contiguous 1/ksplit of the item's 32-channel patches (its share
+// of the weight stream and of the MMAs) into its own TMEM accumulator, parks the fp32 partial tile in its shared
+// memory, and after a cluster barrier reduces the column slice [r NT/ksplit, (r+1) NT/ksplit) of all partials through
+// distributed shared memory -- in rank order, so the sum is deterministic -- applies bias / residual / activation and
+// stores its slice.  grid = items x ksplit exactly (one item per cluster).
+template <int SUB, int NT /* N tile: 128, 64, or 16 (direct-store epilogue, no residual) */, bool KSPLIT = false>
 __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvKParams prm) {
+  static_assert(!KSPLIT || (SUB == 1 && NT >= 64), "split-K variant: one M=128 sub-tile, 64- or 128-wide N tile");
   constexpr int NTC = NT / 64;  // 64-channel store boxes per N tile (0 for the 16-wide tile)
   constexpr int PW = 8 * SUB + 2;
   constexpr uint32_t PATCH_PLANE = (18u * PW * 64u + 1023u) & ~1023u;  // one bf16 plane of a 32-channel patch
@@ -49,6 +56,13 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int items = prm.B * prm.tiles_y * prm.tiles_x * prm.n_ntiles;
+  // split-K: rank within the cluster, this CTA's patch range [p_lo, p_hi) of the item's total_patches
+  const int KS = KSPLIT ? prm.ksplit : 1;
+  const int crank = KSPLIT ? (int)tc::cluster_ctarank() : 0;
+  const int p_lo = KSPLIT ? (prm.total_patches * crank) / KS : 0;
+  const int p_hi = KSPLIT ? (prm.total_patches * (crank + 1)) / KS : 0x7fffffff;
+  const int item0 = KSPLIT ? (int)blockIdx.x / KS : (int)blockIdx.x;
+  const int item_step = KSPLIT ? (int)gridDim.x / KS : (int)gridDim.x;
 
   for (int i = tid; i < prm.n_ntiles * NT; i += CVH_THREADS)
     bias_s[i] = (prm.bias != nullptr && i < prm.Cout) ? prm.bias[i] : 0.f;
@@ -82,20 +96,23 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
     // =========================== TMA producer (whole warp loops, one elected lane issues) ===========
     uint32_t pit = 0;                 // patch counter
     uint32_t bst = 0, bround = 0;     // weight-stage ring position / wrap count
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    for (int item = item0; item < items; item += item_step) {
       const int nt = item % prm.n_ntiles;
       const int mt = item / prm.n_ntiles;
       const int tx = mt % prm.tiles_x;
       const int ty = (mt / prm.tiles_x) % prm.tiles_y;
       const int b = mt / (prm.tiles_x * prm.tiles_y);
       const uint8_t* wbase = prm.wimage + (size_t)nt * prm.total_chunks * B_BYTES;
+      int pglob = 0;  // index of the patch within the item (split-K: only [p_lo, p_hi) are this CTA's)
       for (int s = 0; s < prm.nseg; ++s) {
         const int ks = prm.seg_ksize[s], pd = prm.seg_pad[s];
         const int cblocks = (prm.seg_C[s] + 31) >> 5;
         // a 1x1 segment reads the centre of the same kind of patch: origin shifted by (1 - pad)
         const int org = (ks == 3) ? -pd : -(pd + 1);
         const int x0 = tx * 8 * SUB + org, y0 = ty * CVH_ROWS + org;
-        for (int cb = 0; cb < cblocks; ++cb, ++pit) {
+        for (int cb = 0; cb < cblocks; ++cb) {
+          const int pidx = pglob++;
+          if (KSPLIT && (pidx < p_lo || pidx >= p_hi)) continue;
           const uint32_t pb = pit & 1u, round = pit >> 1;
           if (round > 0) tc::mbar_wait(&p_empty[pb], (round - 1) & 1u);
           uint8_t* pa = patch0 + (size_t)pb * 2u * PATCH_PLANE;
@@ -120,9 +137,11 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
             }
             __syncwarp();
           }
+          ++pit;
         }
       }
     }
+    if (KSPLIT) { tc::cluster_sync(); tc::cluster_sync(); }  // the epilogue's two cluster barriers (all threads arrive)
   } else if (warp == 1) {
     // =========================== MMA issuer (whole warp loops, one elected lane issues) ============
     constexpr uint32_t IDESC_MERGED = tc::idesc_bf16_f32(128, 2 * NT);
@@ -130,16 +149,19 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
     constexpr uint32_t SBO = PW * 64u;
     uint32_t pit = 0, tile_i = 0;
     uint32_t bst = 0, bround = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
+    for (int item = item0; item < items; item += item_step, ++tile_i) {
       const uint32_t a = tile_i & 1u, use = tile_i >> 1;
       if (use > 0) tc::mbar_wait(&acc_empty[a], (use - 1) & 1u);
       tc::fence_after_sync();
       const uint32_t acc = tmem + a * ACC_COLS;
       uint32_t first = 1;
+      int pglob = 0;
       for (int s = 0; s < prm.nseg; ++s) {
         const int ks = prm.seg_ksize[s], C = prm.seg_C[s];
         const int cblocks = (C + 31) >> 5;
-        for (int cb = 0; cb < cblocks; ++cb, ++pit) {
+        for (int cb = 0; cb < cblocks; ++cb) {
+          const int pidx = pglob++;
+          if (KSPLIT && (pidx < p_lo || pidx >= p_hi)) continue;
           const uint32_t pb = pit & 1u;
           tc::mbar_wait(&p_full[pb], (pit >> 1) & 1u);
           tc::fence_after_sync();
@@ -180,11 +202,13 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
           }
           if (tc::elect_one()) tc::mma_commit(&p_empty[pb]);
           __syncwarp();
+          ++pit;
         }
       }
       if (tc::elect_one()) tc::mma_commit(&acc_full[a]);
       __syncwarp();
     }
+    if (KSPLIT) { tc::cluster_sync(); tc::cluster_sync(); }
   } else {
     // =========================== epilogue (warps 2..9) ===========================
     const int et = tid - 64;                  // 0..255
@@ -197,10 +221,73 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
     constexpr int COLS = NT / 2;              // columns per thread: 32 (NT = 64) or 64 (NT = 128)
     const uint32_t swz = (uint32_t)(row & 7);
     uint32_t tile_i = 0;
-    if constexpr (NT == 16) {
+    if constexpr (KSPLIT) {
+      // ---- split-K epilogue: partial tile -> own shared memory, cluster barrier, DSMEM reduction of a column slice ----
+      constexpr int PST = NT + 4;  // padded row stride (floats): conflict-free float4 rows for 8 consecutive lanes
+      float* part = reinterpret_cast<float*>(base);  // [128][PST], over the (now dead) patch + staging buffers
+      const int item = item0;  // exactly one item per cluster
+      const int nt = item % prm.n_ntiles;
+      const int mt = item / prm.n_ntiles;
+      const int tx = mt % prm.tiles_x;
+      const int ty = (mt / prm.tiles_x) % prm.tiles_y;
+      const int b = mt / (prm.tiles_x * prm.tiles_y);
+      tc::mbar_wait(&acc_full[0], 0u);  // every MMA of this CTA's K share has completed: patches are dead, too
+      tc::fence_after_sync();
+#pragma unroll
+      for (int c0 = 0; c0 < COLS; c0 += 32) {
+        uint32_t rm[32], rc[32];
+        tc::tmem_ld32(tmem + lane_base + half * COLS + c0, rm);
+        tc::tmem_ld32(tmem + lane_base + NT + half * COLS + c0, rc);
+        tc::wait_ld();
+        float* dst = part + row * PST + half * COLS + c0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(dst + 4 * q) =
+              make_float4(__uint_as_float(rm[4 * q]) + __uint_as_float(rc[4 * q]),
+                          __uint_as_float(rm[4 * q + 1]) + __uint_as_float(rc[4 * q + 1]),
+                          __uint_as_float(rm[4 * q + 2]) + __uint_as_float(rc[4 * q + 2]),
+                          __uint_as_float(rm[4 * q + 3]) + __uint_as_float(rc[4 * q + 3]));
+      }
+      tc::fence_before_sync();
+      tc::cluster_sync();  // #1: all partial tiles of the cluster are in place
+      {
+        const int CW = NT / KS;                 // columns this CTA finishes
+        const int r2 = et & 127, hsel = et >> 7;  // two threads per row, CW / 2 columns each
+        const int c_lo = crank * CW + hsel * (CW >> 1);
+        const int oy = ty * CVH_ROWS + (r2 >> 3), ox = tx * 8 + (r2 & 7);
+        const bool live = oy < prm.OH && ox < prm.OW;
+        const size_t o = (((size_t)b * prm.OH + oy) * prm.OW + ox) * prm.Cout + nt * NT + c_lo;
+        const uint32_t my = tc::smem_u32(part + r2 * PST + c_lo);
+        for (int c = 0; c < (CW >> 1); c += 4) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = 0; q < KS; ++q) {  // fixed rank order: deterministic sum
+            const float4 v = tc::ld_cluster_f4(tc::mapa(my + 4u * c, (uint32_t)q));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+          if (live) {
+            const float* bs = bias_s + nt * NT + c_lo + c;
+            float v[4] = {acc.x + bs[0], acc.y + bs[1], acc.z + bs[2], acc.w + bs[3]};
+            if (has_res) {
+              const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(prm.res_hi + o + c));
+              const uint2 l2 = __ldg(reinterpret_cast<const uint2*>(prm.res_lo + o + c));
+              v[0] += __uint_as_float(h2.x << 16) + __uint_as_float(l2.x << 16);
+              v[1] += __uint_as_float(h2.x & 0xffff0000u) + __uint_as_float(l2.x & 0xffff0000u);
+              v[2] += __uint_as_float(h2.y << 16) + __uint_as_float(l2.y << 16);
+              v[3] += __uint_as_float(h2.y & 0xffff0000u) + __uint_as_float(l2.y & 0xffff0000u);
+            }
+            uint32_t hi[2], lo[2];
+            tc::split2(apply_act(v[0], prm.act, prm.slope), apply_act(v[1], prm.act, prm.slope), hi[0], lo[0]);
+            tc::split2(apply_act(v[2], prm.act, prm.slope), apply_act(v[3], prm.act, prm.slope), hi[1], lo[1]);
+            *reinterpret_cast<uint2*>(prm.out_hi + o + c) = make_uint2(hi[0], hi[1]);
+            *reinterpret_cast<uint2*>(prm.out_lo + o + c) = make_uint2(lo[0], lo[1]);
+          }
+        }
+      }
+      tc::cluster_sync();  // #2: nobody reads this CTA's shared memory any more
+    } else if constexpr (NT == 16) {
       // 16-wide N tile (the 3x3 128 -> 16 head of the matching encoder): warp group `half` drains sub-tile `half`;
       // a thread holds all 16 channels of its pixel and stores them directly (32 B per plane, image border by test)
-      for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
+      for (int item = item0; item < items; item += item_step, ++tile_i) {
         const int mt = item;  // n_ntiles == 1
         const int tx = mt % prm.tiles_x;
         const int ty = (mt / prm.tiles_x) % prm.tiles_y;
@@ -236,7 +323,7 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
         tc::mbar_arrive(&acc_empty[a]);
       }
     } else
-    for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
+    for (int item = item0; item < items; item += item_step, ++tile_i) {
       const int nt = item % prm.n_ntiles;
       const int mt = item / prm.n_ntiles;
       const int tx = mt % prm.tiles_x;
@@ -328,7 +415,7 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
         tc::tma_store_commit();
       }
     }
-    if (NT != 16 && leader) tc::tma_store_wait_all<0>();
+    if (NT != 16 && !KSPLIT && leader) tc::tma_store_wait_all<0>();
   }
   tc::fence_before_sync();
   __syncthreads();

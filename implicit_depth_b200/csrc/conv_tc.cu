@@ -48,6 +48,7 @@ struct ConvKParams {
   int B, OH, OW, Cout, NT, n_ntiles, act, total_chunks, tiles_x, tiles_y, stages;
   float slope;
   int halo, sub, has_res, tps;
+  int ksplit, total_patches;   // halo kernel, split-K over a cluster of `ksplit` CTAs (1 = off); 32-channel patches per item
   int seg_chunk0[CV_MAX_SEG];  // index of each segment's first chunk in the weight image
 };
 
@@ -261,6 +262,8 @@ struct b200_conv_seg {
   const void* in_hi;  // NHWC bf16 [B,H,W,C]
   const void* in_lo;
   int H, W, C, ksize, stride, pad;
+  int pad_hi;  // padding at the bottom / right edge; `pad` is the top / left one (they differ for TF "SAME" padding
+               // of stride-2 convs on even sizes: (0, 1))
 };
 struct b200_conv_desc {
   b200_conv_seg seg[CV_MAX_SEG];
@@ -308,7 +311,8 @@ extern "C" int b200_conv_uses_halo(const b200_conv_desc* d) {
   if (all_1x1) return 0;
   for (int s = 0; s < d->nseg; ++s) {
     const b200_conv_seg& sg = d->seg[s];
-    const bool ok = sg.stride == 1 && ((sg.ksize == 3 && (sg.pad == 0 || sg.pad == 1)) || (sg.ksize == 1 && sg.pad == 0));
+    const bool ok = sg.stride == 1 && sg.pad_hi == sg.pad &&
+                    ((sg.ksize == 3 && (sg.pad == 0 || sg.pad == 1)) || (sg.ksize == 1 && sg.pad == 0));
     if (!ok || (n16 && sg.ksize != 3)) return 0;
   }
   return 1;
@@ -380,7 +384,8 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
       return -1;
     }
     // output size implied by this segment must match
-    const int oh = (sg.H + 2 * sg.pad - sg.ksize) / sg.stride + 1, ow = (sg.W + 2 * sg.pad - sg.ksize) / sg.stride + 1;
+    const int oh = (sg.H + sg.pad + sg.pad_hi - sg.ksize) / sg.stride + 1;
+    const int ow = (sg.W + sg.pad + sg.pad_hi - sg.ksize) / sg.stride + 1;
     if (oh != d->OH || ow != d->OW) {
       delete p;
       b200_set_error("conv_create: segment %d gives %dx%d outputs, conv says %dx%d", s, oh, ow, d->OH, d->OW);
@@ -459,6 +464,25 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
     p->smem = 1024 + S * stage_bytes + (2 * S + 4) * 8 + 16;
   }
   const int items = k.B * k.tiles_x * k.tiles_y * k.n_ntiles;
+  // Split-K over a thread-block cluster (conv_halo.cuh): for layers whose item count leaves most of the machine idle
+  // (12x16 ... 24x32 maps: 16-64 items, each streaming all of its weights through one SM), `ksplit` CTAs share an item.
+  k.ksplit = 1;
+  k.total_patches = 0;
+  if (halo) {
+    for (int s = 0; s < d->nseg; ++s) k.total_patches += (d->seg[s].C + 31) / 32;
+    int lim = n_sm;
+    if (d->max_ctas > 0 && lim > d->max_ctas) lim = d->max_ctas;
+    if (k.NT >= 64 && k.sub == 1) {
+      for (int S = 8; S >= 2; S >>= 1)
+        if (items * S <= lim && 2 * S <= k.total_patches && k.NT / S >= 8) {
+          k.ksplit = S;
+          break;
+        }
+    }
+  }
+  if (k.ksplit > 1) {
+    p->grid = items * k.ksplit;
+  } else {
   // Balanced persistent grid: with `rounds` = ceil(items / SMs) items per CTA anyway, ceil(items / rounds) CTAs finish
   // at the same time as a full grid would (e.g. 768 items: 128 CTAs x 6 instead of 148 CTAs of which 28 do 6 and 120
   // do 5) and leave the other SMs to kernels of concurrent streams (the launch plans run independent layers side by
@@ -467,6 +491,7 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   if (d->max_ctas > 0 && cap > d->max_ctas) cap = d->max_ctas;
   const int rounds = (items + cap - 1) / cap;
   p->grid = (items + rounds - 1) / rounds;
+  }
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -480,6 +505,10 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
       e = cudaFuncSetAttribute(conv_halo_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_halo_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_halo_kernel<1, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_halo_kernel<1, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       delete p;
       b200_set_error("conv_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -503,14 +532,23 @@ extern "C" int b200_conv_run(void* plan, void* stream) {
   cfg.blockDim = dim3(p->k.halo ? CVH_THREADS : CV_THREADS);
   cfg.dynamicSmemBytes = p->smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (p->k.ksplit > 1) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)p->k.ksplit;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   cudaError_t le;
   if (!p->k.halo)
     le = cudaLaunchKernelEx(&cfg, conv_tc_kernel, p->k);
+  else if (p->k.ksplit > 1 && p->k.NT == 128) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 128, true>, p->k);
+  else if (p->k.ksplit > 1) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 64, true>, p->k);
   else if (p->k.NT == 128) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 128>, p->k);
   else if (p->k.NT == 16 && p->k.sub == 2) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<2, 16>, p->k);
   else if (p->k.NT == 16) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 16>, p->k);

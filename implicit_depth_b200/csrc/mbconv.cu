@@ -1,7 +1,7 @@
 // Memory-bound pieces of the EfficientNetV2 image encoder's MBConv blocks (torchvision efficientnet_v2_s layout,
 // the stand-in for timm's tf_efficientnetv2_s_in21ft1k at the reference call site bd_model.py:46-51), on NHWC
 // split-bf16 activations:
-//   dwconv3x3_kernel   depthwise 3x3 (stride 1|2, pad 1) + folded BatchNorm bias + SiLU
+//   dwconv3x3_kernel   depthwise 3x3 (stride 1|2; pad (1,1), or (0,1) = TF "SAME" at stride 2) + folded BN bias + SiLU
 //   se_pool_kernel     squeeze: per-(frame, channel) mean over the image, deterministic two-level reduction
 //   se_fc_kernel       excitation: fc1 + SiLU + fc2 + sigmoid -> scale[b, c]  (fc2 weights transposed)
 //   se_scale_kernel    x * scale[b, c]
@@ -39,7 +39,7 @@ __device__ __forceinline__ void mb_store8(__nv_bfloat16* hi, __nv_bfloat16* lo, 
 __global__ void __launch_bounds__(256)
 dwconv3x3_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                  const float* __restrict__ wt, const float* __restrict__ bias, __nv_bfloat16* __restrict__ oh,
-                 __nv_bfloat16* __restrict__ ol, int B, int H, int W, int C, int stride, int OH, int OW) {
+                 __nv_bfloat16* __restrict__ ol, int B, int H, int W, int C, int stride, int OH, int OW, int pad_lo) {
   const int cg = C >> 3;
   const size_t total = (size_t)B * OH * OW * cg;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -58,11 +58,11 @@ dwconv3x3_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __re
     }
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
-      const int y = oy * stride + dy - 1;
+      const int y = oy * stride + dy - pad_lo;
       if (y < 0 || y >= H) continue;
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        const int x = ox * stride + dx - 1;
+        const int x = ox * stride + dx - pad_lo;
         if (x < 0 || x >= W) continue;
         float v[8];
         mb_load8(hi, lo, (((size_t)b * H + y) * W + x) * C + c8 * 8, v);
@@ -82,17 +82,19 @@ dwconv3x3_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __re
 }
 
 extern "C" int b200_dwconv3x3_silu(const void* in_hi, const void* in_lo, const float* wt, const float* bias,
-                                   void* out_hi, void* out_lo, int B, int H, int W, int C, int stride, void* stream) {
+                                   void* out_hi, void* out_lo, int B, int H, int W, int C, int stride, int pad_lo,
+                                   void* stream) {
   B200_CHECK_ARG(in_hi && in_lo && wt && bias && out_hi && out_lo, "dwconv3x3: null pointer");
   B200_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2),
                  "dwconv3x3: bad arguments (C %% 8 == 0, stride 1|2; got C=%d stride=%d)", C, stride);
-  const int OH = (H + 2 - 3) / stride + 1, OW = (W + 2 - 3) / stride + 1;
+  B200_CHECK_ARG(pad_lo == 0 || pad_lo == 1, "dwconv3x3: pad_lo is 0 (TF 'SAME' at stride 2 on even sizes) or 1");
+  const int OH = (H + pad_lo + 1 - 3) / stride + 1, OW = (W + pad_lo + 1 - 3) / stride + 1;
   const size_t total = (size_t)B * OH * OW * (C / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   dwconv3x3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo,
                                                             wt, bias, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
-                                                            B, H, W, C, stride, OH, OW);
+                                                            B, H, W, C, stride, OH, OW, pad_lo);
   B200_CHECK_LAUNCH("dwconv3x3");
   return 0;
 }
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(256)
 dwconv3x3_pool_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                       const float* __restrict__ wt, const float* __restrict__ bias, __nv_bfloat16* __restrict__ oh,
                       __nv_bfloat16* __restrict__ ol, float* __restrict__ partial, int H, int W, int C, int stride,
-                      int OH, int OW) {
+                      int OH, int OW, int pad_lo) {
   __shared__ float red[32][65];
   const int b = blockIdx.z, c0 = blockIdx.y * 64;
   const int cgp = threadIdx.x & 7, pl = threadIdx.x >> 3;
@@ -269,11 +271,11 @@ dwconv3x3_pool_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16*
       }
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy) {
-        const int y = oy * stride + dy - 1;
+        const int y = oy * stride + dy - pad_lo;
         if (y < 0 || y >= H) continue;
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          const int x = ox * stride + dx - 1;
+          const int x = ox * stride + dx - pad_lo;
           if (x < 0 || x >= W) continue;
           float v[8];
           mb_load8(hi, lo, (((size_t)b * H + y) * W + x) * C + c, v);
@@ -386,19 +388,20 @@ se_fc2_kernel(const float* __restrict__ s1, const float* __restrict__ w2t, const
 extern "C" int b200_mbconv_dw_se(const void* in_hi, const void* in_lo, const float* wt, const float* bias,
                                  const float* w1, const float* b1, const float* w2t, const float* b2,
                                  float* partial_ws, float* s1_ws, float* scale_ws, void* out_hi, void* out_lo, int B,
-                                 int H, int W, int C, int stride, int S, void* stream) {
+                                 int H, int W, int C, int stride, int S, int pad_lo, void* stream) {
   B200_CHECK_ARG(in_hi && in_lo && wt && bias && w1 && b1 && w2t && b2 && partial_ws && s1_ws && scale_ws && out_hi &&
                      out_lo,
                  "mbconv_dw_se: null pointer");
   B200_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2),
                  "mbconv_dw_se: bad arguments (C %% 8 == 0, stride 1|2; got C=%d stride=%d)", C, stride);
   B200_CHECK_ARG(S > 0 && S <= 128 && C <= 12288, "mbconv_dw_se: bad sizes (S <= 128, C <= 12288; got C=%d S=%d)", C, S);
+  B200_CHECK_ARG(pad_lo == 0 || pad_lo == 1, "mbconv_dw_se: pad_lo is 0 (TF 'SAME' at stride 2 on even sizes) or 1");
   cudaStream_t st = (cudaStream_t)stream;
-  const int OH = (H + 2 - 3) / stride + 1, OW = (W + 2 - 3) / stride + 1;
+  const int OH = (H + pad_lo + 1 - 3) / stride + 1, OW = (W + pad_lo + 1 - 3) / stride + 1;
   const int OHW = OH * OW, nPB = (OHW + DWP_PIX - 1) / DWP_PIX;
   dwconv3x3_pool_kernel<<<dim3(nPB, (C + 63) / 64, B), 256, 0, st>>>(
       (const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo, wt, bias, (__nv_bfloat16*)out_hi,
-      (__nv_bfloat16*)out_lo, partial_ws, H, W, C, stride, OH, OW);
+      (__nv_bfloat16*)out_lo, partial_ws, H, W, C, stride, OH, OW, pad_lo);
   se_fc1_kernel<<<dim3((S + FC1_ROWS - 1) / FC1_ROWS, B), 256, (size_t)C * sizeof(float), st>>>(
       partial_ws, w1, b1, s1_ws, C, S, nPB, 1.f / (float)OHW);
   se_fc2_kernel<<<dim3((C + 127) / 128, B), 128, 0, st>>>(s1_ws, w2t, b2, scale_ws, C, S);

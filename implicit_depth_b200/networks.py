@@ -160,8 +160,9 @@ class Plan:
         a0, w0, s0, p0 = segs[0]
         k0 = w0.shape[-1]
         B = a0.B
-        OH = (a0.H + 2 * p0 - k0) // s0 + 1
-        OW = (a0.W + 2 * p0 - k0) // s0 + 1
+        from .conv import out_size
+
+        OH, OW = out_size(a0.H, a0.W, k0, s0, p0)
         if out is None and want_split:
             out = self.act(B, OH, OW, cout)
         if out_f32 is None and want_f32:

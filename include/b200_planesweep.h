@@ -97,7 +97,10 @@ int b200_fv_tc_layout(int K, int* out);
 typedef struct {
   const void* in_hi; /* NHWC bf16 [B,H,W,C], 16-byte aligned, C % 8 == 0 */
   const void* in_lo;
-  int H, W, C, ksize /*1|3*/, stride /*1|2*/, pad;
+  int H, W, C, ksize /*1|3*/, stride /*1|2*/, pad /* top / left */;
+  int pad_hi;        /* bottom / right padding: == pad for torch-style symmetric padding; (pad, pad_hi) = (0, 1) is the
+                        TF "SAME" padding of a stride-2 3x3 conv on an even-sized map (timm tf_efficientnetv2_s,
+                        reference call site experiment_modules/bd_model.py:46-51) */
 } b200_conv_seg;
 typedef struct {
   b200_conv_seg seg[4]; /* K-segments: concatenated inputs and/or the shortcut conv of a BasicBlock */
@@ -149,9 +152,10 @@ int b200_instance_norm_ws_bytes(int B, int C, long long* partial_bytes, long lon
 /* ---- EfficientNetV2 image-prior encoder (reference call site bd_model.py:46-51: timm tf_efficientnetv2_s,
  * features_only; torchvision efficientnet_v2_s layout).  Its dense convolutions run on b200_conv_* (act 4 = SiLU);
  * these are the memory-bound parts of the MBConv blocks, NHWC split-bf16 in and out. ---- */
-/* depthwise 3x3 (stride 1|2, pad 1) + bias (BatchNorm folded) + SiLU; wt [9][C] tap-major fp32. */
+/* depthwise 3x3 (stride 1|2) + bias (BatchNorm folded) + SiLU; wt [9][C] tap-major fp32.  Padding (pad_lo, 1):
+ * pad_lo = 1 is torch's symmetric pad 1, pad_lo = 0 the TF "SAME" padding of a stride-2 conv on an even-sized map. */
 int b200_dwconv3x3_silu(const void* in_hi, const void* in_lo, const float* wt, const float* bias, void* out_hi,
-                        void* out_lo, int B, int H, int W, int C, int stride, void* stream);
+                        void* out_lo, int B, int H, int W, int C, int stride, int pad_lo, void* stream);
 /* SqueezeExcitation: mean over H*W -> fc1 w1 [S][C] + SiLU -> fc2 (transposed: w2t [S][C]) + sigmoid -> x * scale
  * (in place when out == in).  mean_ws / scale_ws: [B,C] fp32.  Deterministic reduction. */
 int b200_squeeze_excite(const void* in_hi, const void* in_lo, const float* w1, const float* b1, const float* w2t,
@@ -164,7 +168,7 @@ int b200_squeeze_excite(const void* in_hi, const void* in_lo, const float* w1, c
 int b200_mbconv_dw_se(const void* in_hi, const void* in_lo, const float* wt, const float* bias, const float* w1,
                       const float* b1, const float* w2t, const float* b2, float* partial_ws, float* s1_ws,
                       float* scale_ws, void* out_hi, void* out_lo, int B, int H, int W, int C, int stride, int S,
-                      void* stream);
+                      int pad_lo /* like b200_dwconv3x3_silu */, void* stream);
 int b200_mbconv_pool_block(void);
 /* out = a + b on split activations of n elements (n % 8 == 0). */
 int b200_split_add(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* out_hi, void* out_lo,

@@ -32,6 +32,10 @@ CASES = [
     (3, 6, 8, [384, 256], 384, 3, 1, "relu", False),  # coarsest level, three N tiles
     (2, 37, 45, [128], 16, 3, 1, "lrelu", False),     # narrow N, ragged size, several items per CTA
     (5, 96, 128, [128], 16, 3, 1, "none", False),     # narrow N, M=256 double tiles on a full grid
+    (2, 24, 32, [256], 256, 3, 1, "lrelu", True),     # cluster split-K x4 with a residual (32 items, 8 patches)
+    (1, 13, 19, [192], 128, 3, 1, "elu", True),       # split-K x2, ragged map: border rows / columns of the slice stores
+    (4, 12, 16, [384, 256], 384, 3, 1, "lrelu", False),  # CVEncoder level 3 at cfg2: 24 items x 4 CTAs
+    (1, 24, 32, [512], 64, 3, 1, "relu", True),       # 64-wide N tile, split-K x8 (8 items, 16 patches), residual
 ]
 
 
