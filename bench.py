@@ -553,9 +553,9 @@ def main_b200(args):
                    "timing": "one CUDA-event bracket around all steps on the compute stream, closed after the last "
                              "NCCL gathers; max over ranks",
                    "cuda_graph": not args.no_graph,
-                   "image_encoder": "EfficientNetV2-S (torchvision layout) on the hand-written conv / MBConv kernels, "
-                                    "fp32-grade split-bf16 like the rest of the forward (cuDNN TF32 would put pred_0 "
-                                    "1.7e-2 off the fp32 reference)"},
+                   "image_encoder": "EfficientNetV2-S in timm's tf_efficientnetv2_s layout (reference keys, TF SAME "
+                                    "padding) on the hand-written conv / MBConv kernels, fp32-grade split-bf16 like the "
+                                    "rest of the forward (cuDNN TF32 would put pred_0 1.7e-2 off the fp32 reference)"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "pipeline": e2e_mode, "plain_pipeline": e2e_plain, "encoder_ahead_pipeline": e2e_ahead,
                 "how": "FramePipeline: one pinned staging buffer per batch -> one H2D copy -> forward reading the device "

@@ -31,9 +31,10 @@ def default_options(**kw):
 
 
 class EffNetV2SFeatures(nn.Module):
-    """Image-prior encoder stand-in with the channel/stride layout of timm's `tf_efficientnetv2_s_in21ft1k`
-    features ([24,48,64,160,256] at /2../32; reference call site bd_model.py:46-51).  Plain torchvision/cuDNN:
-    this module is outside the hand-written hot path by design."""
+    """torchvision-layout EfficientNetV2-S features ([24,48,64,160,256] at /2../32): same layers as the reference's
+    timm encoder but torch-style symmetric padding and `features.N...` keys.  Kept for users who train with
+    torchvision weights (`B200BDModel(opts, encoder=EffNetV2SFeatures())` still runs on the hand-written kernels);
+    the default encoder is `image_encoder.TfEfficientNetV2SFeatures`, whose keys and padding are the reference's."""
 
     TAPS = (1, 2, 3, 5, 6)
 
@@ -88,15 +89,18 @@ class B200BDModel(nn.Module):
         super().__init__()
         opts = default_options() if opts is None else opts
         self.run_opts = opts
-        # the built-in EfficientNetV2-S runs on the hand-written kernels (image_encoder.py); an injected encoder is
-        # called as the PyTorch module it is
-        self.native_image_encoder = encoder is None
+        # EfficientNetV2-S (the built-in timm-layout module, or either layout passed in) runs on the hand-written
+        # kernels (image_encoder.py); any other injected encoder is called as the PyTorch module it is
+        from .image_encoder import TfEfficientNetV2SFeatures
+
         if encoder is not None:
             self.encoder = encoder
         elif "efficientnet" in opts.image_encoder_name:
-            self.encoder = EffNetV2SFeatures()
+            # timm `tf_efficientnetv2_s_in21ft1k` layout (bd_model.py:46-51): released checkpoints load as they are
+            self.encoder = TfEfficientNetV2SFeatures()
         else:
             raise ValueError("Unrecognized option for image encoder type!")
+        self.native_image_encoder = isinstance(self.encoder, (TfEfficientNetV2SFeatures, EffNetV2SFeatures))
         enc_ch = list(self.encoder.num_ch_enc)
         ms = opts.matching_scale
         if opts.cv_encoder_type != "multi_scale_encoder":
@@ -233,8 +237,7 @@ class B200BDModel(nn.Module):
             from .image_encoder import plan_efficientnet_v2_s
 
             encp = Plan(dev)  # image-prior encoder on the conv kernels
-            img_feats = plan_efficientnet_v2_s(encp, self.encoder.features, lambda: slots["cur_image"], B, H, W,
-                                               taps=self.encoder.TAPS)
+            img_feats = plan_efficientnet_v2_s(encp, self.encoder, lambda: slots["cur_image"], B, H, W)
             if self.encoder_ahead:
                 # the encoder is launched apart from the forward: `post` reads copies of its outputs, so the encoder
                 # of the next batch may overwrite its own buffers while this batch is still in the back phase

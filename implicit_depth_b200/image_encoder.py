@@ -3,9 +3,19 @@
 The reference takes its image encoder from timm (`tf_efficientnetv2_s_in21ft1k`, features_only, bd_model.py:46-51; a
 third-party backbone).  cuDNN runs it either in TF32 -- which alone moves `pred_0` 1.7e-2
 away from the fp32 reference, outside the 1e-3 parity budget -- or in strict fp32 at 9.5 ms per batch of four
-frames, longer than the whole rest of the forward.  This module runs the same layers (torchvision `efficientnet_v2_s`
-layout, the stand-in used throughout this repo) on the split-bf16 tensor-core conv kernels (fp32-grade results) plus
-three small MBConv kernels (csrc/mbconv.cu): depthwise 3x3, squeeze-excite, scale.
+frames, longer than the whole rest of the forward.  This module runs the same layers on the split-bf16 tensor-core
+conv kernels (fp32-grade results) plus the small MBConv kernels of csrc/mbconv.cu (depthwise 3x3 with the squeeze
+fused in, excitation, scale).
+
+`TfEfficientNetV2SFeatures` is the parameter container: timm 0.6.12's module tree for `tf_efficientnetv2_s` with
+`features_only=True` (`conv_stem`, `bn1`, `blocks.{stage}.{block}.{conv|conv_exp|conv_pw|conv_dw|se.conv_reduce|...}`),
+so `load_state_dict` takes the `encoder.*` entries of a released checkpoint as they are, and TF "SAME" padding
+(asymmetric (0, 1) for the five stride-2 convolutions on even-sized maps) like timm's `Conv2dSame`.  timm is not
+installed here and its model file is not part of the reference tree: the definition below is restated from the
+published architecture (arch string `cn_r2_k3_s1_e1_c24_skip / er_r4_k3_s2_e4_c48 / er_r4_k3_s2_e4_c64 /
+ir_r6_k3_s2_e4_c128_se0.25 / ir_r9_k3_s1_e6_c160_se0.25 / ir_r15_k3_s2_e6_c256_se0.25`, BatchNorm eps 1e-3, SiLU) and is
+"parity unpinned" against the original package.  The torchvision `efficientnet_v2_s().features[:7]` layout (same
+layers, torch-style symmetric padding) is planned by the same code through `describe_torchvision`.
 
 Channel counts that the conv kernels cannot produce (24, 160, 192, 960: Cout must be a multiple of 16 up to 128 and
 of 128 beyond) are zero-padded; padded channels stay exactly zero through SiLU / depthwise / SE / residuals and the
@@ -13,10 +23,12 @@ consumers' weights are padded with zero columns (`SplitAct.Cl` = logical channel
 """
 from __future__ import annotations
 
-
 import torch
+import torch.nn.functional as F
+from torch import nn
 
 from . import _abi
+from .conv import out_size, same_pad
 from .networks import Plan, _fold_bn
 
 FUSED_DW_SE = True  # False = separate depthwise / pool / fc kernels (kept for the kernel-level tests)
@@ -39,46 +51,59 @@ def _padv(v, n):
     return out
 
 
-def _cna(g: Plan, x, cna, act, stride=1, residual=None):
-    """torchvision Conv2dNormActivation (conv, BatchNorm[, SiLU]) with BN folded, on the conv kernels."""
+def _pad_for(x, k, stride, same):
+    """Padding of a k x k conv on activation `x`: torch-style symmetric k // 2, or TF "SAME"."""
+    return same_pad(x.H, x.W, k, stride) if same else k // 2
+
+
+def _cna(g: Plan, x, cna, act, stride=1, residual=None, same=False):
+    """(conv, BatchNorm) pair [+ activation] with BN folded, on the conv kernels."""
     conv, bn = cna[0], cna[1]
     w, b = _fold_bn(conv.weight, bn)
     cout = conv.out_channels
     cp = pad_ch(cout)
     k = conv.kernel_size[0]
-    y, _ = g.conv([(x, _padw(w.to(g.device), cp, x.C), stride, k // 2)], _padv(b.to(g.device), cp), cp, act=act,
-                  residual=residual)
+    y, _ = g.conv([(x, _padw(w.to(g.device), cp, x.C), stride, _pad_for(x, k, stride, same))],
+                  _padv(b.to(g.device), cp), cp, act=act, residual=residual)
     y.Cl = cout
     return y
 
 
-def _dwconv(g: Plan, x, cna, stride):
+def _dw_pad(x, stride, same):
+    lo, hi = (same_pad(x.H, x.W, 3, stride) if same else (1, 1))
+    assert hi == 1 and lo in (0, 1)
+    return lo
+
+
+def _dwconv(g: Plan, x, cna, stride, same=False):
     conv, bn = cna[0], cna[1]
     w, b = _fold_bn(conv.weight, bn)  # [C, 1, 3, 3]
     C = x.C
     wt = torch.zeros((9, C), dtype=torch.float32, device=g.device)
     wt[:, :w.shape[0]] = w.to(g.device).float().reshape(w.shape[0], 9).t()
     bias = _padv(b.to(g.device), C)
-    OH, OW = (x.H + 2 - 3) // stride + 1, (x.W + 2 - 3) // stride + 1
+    pad_lo = _dw_pad(x, stride, same)
+    OH, OW = out_size(x.H, x.W, 3, stride, (pad_lo, 1))
     y = g.act(x.B, OH, OW, C)
     y.Cl = getattr(x, "Cl", C)
     g._keep += [wt, bias]
     g.add(lambda: _abi.call("b200_dwconv3x3_silu", _abi.ptr(x.hi), _abi.ptr(x.lo), _abi.ptr(wt), _abi.ptr(bias),
-                            _abi.ptr(y.hi), _abi.ptr(y.lo), x.B, x.H, x.W, C, stride, _abi.stream_ptr()),
+                            _abi.ptr(y.hi), _abi.ptr(y.lo), x.B, x.H, x.W, C, stride, pad_lo, _abi.stream_ptr()),
           reads=[x], writes=[y])
     return y
 
 
 def _squeeze_excite(g: Plan, x, se):
-    """torchvision SqueezeExcitation: avgpool -> fc1 -> SiLU -> fc2 -> sigmoid -> scale (in place)."""
-    C, S = x.C, se.fc1.out_channels
-    cl = se.fc1.in_channels
+    """Squeeze-excitation: avgpool -> fc1 -> SiLU -> fc2 -> sigmoid -> scale (in place); `se` = (fc1, fc2) 1x1 convs."""
+    fc1, fc2 = se
+    C, S = x.C, fc1.out_channels
+    cl = fc1.in_channels
     w1 = torch.zeros((S, C), dtype=torch.float32, device=g.device)
-    w1[:, :cl] = se.fc1.weight.detach().to(g.device).float().reshape(S, cl)
-    b1 = se.fc1.bias.detach().to(g.device).float().contiguous()
+    w1[:, :cl] = fc1.weight.detach().to(g.device).float().reshape(S, cl)
+    b1 = fc1.bias.detach().to(g.device).float().contiguous()
     w2 = torch.zeros((S, C), dtype=torch.float32, device=g.device)  # transposed: coalesced over channels
-    w2[:, :cl] = se.fc2.weight.detach().to(g.device).float().reshape(cl, S).t()
-    b2 = _padv(se.fc2.bias.to(g.device), C)
+    w2[:, :cl] = fc2.weight.detach().to(g.device).float().reshape(cl, S).t()
+    b2 = _padv(fc2.bias.to(g.device), C)
     mean = g.empty((x.B, C))
     scale = g.empty((x.B, C))
     g._keep += [w1, b1, w2, b2]
@@ -88,22 +113,24 @@ def _squeeze_excite(g: Plan, x, se):
     return x
 
 
-def _dwconv_se(g: Plan, x, cna, stride, se):
-    """MBConv middle: depthwise 3x3 + BN + SiLU, then SqueezeExcitation, as one chain of four short kernels with the
-    squeeze fused into the depthwise conv (`b200_mbconv_dw_se`)."""
+def _dwconv_se(g: Plan, x, cna, stride, se, same=False):
+    """MBConv middle: depthwise 3x3 + BN + SiLU, then squeeze-excitation, as one chain of four short kernels with the
+    squeeze fused into the depthwise conv (`b200_mbconv_dw_se`); `se` = (fc1, fc2) 1x1 convs."""
     conv, bn = cna[0], cna[1]
+    fc1, fc2 = se
     w, b = _fold_bn(conv.weight, bn)  # [C, 1, 3, 3]
-    C, S, cl = x.C, se.fc1.out_channels, se.fc1.in_channels
+    C, S, cl = x.C, fc1.out_channels, fc1.in_channels
     wt = torch.zeros((9, C), dtype=torch.float32, device=g.device)
     wt[:, :w.shape[0]] = w.to(g.device).float().reshape(w.shape[0], 9).t()
     bias = _padv(b.to(g.device), C)
     w1 = torch.zeros((S, C), dtype=torch.float32, device=g.device)
-    w1[:, :cl] = se.fc1.weight.detach().to(g.device).float().reshape(S, cl)
-    b1 = se.fc1.bias.detach().to(g.device).float().contiguous()
+    w1[:, :cl] = fc1.weight.detach().to(g.device).float().reshape(S, cl)
+    b1 = fc1.bias.detach().to(g.device).float().contiguous()
     w2 = torch.zeros((S, C), dtype=torch.float32, device=g.device)  # transposed: coalesced over channels
-    w2[:, :cl] = se.fc2.weight.detach().to(g.device).float().reshape(cl, S).t()
-    b2 = _padv(se.fc2.bias.to(g.device), C)
-    OH, OW = (x.H + 2 - 3) // stride + 1, (x.W + 2 - 3) // stride + 1
+    w2[:, :cl] = fc2.weight.detach().to(g.device).float().reshape(cl, S).t()
+    b2 = _padv(fc2.bias.to(g.device), C)
+    pad_lo = _dw_pad(x, stride, same)
+    OH, OW = out_size(x.H, x.W, 3, stride, (pad_lo, 1))
     pix = _abi.load().b200_mbconv_pool_block()
     partial = g.empty((x.B, (OH * OW + pix - 1) // pix, C))
     s1 = g.empty((x.B, S))
@@ -113,16 +140,189 @@ def _dwconv_se(g: Plan, x, cna, stride, se):
     g._keep += [wt, bias, w1, b1, w2, b2]
     g.add(lambda: _abi.call("b200_mbconv_dw_se", _abi.ptr(x.hi), _abi.ptr(x.lo), _abi.ptr(wt), _abi.ptr(bias),
                             _abi.ptr(w1), _abi.ptr(b1), _abi.ptr(w2), _abi.ptr(b2), _abi.ptr(partial), _abi.ptr(s1),
-                            _abi.ptr(scale), _abi.ptr(y.hi), _abi.ptr(y.lo), x.B, x.H, x.W, C, stride, S,
+                            _abi.ptr(scale), _abi.ptr(y.hi), _abi.ptr(y.lo), x.B, x.H, x.W, C, stride, S, pad_lo,
                             _abi.stream_ptr()), launches=4, reads=[x], writes=[y])
     return y
 
 
-def plan_efficientnet_v2_s(g: Plan, features, get_image, B, H, W, taps=(1, 2, 3, 5, 6)):
-    """Launch plan of torchvision `efficientnet_v2_s().features[:7]` (stem + 6 stages).  Returns the SplitActs of the
-    tapped stages (channels [24, 48, 64, 160, 256] at /2 .. /32; `.Cl` holds the logical channel count)."""
+# ---- layout-neutral description -------------------------------------------------------------------------------
+# stem: (conv, bn); stages: list of lists of blocks; a block is a dict
+#   kind "conv"  : cna, stride, skip                      one 3x3 conv + BN + SiLU (+ input, added AFTER the activation)
+#   kind "fused" : exp, pwl, stride, skip                 3x3 expand + BN + SiLU -> 1x1 project + BN (+ input)
+#   kind "mb"    : pw, dw, se (fc1, fc2), pwl, stride, skip   1x1 expand -> depthwise 3x3 -> squeeze-excite -> 1x1 project
+def describe_torchvision(features):
+    """torchvision `efficientnet_v2_s().features[:7]` -> (stem, stages, same_padding=False)."""
     from torchvision.models.efficientnet import FusedMBConv, MBConv
 
+    stages = []
+    for si in range(1, len(features)):
+        blocks = []
+        for blk in features[si]:
+            L = blk.block
+            if isinstance(blk, FusedMBConv) and len(L) == 1:
+                blocks.append(dict(kind="conv", cna=(L[0][0], L[0][1]), stride=L[0][0].stride[0], skip=blk.use_res_connect))
+            elif isinstance(blk, FusedMBConv):
+                blocks.append(dict(kind="fused", exp=(L[0][0], L[0][1]), pwl=(L[1][0], L[1][1]),
+                                   stride=L[0][0].stride[0], skip=blk.use_res_connect))
+            elif isinstance(blk, MBConv):
+                blocks.append(dict(kind="mb", pw=(L[0][0], L[0][1]), dw=(L[1][0], L[1][1]), se=(L[2].fc1, L[2].fc2),
+                                   pwl=(L[3][0], L[3][1]), stride=L[1][0].stride[0], skip=blk.use_res_connect))
+            else:
+                raise TypeError(f"unsupported block {type(blk).__name__}")
+        stages.append(blocks)
+    return (features[0][0], features[0][1]), stages, False
+
+
+class _ConvBnAct(nn.Module):
+    """timm `ConvBnAct` ("cn"): conv 3x3 -> BN -> SiLU (+ input when stride 1 and in == out)."""
+
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, 3, stride, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout, eps=1e-3)
+        self.has_skip = stride == 1 and cin == cout
+
+    def forward(self, x):
+        y = F.silu(self.bn1(_conv_same(x, self.conv)))
+        return y + x if self.has_skip else y
+
+
+class _EdgeResidual(nn.Module):
+    """timm `EdgeResidual` ("er", FusedMBConv): conv_exp 3x3 -> bn1 -> SiLU -> conv_pwl 1x1 -> bn2 (+ input)."""
+
+    def __init__(self, cin, cout, stride, exp):
+        super().__init__()
+        self.conv_exp = nn.Conv2d(cin, cin * exp, 3, stride, bias=False)
+        self.bn1 = nn.BatchNorm2d(cin * exp, eps=1e-3)
+        self.conv_pwl = nn.Conv2d(cin * exp, cout, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout, eps=1e-3)
+        self.has_skip = stride == 1 and cin == cout
+
+    def forward(self, x):
+        y = self.bn2(self.conv_pwl(F.silu(self.bn1(_conv_same(x, self.conv_exp)))))
+        return y + x if self.has_skip else y
+
+
+class _SqueezeExcite(nn.Module):
+    """timm `SqueezeExcite`: mean -> conv_reduce -> SiLU -> conv_expand -> sigmoid gate."""
+
+    def __init__(self, chs, rd):
+        super().__init__()
+        self.conv_reduce = nn.Conv2d(chs, rd, 1)
+        self.conv_expand = nn.Conv2d(rd, chs, 1)
+
+    def forward(self, x):
+        s = self.conv_expand(F.silu(self.conv_reduce(x.mean((2, 3), keepdim=True))))
+        return x * torch.sigmoid(s)
+
+
+class _InvertedResidual(nn.Module):
+    """timm `InvertedResidual` ("ir", MBConv): conv_pw 1x1 -> bn1 -> SiLU -> conv_dw 3x3 -> bn2 -> SiLU -> se ->
+    conv_pwl 1x1 -> bn3 (+ input).  The squeeze width is se_ratio x the block's INPUT channels."""
+
+    def __init__(self, cin, cout, stride, exp, se_ratio):
+        super().__init__()
+        mid = cin * exp
+        self.conv_pw = nn.Conv2d(cin, mid, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(mid, eps=1e-3)
+        self.conv_dw = nn.Conv2d(mid, mid, 3, stride, groups=mid, bias=False)
+        self.bn2 = nn.BatchNorm2d(mid, eps=1e-3)
+        self.se = _SqueezeExcite(mid, int(round(cin * se_ratio)))
+        self.conv_pwl = nn.Conv2d(mid, cout, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(cout, eps=1e-3)
+        self.has_skip = stride == 1 and cin == cout
+
+    def forward(self, x):
+        y = F.silu(self.bn1(self.conv_pw(x)))
+        y = F.silu(self.bn2(_conv_same(y, self.conv_dw)))
+        y = self.bn3(self.conv_pwl(self.se(y)))
+        return y + x if self.has_skip else y
+
+
+def _conv_same(x, conv):
+    """timm `Conv2dSame`: TF "SAME" padding computed from the input size, then a padding-free conv."""
+    k, s = conv.kernel_size[0], conv.stride[0]
+    pads = []
+    for n in (x.shape[-1], x.shape[-2]):  # F.pad order: W first
+        total = max((-(-n // s) - 1) * s + k - n, 0)
+        pads += [total // 2, total - total // 2]
+    return F.conv2d(F.pad(x, pads), conv.weight, conv.bias, s, 0, 1, conv.groups)
+
+
+class TfEfficientNetV2SFeatures(nn.Module):
+    """timm 0.6.12 `create_model("tf_efficientnetv2_s_in21ft1k", features_only=True)` (reference call site
+    experiment_modules/bd_model.py:46-51): same module names / state-dict keys, TF "SAME" padding, BatchNorm eps 1e-3.
+    `forward` (plain PyTorch) returns the five feature maps [24, 48, 64, 160, 256] at /2 ... /32; the product runs the
+    same layers through `plan_efficientnet_v2_s`."""
+
+    # (type, repeats, stride, expansion, out channels, se ratio) -- the tf_efficientnetv2_s arch definition
+    ARCH = (("cn", 2, 1, 1, 24, 0.0), ("er", 4, 2, 4, 48, 0.0), ("er", 4, 2, 4, 64, 0.0), ("ir", 6, 2, 4, 128, 0.25),
+            ("ir", 9, 1, 6, 160, 0.25), ("ir", 15, 2, 6, 256, 0.25))
+    TAPS = (0, 1, 2, 4, 5)  # stage outputs returned (feature_info reductions 2, 4, 8, 16, 32)
+
+    def __init__(self):
+        super().__init__()
+        self.conv_stem = nn.Conv2d(3, 24, 3, 2, bias=False)
+        self.bn1 = nn.BatchNorm2d(24, eps=1e-3)
+        stages, cin = [], 24
+        for kind, reps, stride, exp, cout, se in self.ARCH:
+            blocks = []
+            for r in range(reps):
+                st = stride if r == 0 else 1
+                if kind == "cn":
+                    blocks.append(_ConvBnAct(cin, cout, st))
+                elif kind == "er":
+                    blocks.append(_EdgeResidual(cin, cout, st, exp))
+                else:
+                    blocks.append(_InvertedResidual(cin, cout, st, exp, se))
+                cin = cout
+            stages.append(nn.Sequential(*blocks))
+        self.blocks = nn.Sequential(*stages)
+        self.num_ch_enc = [24, 48, 64, 160, 256]
+
+    def forward(self, x):
+        x = F.silu(self.bn1(_conv_same(x, self.conv_stem)))
+        outs = []
+        for i, stage in enumerate(self.blocks):
+            x = stage(x)
+            if i in self.TAPS:
+                outs.append(x)
+        return outs
+
+
+def describe_tf_efficientnetv2(enc):
+    """`TfEfficientNetV2SFeatures` (timm layout) -> (stem, stages, same_padding=True)."""
+    stages = []
+    for stage in enc.blocks:
+        blocks = []
+        for blk in stage:
+            if isinstance(blk, _ConvBnAct):
+                blocks.append(dict(kind="conv", cna=(blk.conv, blk.bn1), stride=blk.conv.stride[0], skip=blk.has_skip))
+            elif isinstance(blk, _EdgeResidual):
+                blocks.append(dict(kind="fused", exp=(blk.conv_exp, blk.bn1), pwl=(blk.conv_pwl, blk.bn2),
+                                   stride=blk.conv_exp.stride[0], skip=blk.has_skip))
+            else:
+                blocks.append(dict(kind="mb", pw=(blk.conv_pw, blk.bn1), dw=(blk.conv_dw, blk.bn2),
+                                   se=(blk.se.conv_reduce, blk.se.conv_expand), pwl=(blk.conv_pwl, blk.bn3),
+                                   stride=blk.conv_dw.stride[0], skip=blk.has_skip))
+        stages.append(blocks)
+    return (enc.conv_stem, enc.bn1), stages, True
+
+
+def describe(encoder):
+    if isinstance(encoder, TfEfficientNetV2SFeatures):
+        return describe_tf_efficientnetv2(encoder)
+    feats = getattr(encoder, "features", encoder)
+    return describe_torchvision(feats)
+
+
+def plan_efficientnet_v2_s(g: Plan, encoder, get_image, B, H, W, taps=None):
+    """Launch plan of the EfficientNetV2-S feature extractor: `encoder` is a `TfEfficientNetV2SFeatures` (timm layout,
+    "SAME" padding) or a torchvision `efficientnet_v2_s().features[:7]` (or a module holding it as `.features`).
+    `taps`: indices of the stages (0-based, after the stem) whose outputs are returned; default = the five feature maps.
+    Returns their SplitActs (channels [24, 48, 64, 160, 256] at /2 .. /32; `.Cl` holds the logical channel count)."""
+    stem, stages, same = describe(encoder)
+    taps = (0, 1, 2, 4, 5) if taps is None else tuple(taps)
     dev = g.device
     img8 = torch.zeros((B, 8, H, W), device=dev, dtype=torch.float32)  # channels 3..7 stay zero
     g._keep.append(img8)
@@ -134,34 +334,28 @@ def plan_efficientnet_v2_s(g: Plan, features, get_image, B, H, W, taps=(1, 2, 3,
         return img8
 
     x = g.from_f32(load, B, 8, H, W)
-    x = _cna(g, x, features[0], "silu", stride=2)
+    x = _cna(g, x, stem, "silu", stride=2, same=same)
     outs = []
-    for si in range(1, len(features)):
-        for blk in features[si]:
+    for si, blocks in enumerate(stages):
+        for blk in blocks:
             inp = x
-            res = inp if blk.use_res_connect else None
-            if isinstance(blk, FusedMBConv):
-                layers = blk.block
-                stride = layers[0][0].stride[0]
-                if len(layers) == 1:  # expand ratio 1: a single 3x3 conv + SiLU
-                    x = _cna(g, inp, layers[0], "silu", stride, residual=None)
-                    if res is not None:  # the residual is added AFTER the activation: not the conv epilogue's order
-                        x = _add(g, x, res)
-                else:
-                    h = _cna(g, inp, layers[0], "silu", stride)
-                    x = _cna(g, h, layers[1], "none", 1, residual=res)
-            elif isinstance(blk, MBConv):
-                layers = blk.block
-                stride = layers[1][0].stride[0]
-                h = _cna(g, inp, layers[0], "silu", 1)
-                if FUSED_DW_SE:
-                    h = _dwconv_se(g, h, layers[1], stride, layers[2])
-                else:
-                    h = _dwconv(g, h, layers[1], stride)
-                    h = _squeeze_excite(g, h, layers[2])
-                x = _cna(g, h, layers[3], "none", 1, residual=res)
+            res = inp if blk["skip"] else None
+            stride = blk["stride"]
+            if blk["kind"] == "conv":  # a single 3x3 conv + SiLU
+                x = _cna(g, inp, blk["cna"], "silu", stride, residual=None, same=same)
+                if res is not None:  # the residual is added AFTER the activation: not the conv epilogue's order
+                    x = _add(g, x, res)
+            elif blk["kind"] == "fused":
+                h = _cna(g, inp, blk["exp"], "silu", stride, same=same)
+                x = _cna(g, h, blk["pwl"], "none", 1, residual=res)
             else:
-                raise TypeError(f"unsupported block {type(blk).__name__}")
+                h = _cna(g, inp, blk["pw"], "silu", 1)
+                if FUSED_DW_SE:
+                    h = _dwconv_se(g, h, blk["dw"], stride, blk["se"], same=same)
+                else:
+                    h = _dwconv(g, h, blk["dw"], stride, same=same)
+                    h = _squeeze_excite(g, h, blk["se"])
+                x = _cna(g, h, blk["pwl"], "none", 1, residual=res)
         if si in taps:
             outs.append(x)
     return outs

@@ -3,17 +3,16 @@ import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from implicit_depth_b200 import synthetic
-from implicit_depth_b200.bd_model import EffNetV2SFeatures
-from implicit_depth_b200.image_encoder import plan_efficientnet_v2_s
+from implicit_depth_b200.image_encoder import TfEfficientNetV2SFeatures, plan_efficientnet_v2_s
 from implicit_depth_b200.networks import Plan
 
 torch.set_grad_enabled(False)
 B, H, W = int(os.environ.get("B", 4)), 384, 512
-enc = EffNetV2SFeatures().eval()
+enc = TfEfficientNetV2SFeatures().eval()
 synthetic.init_model_weights(enc, seed=3)
 img = torch.randn(B, 3, H, W, device="cuda")
 g = Plan("cuda")
-plan_efficientnet_v2_s(g, enc.features, lambda: img, B, H, W, taps=enc.TAPS)
+plan_efficientnet_v2_s(g, enc, lambda: img, B, H, W)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
 

@@ -372,23 +372,27 @@ def test_cfg4_temporal_model_640x480_96_planes_vs_oracle():
         prev_pose = cur_c["cam_T_world_b44"]
 
 
-def test_native_image_encoder_vs_torch_fp32():
-    """EfficientNetV2-S image encoder on the hand-written kernels (image_encoder.py) against the same torchvision
-    module evaluated by torch on the CPU in fp32; zero-padded channels must stay exactly zero."""
+@pytest.mark.parametrize("layout", ["timm_tf_same", "torchvision"])
+def test_native_image_encoder_vs_torch_fp32(layout):
+    """EfficientNetV2-S image encoder on the hand-written kernels (image_encoder.py) against the same module evaluated
+    by torch on the CPU in fp32 -- the timm `tf_efficientnetv2_s` layout with TF "SAME" padding (the reference's
+    encoder, bd_model.py:46-51; even AND odd map sizes: asymmetric (0,1) vs symmetric (1,1) padding at the stride-2
+    convs) and the torchvision layout; zero-padded channels must stay exactly zero."""
     from implicit_depth_b200.bd_model import EffNetV2SFeatures
-    from implicit_depth_b200.image_encoder import plan_efficientnet_v2_s
+    from implicit_depth_b200.image_encoder import TfEfficientNetV2SFeatures, plan_efficientnet_v2_s
     from implicit_depth_b200.networks import Plan
 
-    enc = EffNetV2SFeatures().eval()
+    enc = (TfEfficientNetV2SFeatures() if layout == "timm_tf_same" else EffNetV2SFeatures()).eval()
     synthetic.init_model_weights(enc, seed=3)
     rng = np.random.default_rng(3100)
-    for (B, H, W) in ((2, 96, 128), (1, 192, 256)):
+    shapes = [(2, 96, 128), (1, 192, 256)] + ([(1, 93, 125)] if layout == "timm_tf_same" else [])
+    for (B, H, W) in shapes:
         img = torch.from_numpy(rng.standard_normal((B, 3, H, W)).astype(np.float32))
         with torch.no_grad():
             ref = enc(img)
         g = Plan("cuda")
         slots = {"img": img.cuda()}
-        acts = plan_efficientnet_v2_s(g, enc.features, lambda: slots["img"], B, H, W, taps=enc.TAPS)
+        acts = plan_efficientnet_v2_s(g, enc, lambda: slots["img"], B, H, W)
         g.run()
         torch.cuda.synchronize()
         assert [a.Cl for a in acts] == [24, 48, 64, 160, 256]
@@ -397,6 +401,28 @@ def test_native_image_encoder_vs_torch_fp32():
             assert got.shape[2:] == tuple(r.shape[2:])
             assert rel_err(got[:, :a.Cl], r.numpy()) < TOL
             assert not got[:, a.Cl:].any()
+
+
+def test_timm_keyed_checkpoint_loads_and_mixed_parity_sizes_are_refused():
+    """A state dict with timm's `tf_efficientnetv2_s` key names (what the released checkpoints hold under `encoder.`)
+    loads strictly into the default model; a map whose height and width differ in parity at a stride-2 conv needs
+    different "SAME" padding per axis, which the kernels do not have: refused loudly, never silently mis-padded."""
+    import sys
+
+    from implicit_depth_b200.image_encoder import TfEfficientNetV2SFeatures, plan_efficientnet_v2_s
+    from implicit_depth_b200.networks import Plan
+
+    sys.path.insert(0, f"{GOLDEN}/shims")
+    import timm  # the shim: an independent restatement of the published model definition (tests only)
+
+    theirs = timm.create_model("tf_efficientnetv2_s_in21ft1k", pretrained=False, features_only=True)
+    m = B200BDModel(default_options(image_width=256, image_height=192, matching_num_depth_bins=16))
+    missing, unexpected = m.encoder.load_state_dict(theirs.state_dict(), strict=True)
+    assert not missing and not unexpected
+    assert {k for k in m.state_dict() if k.startswith("encoder.")} == {"encoder." + k for k in theirs.state_dict()}
+    g = Plan("cuda")
+    with pytest.raises(NotImplementedError):
+        plan_efficientnet_v2_s(g, TfEfficientNetV2SFeatures(), lambda: None, 1, 96, 127)
 
 
 @pytest.mark.parametrize("dec_name", ["unet_pp", "skip"])
