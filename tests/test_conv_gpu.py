@@ -175,3 +175,23 @@ def test_maxblurpool_matches_torch(shape):
     got = out.float_nchw().double()
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 32, 24, 96), (1, 96, 128, 8, 32), (1, 12, 16, 64, 256)])
+def test_conv_stride2_tf_same_padding(shape):
+    """TF "SAME" padding (timm `Conv2dSame`, the reference's tf_efficientnetv2_s encoder, bd_model.py:46-51) of a
+    stride-2 3x3 conv on an even-sized map: padding (0, 1) -- nothing at the top / left, one pixel at the bottom /
+    right -- as a shifted TMA box origin; the out-of-bounds column / row is zero-filled by the TMA unit."""
+    B, H, W, C, Cout = shape
+    torch.manual_seed(H + C)
+    x = torch.randn(B, C, H, W, device="cuda")
+    w = torch.randn(Cout, C, 3, 3, device="cuda") / (9 * C) ** 0.5
+    bias = torch.randn(Cout, device="cuda")
+    a = SplitAct.from_nchw_torch(x)
+    out = SplitAct(B, H // 2, W // 2, Cout, "cuda")
+    plan = ConvPlan([(a, 3, 2, (0, 1))], [w], bias, out, B, Cout, act="silu")
+    assert (plan.OH, plan.OW) == (H // 2, W // 2)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = F.silu(F.conv2d(F.pad(a.float_nchw().double(), [0, 1, 0, 1]), w.double(), bias.double(), 2, 0))
+    assert (out.float_nchw().double() - ref).abs().max().item() < 3e-5 * ref.abs().max().item()

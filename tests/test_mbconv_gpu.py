@@ -21,24 +21,25 @@ def _inputs(seed, B, C, H, W, S):
                 w2=r(C, S) / S ** 0.5, b2=0.1 * r(C))
 
 
-def _torch_ref(t, stride):
+def _torch_ref(t, stride, pad_lo=1):
     x = SplitAct.from_nchw_torch(t["x"]).float_nchw()  # what the kernels actually read (hi + lo)
     C = x.shape[1]
-    y = F.silu(F.conv2d(x.double(), t["wd"].double(), t["bd"].double(), stride=stride, padding=1, groups=C))
+    xp = F.pad(x.double(), [pad_lo, 1, pad_lo, 1])  # (1, 1): torch pad 1; (0, 1): TF "SAME" at stride 2, even sizes
+    y = F.silu(F.conv2d(xp, t["wd"].double(), t["bd"].double(), stride=stride, padding=0, groups=C))
     m = y.mean((2, 3))
     s1 = F.silu(m @ t["w1"].double().t() + t["b1"].double())
     sc = torch.sigmoid(s1 @ t["w2"].double().t() + t["b2"].double())
     return (y * sc[:, :, None, None]).float()
 
 
-def _run_fused(t, stride):
+def _run_fused(t, stride, pad_lo=1):
     B, C, H, W = t["x"].shape
     S = t["w1"].shape[0]
     c = lambda v: v.cuda().float().contiguous()
     x = SplitAct.from_nchw_torch(t["x"].cuda())
     wt = c(t["wd"].reshape(C, 9).t())
     bias, w1, b1, w2t, b2 = c(t["bd"]), c(t["w1"]), c(t["b1"]), c(t["w2"].t()), c(t["b2"])
-    OH, OW = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+    OH, OW = (H + pad_lo + 1 - 3) // stride + 1, (W + pad_lo + 1 - 3) // stride + 1
     pix = _abi.load().b200_mbconv_pool_block()
     partial = torch.full((B, (OH * OW + pix - 1) // pix, C), float("nan"), device="cuda")
     s1 = torch.full((B, S), float("nan"), device="cuda")
@@ -46,7 +47,7 @@ def _run_fused(t, stride):
     y = SplitAct(B, OH, OW, C, "cuda")
     _abi.call("b200_mbconv_dw_se", _abi.ptr(x.hi), _abi.ptr(x.lo), _abi.ptr(wt), _abi.ptr(bias), _abi.ptr(w1),
               _abi.ptr(b1), _abi.ptr(w2t), _abi.ptr(b2), _abi.ptr(partial), _abi.ptr(s1), _abi.ptr(scale),
-              _abi.ptr(y.hi), _abi.ptr(y.lo), B, H, W, C, stride, S, _abi.stream_ptr())
+              _abi.ptr(y.hi), _abi.ptr(y.lo), B, H, W, C, stride, S, pad_lo, _abi.stream_ptr())
     torch.cuda.synchronize()
     return y.float_nchw().cpu(), (x, wt, bias, w1, b1, w2t, b2)
 
@@ -62,13 +63,25 @@ def test_mbconv_dw_se_vs_torch(shape):
     assert rel_err(got.numpy(), ref.numpy()) < 2e-5  # fp32 arithmetic + one split-bf16 rounding (2^-17)
 
 
+@pytest.mark.parametrize("shape", [(2, 256, 24, 32, 16), (1, 768, 12, 16, 32), (3, 72, 6, 10, 5)])
+def test_mbconv_dw_se_tf_same_padding_stride2(shape):
+    """TF "SAME" padding of the stride-2 depthwise convs of timm's tf_efficientnetv2_s (stages 3 and 5) on even-sized
+    maps: no padding at the top / left, one pixel at the bottom / right."""
+    B, C, H, W, S = shape
+    t = _inputs(300 + C, B, C, H, W, S)
+    got, _ = _run_fused(t, 2, pad_lo=0)
+    ref = _torch_ref(t, 2, pad_lo=0)
+    assert got.shape == ref.shape == (B, C, H // 2, W // 2)
+    assert rel_err(got.numpy(), ref.numpy()) < 2e-5
+
+
 def test_mbconv_dw_se_matches_separate_kernels_and_is_batch_invariant():
     B, C, H, W, stride, S = 3, 512, 24, 32, 1, 32
     t = _inputs(7, B, C, H, W, S)
     got, (x, wt, bias, w1, b1, w2t, b2) = _run_fused(t, stride)
     y = SplitAct(B, H, W, C, "cuda")
     _abi.call("b200_dwconv3x3_silu", _abi.ptr(x.hi), _abi.ptr(x.lo), _abi.ptr(wt), _abi.ptr(bias), _abi.ptr(y.hi),
-              _abi.ptr(y.lo), B, H, W, C, stride, _abi.stream_ptr())
+              _abi.ptr(y.lo), B, H, W, C, stride, 1, _abi.stream_ptr())
     mean, scale = torch.empty((B, C), device="cuda"), torch.empty((B, C), device="cuda")
     _abi.call("b200_squeeze_excite", _abi.ptr(y.hi), _abi.ptr(y.lo), _abi.ptr(w1), _abi.ptr(b1), _abi.ptr(w2t),
               _abi.ptr(b2), _abi.ptr(mean), _abi.ptr(scale), _abi.ptr(y.hi), _abi.ptr(y.lo), B, H * W, C, S,
@@ -83,9 +96,10 @@ def test_mbconv_dw_se_matches_separate_kernels_and_is_batch_invariant():
 
 def test_mbconv_dw_se_bad_arguments():
     lib = _abi.load()
-    assert lib.b200_mbconv_dw_se(*([None] * 13), 1, 4, 4, 8, 1, 4, None) == -1
+    assert lib.b200_mbconv_dw_se(*([None] * 13), 1, 4, 4, 8, 1, 4, 1, None) == -1
     d = torch.zeros(64, device="cuda")
     p = _abi.ptr(d)
-    assert lib.b200_mbconv_dw_se(*([p] * 13), 1, 4, 4, 12, 1, 4, None) == -1   # C % 8
-    assert lib.b200_mbconv_dw_se(*([p] * 13), 1, 4, 4, 8, 3, 4, None) == -1    # stride
-    assert lib.b200_mbconv_dw_se(*([p] * 13), 1, 4, 4, 8, 1, 200, None) == -1  # S > 128
+    assert lib.b200_mbconv_dw_se(*([p] * 13), 1, 4, 4, 12, 1, 4, 1, None) == -1   # C % 8
+    assert lib.b200_mbconv_dw_se(*([p] * 13), 1, 4, 4, 8, 3, 4, 1, None) == -1    # stride
+    assert lib.b200_mbconv_dw_se(*([p] * 13), 1, 4, 4, 8, 1, 200, 1, None) == -1  # S > 128
+    assert lib.b200_mbconv_dw_se(*([p] * 13), 1, 4, 4, 8, 2, 4, 2, None) == -1    # pad_lo
