@@ -295,7 +295,7 @@ def binary_search_depth(feature_s0, weights, prior=None, iters=12, min_bound=0.5
     return z, pred
 
 
-def sample_prior(rendered_depth, prior_prediction, cam_to_world, prior_world_to_cam, K, invK):
+def sample_prior(rendered_depth, prior_prediction, cam_to_world, prior_world_to_cam, K, invK, return_coords=False):
     """`BDModel.sample_prior`, `experiment_modules/bd_model.py:395-410`: warp the previous prediction into the
     current view through the rendered depth; `F.grid_sample(mode="nearest")` (zeros padding,
     align_corners=False: unnormalise ((g+1)*size-1)/2, round half to even); -1 where rendered depth <= 0
@@ -303,6 +303,7 @@ def sample_prior(rendered_depth, prior_prediction, cam_to_world, prior_world_to_
     B, _, H, W = rendered_depth.shape
     dt = rendered_depth.dtype.type
     out = np.zeros_like(rendered_depth)
+    coords = np.zeros((B, 2, H, W), rendered_depth.dtype)  # un-normalised sample positions (arbiter of rounding flips)
     pix = pixel_grid(H, W, rendered_depth.dtype.type)
     for b in range(B):
         cur_to_prior = prior_world_to_cam[b] @ cam_to_world[b]
@@ -319,7 +320,8 @@ def sample_prior(rendered_depth, prior_prediction, cam_to_world, prior_world_to_
         v = np.where(ok, flat[np.where(ok, ry * W + rx, 0)], dt(0))
         v = np.where(rendered_depth[b].reshape(-1) > 0, v, dt(-1))
         out[b, 0] = v.reshape(H, W)
-    return out
+        coords[b, 0], coords[b, 1] = ix.reshape(H, W), iy.reshape(H, W)
+    return (out, coords) if return_coords else out
 
 
 # --------------------------------------------------------------------------- #

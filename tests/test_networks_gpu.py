@@ -363,9 +363,26 @@ def test_cfg4_temporal_model_640x480_96_planes_vs_oracle():
         ref = ON.bd_forward(sd, enc_cpu, cur_t, src_t, m.run_opts, torch_volume=True)
         assert tuple(out["pred_0"].shape) == (1, 1, 240, 320)
         assert tuple(out["lowest_cost_bhw"].shape) == (1, 120, 160)
-        assert rel_err(out["pred_0"].cpu().numpy(), ref["pred_0"].numpy()) < TOL
+        got, want = out["pred_0"].cpu().numpy(), ref["pred_0"].numpy()
+        same_prior = np.ones(got.shape, bool)
         if prev_pred is not None:
-            assert (cur_c["prior_mask"].cpu().numpy() != ref["prior_mask"].numpy()).mean() < 2e-3
+            # the warped prior is a NEAREST sample (bd_model.py:395-410): a sample position within rounding of a
+            # half-integer may pick the neighbouring texel (like an argmax near-tie); such a pixel's MLP input differs,
+            # so it is judged by the fp64 arbiter of its sample position and left out of the 1e-3 comparison
+            pm_got, pm_ref = cur_c["prior_mask"].cpu().numpy(), ref["prior_mask"].numpy()
+            d64 = lambda k: cur_t[k].double().numpy()
+            _, xy = O.sample_prior(d64("rendered_depth"), d64("prior_prediction"), d64("world_T_cam_b44"),
+                                   d64("prior_cam_T_world"), d64("K_s0_b44"), d64("invK_s0_b44"), return_coords=True)
+            to_half = np.minimum(np.abs(xy[:, 0:1] - np.floor(xy[:, 0:1]) - 0.5), np.abs(xy[:, 1:2] - np.floor(xy[:, 1:2]) - 0.5))
+            flips = pm_got != pm_ref
+            n_flip, n_tie = int(flips.sum()), int((to_half[flips] < 1e-3).sum())
+            record(f"cfg4_temporal/frame{frame}", kind="prior_nearest_sample", pixels=int(flips.size), n_bad=n_flip,
+                   n_at_rounding_boundary=n_tie, worst_dist_to_half_px=float(to_half[flips].max()) if n_flip else 0.0)
+            assert n_flip == n_tie and n_flip < 2e-3 * flips.size
+            same_prior = ~flips
+        e = float(np.abs(got - want)[same_prior].max() / np.abs(want).max())
+        record(f"cfg4_temporal/frame{frame}", kind="pred_0", rel_err=e, rel_err_all_pixels=rel_err(got, want))
+        assert e < TOL
         # carry the state forward exactly like the evaluation loop (sigmoid of the logits, test_bd.py:212-214)
         prev_pred = torch.sigmoid(out["pred_0"])
         prev_pred_ref = prev_pred.cpu()  # same state on both sides: the comparison stays per-frame
