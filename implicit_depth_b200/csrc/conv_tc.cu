@@ -373,6 +373,23 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
       if (items2 < n_sm || 10 * waves1 < 17 * waves2) k.sub = 1;
     }
   }
+  // Split-K over a thread-block cluster (conv_halo.cuh): for layers whose item count leaves most of the machine idle
+  // (12x16 ... 24x32 maps: 16-64 items, each streaming all of its weights through one SM), `ksplit` CTAs share an item.
+  // The split factor depends on the layer's geometry only (items PER IMAGE), never on the batch size: a frame's result
+  // must not depend on what else is in the batch (the sum order changes with the factor).  Sized so that a batch of
+  // four frames fills the machine (4 x items per image x S <= SMs); larger batches run their clusters in waves.
+  k.ksplit = 1;
+  k.total_patches = 0;
+  if (halo && k.NT >= 64) {
+    for (int s = 0; s < d->nseg; ++s) k.total_patches += (d->seg[s].C + 31) / 32;
+    const int per_image = ((d->OW + 7) / 8) * ((d->OH + CVH_ROWS - 1) / CVH_ROWS) * k.n_ntiles;  // M = 128 items
+    for (int S = 8; S >= 2; S >>= 1)
+      if (4 * per_image * S <= n_sm && 2 * S <= k.total_patches && k.NT / S >= 8) {
+        k.ksplit = S;
+        k.sub = 1;
+        break;
+      }
+  }
   const int cw = halo ? 32 : 64;  // channels per K chunk
   for (int s = 0; s < d->nseg; ++s) {
     const b200_conv_seg& sg = d->seg[s];
@@ -466,20 +483,6 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   const int items = k.B * k.tiles_x * k.tiles_y * k.n_ntiles;
   // Split-K over a thread-block cluster (conv_halo.cuh): for layers whose item count leaves most of the machine idle
   // (12x16 ... 24x32 maps: 16-64 items, each streaming all of its weights through one SM), `ksplit` CTAs share an item.
-  k.ksplit = 1;
-  k.total_patches = 0;
-  if (halo) {
-    for (int s = 0; s < d->nseg; ++s) k.total_patches += (d->seg[s].C + 31) / 32;
-    int lim = n_sm;
-    if (d->max_ctas > 0 && lim > d->max_ctas) lim = d->max_ctas;
-    if (k.NT >= 64 && k.sub == 1) {
-      for (int S = 8; S >= 2; S >>= 1)
-        if (items * S <= lim && 2 * S <= k.total_patches && k.NT / S >= 8) {
-          k.ksplit = S;
-          break;
-        }
-    }
-  }
   if (k.ksplit > 1) {
     p->grid = items * k.ksplit;
   } else {

@@ -52,6 +52,7 @@ class FramePipeline:
         frame, which the forward then reads in place."""
         if not isinstance(self.slots[slot], StagedFrame) or self.slots[slot].staging.fields != frame.staging.fields:
             self.slots[slot] = frame.staging.device_frame(self.device)
+            self.s_in.wait_stream(torch.cuda.current_stream(self.device))  # allocation-time work of the caller's stream
         with torch.cuda.stream(self.s_in):
             if self.ev_free[slot] is not None:
                 self.s_in.wait_event(self.ev_free[slot])
@@ -67,6 +68,7 @@ class FramePipeline:
         if not isinstance(self.slots[slot], tuple):
             mk = lambda d: {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in d.items()}
             self.slots[slot] = (mk(cur), mk(src))
+            self.s_in.wait_stream(torch.cuda.current_stream(self.device))
         dcur, dsrc = self.slots[slot]
         with torch.cuda.stream(self.s_in):
             if self.ev_free[slot] is not None:

@@ -112,7 +112,9 @@ class FrameStaging:
     def device_frame(self, device):
         """A device-side slot.  Allocate a few and REUSE them (`pipeline.FramePipeline` keeps two): the forward
         captures one CUDA graph per slot address, so a fresh slot per batch would re-capture every call."""
-        return StagedFrame(self, torch.zeros(self.numel, dtype=torch.float32, device=device))
+        # torch.empty: no fill kernel on the caller's stream that could race with an upload issued on a copy stream
+        # (the alignment gaps between the fields are never read)
+        return StagedFrame(self, torch.empty(self.numel, dtype=torch.float32, device=device))
 
     @staticmethod
     def upload(host_frame, device_frame, stream=None):

@@ -33,7 +33,7 @@ def main():
     keys = ("pred_0", "lowest_cost_bhw", "overall_mask_bhw")
     n_steps = 3
     batches = [synthetic.make_frame_batch(9000 + s, world * BL, K, H, W) for s in range(n_steps)]
-    to_dev = lambda d: {k: torch.from_numpy(v).to(dev) for k, v in d.items()}
+    to_dev = lambda d: {k: (v if torch.is_tensor(v) else torch.from_numpy(v)).to(dev) for k, v in d.items()}
 
     # --- reference: rank 0 runs every global batch alone (the kernels are batch-invariant) -------------------
     full = []
@@ -67,11 +67,16 @@ def main():
         good = True
         for s, res in enumerate(pipe.run(iter(hosts))):
             if rank == 0:
-                good &= all(torch.equal(res[k], full[s][k]) for k in keys)
+                eq = {k: bool(torch.equal(res[k], full[s][k])) for k in keys}
+                good &= all(eq.values())
             elif mode == "root":
+                eq = {"empty": len(res) == 0}
                 good &= (len(res) == 0)
             else:
-                good &= all(tuple(res[k].shape) == (world * BL,) + tuple(probe[k].shape[1:]) for k in keys)
+                eq = {k: tuple(res[k].shape) == (world * BL,) + tuple(probe[k].shape[1:]) for k in keys}
+                good &= all(eq.values())
+            if not all(eq.values()):
+                print(f"[rank {rank}] mode {mode} step {s}: {eq}", file=sys.stderr, flush=True)
         flag = torch.tensor([1 if good else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         ok_plan[mode] = bool(flag.item())

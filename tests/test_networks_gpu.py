@@ -540,3 +540,21 @@ def test_in_place_weight_updates_rebuild_plans_and_graphs():
         fresh.load_state_dict(m.state_dict())
         want = fresh.cuda().eval()("test", c, s, return_mask=True)["pred_0"]
         assert torch.equal(b, want)
+
+
+def test_full_forward_is_invariant_to_batch_size_and_composition():
+    """A frame's outputs must not depend on how many / which other frames share its batch (the reference protects this
+    property by looping its matching encoder, bd_model.py:149-160; here every kernel's reduction order -- including the
+    split-K factor of the low-resolution convs -- is a function of the layer geometry only).  Also what makes the
+    multi-GPU gather equal to a single-GPU run (tests/test_parallel_gpu.py)."""
+    m, _, _ = seeded(image_width=256, image_height=192, matching_num_depth_bins=16)
+    cur, src = synthetic.make_frame_batch(4300, 3, 7, 192, 256)
+    c = {k: torch.from_numpy(v).cuda() for k, v in cur.items()}
+    s = {k: torch.from_numpy(v).cuda() for k, v in src.items()}
+    full = m("test", c, s, return_mask=True)
+    full = {k: v.clone() for k, v in full.items()}
+    for sel in ([1], [2, 0]):
+        part = m("test", {k: v[sel].contiguous() for k, v in c.items()}, {k: v[sel].contiguous() for k, v in s.items()},
+                 return_mask=True)
+        for k in ("pred_0", "lowest_cost_bhw", "overall_mask_bhw"):
+            assert torch.equal(part[k], full[k][sel]), (k, sel)

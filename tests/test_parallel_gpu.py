@@ -52,6 +52,7 @@ def test_two_gpu_gather_equals_single_gpu_outputs():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     line = [l for l in r.stdout.splitlines() if l.startswith("GATHER_OK ")]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-4000:]
+    sys.stderr.write("\n".join(l for l in r.stderr.splitlines() if l.startswith("[rank")) + "\n")
     res = json.loads(line[-1][len("GATHER_OK "):])
     from cases import record
 
