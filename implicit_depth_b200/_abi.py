@@ -22,6 +22,7 @@ SIGNATURES = {
     "b200_feats_to_pixel_major": [c_f, c_f, c_i, c_i, c_i, c_ll, c_ll, c_i, ctypes.c_void_p],
     "b200_volume_argmax": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
     "b200_cv_dot": [c_f] * 7 + [c_i] * 6 + [ctypes.c_void_p],
+    "b200_cv_dot_band": [c_f] * 7 + [c_i] * 6 + [ctypes.c_void_p],
     "b200_fv_mlp_simt": [c_f] * 13 + [c_i] * 7 + [ctypes.c_void_p],
     "b200_fv_mlp_tc": [c_f] * 12 + [c_i] * 7 + [ctypes.c_void_p],
     "b200_fv_tc_wimage_bytes": [c_i],

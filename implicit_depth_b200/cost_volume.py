@@ -106,8 +106,15 @@ class B200CostVolumeManager(nn.Module):
     FEAT_LAYOUT = 0  # gather layout `forward_pixel_major` expects (csrc/common.cuh)
 
     def __init__(self, matching_height, matching_width, num_depth_bins=64, matching_dim_size=None,
-                 num_source_views=None):
+                 num_source_views=None, dot_impl="gather"):
+        """dot_impl: "gather" = per-tap global loads through L1 (csrc/cv_dot.cu; the default: 0.32 ms per B=4 launch at
+        BASELINE cfg2), "band" = source bands staged in shared memory by TMA (csrc/cv_dot_band.cu; 0.65 ms: with 64-byte
+        fp32 texels a 20x20 box is re-used by only 2.5 taps per texel, so the staging traffic exceeds what the hardware L1
+        already saves the gather -- measurements in profiles/r02i_volume_kernels.md).  Same results bit for bit."""
         super().__init__()
+        if dot_impl not in ("band", "gather"):
+            raise ValueError(f"unknown dot_impl {dot_impl!r} (band | gather)")
+        self.dot_impl = dot_impl
         self.num_depth_bins = num_depth_bins
         self.matching_height = matching_height
         self.matching_width = matching_width
@@ -194,8 +201,9 @@ class B200CostVolumeManager(nn.Module):
                                         B, K, D)
         cost = torch.empty((B, D, h, w), device=cur_pm.device, dtype=torch.float32)
         lowest = torch.empty((B, h, w), device=cur_pm.device, dtype=torch.float32)
-        _abi.call("b200_cv_dot", _abi.ptr(cur_pm), _abi.ptr(src_pm), _abi.ptr(cams), _abi.ptr(planes),
-                  _abi.ptr(cost), _abi.ptr(lowest), None, B, K, FEAT_C, h, w, D, _abi.stream_ptr())
+        _abi.call("b200_cv_dot_band" if self.dot_impl == "band" else "b200_cv_dot", _abi.ptr(cur_pm), _abi.ptr(src_pm),
+                  _abi.ptr(cams), _abi.ptr(planes), _abi.ptr(cost), _abi.ptr(lowest), None, B, K, FEAT_C, h, w, D,
+                  _abi.stream_ptr())
         planes_bdhw = planes.view(B, D, 1, 1).expand(B, D, h, w) if depth_planes_bdhw is None else depth_planes_bdhw
         return cost, lowest, planes_bdhw, None
 

@@ -29,7 +29,9 @@ umma_probe_kernel(const float* __restrict__ A, const float* __restrict__ Bm, flo
   uint8_t* a_lo = a_hi + nchunk * 16384;
   uint8_t* b_hi = a_lo + nchunk * 16384;                 // nchunk x [N x 64] bf16
   uint8_t* b_lo = b_hi + nchunk * N * 128;
-  uint8_t* tail = b_lo + nchunk * N * 128;
+  // mode 5 (K = 32: nchunk = 0) lays its own patch / weight tiles out from `base`: keep the barrier and the TMEM slot
+  // behind them (racecheck, profiles/r02h_sanitizer.md: they used to alias the patch that mode 5 zero-fills)
+  uint8_t* tail = (mode == 5) ? base + 16384 + 8192 : b_lo + nchunk * N * 128;
   uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 8);
 
@@ -175,6 +177,7 @@ extern "C" int b200_umma_probe(const float* A, const float* Bm, float* D, int K,
   B200_CHECK_ARG(mode != 4 || K == 64, "umma_probe: mode 4 needs K == 64");
   const int nchunk = K >= 64 ? K / 64 : 1;
   size_t smem = 1024 + (size_t)nchunk * (2 * 16384 + 2 * N * 128) + 64;
+  if (mode == 5) smem = 1024 + 16384 + 8192 + 64;  // patch (16 KB) + weight tile (<= 8 KB) + barrier / TMEM slot
   B200_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, Bm, D, K, N, mode);
   B200_CHECK_LAUNCH("umma_probe");

@@ -59,6 +59,11 @@ int b200_volume_argmax(const float* vol, const float* planes, float* lowest, int
  *   out: cost [B,D,h,w]; lowest [B,h,w] or NULL; best_idx [B,h,w] int32 or NULL. */
 int b200_cv_dot(const float* cur, const float* src, const float* cams, const float* planes, float* cost,
                 float* lowest, int* best_idx, int B, int K, int C, int h, int w, int D, void* stream);
+/* Same contract, same results bit for bit, shared-memory-band version (csrc/cv_dot_band.cu): per (8x8 pixel tile, 4
+ * planes, view) ONE TMA box of 20x20 texel records is staged in shared memory (zero fill = grid_sample's zeros padding)
+ * and the four bilinear taps are LDS.128; iterations whose bounding box does not fit gather from global memory. */
+int b200_cv_dot_band(const float* cur, const float* src, const float* cams, const float* planes, float* cost,
+                     float* lowest, int* best_idx, int B, int K, int C, int h, int w, int D, void* stream);
 
 /* Fused metadata-MLP plane sweep = FeatureVolumeManager.build_cost_volume
  * (modules/cost_volume.py:437-706) / FastFeatureVolumeManager (:938-1146) with the MLP of

@@ -21,9 +21,11 @@ pm = lambda layout: (_pixel_major(t["cur_feats"], B, C, h, w, layout),
                      _pixel_major(t["src_feats"].reshape(B * K, C, h, w), B * K, C, h, w, layout))
 cur_pm, src_pm = pm(0)
 geo = (t["src_extrinsics"], t["src_poses"], t["src_Ks"], t["cur_invK"], mn, mx, None)
-dot = B200CostVolumeManager(h, w, num_depth_bins=D).cuda()
-print("dot manager (layout + prep + kernel) ms:", timeit(lambda: dot(min_depth=mn, max_depth=mx, **t)))
-print("dot pixel-major (prep + kernel) ms:", timeit(lambda: dot.forward_pixel_major(cur_pm, src_pm, *geo, False, B, K, h, w)))
+for dot_impl in ("band", "gather"):
+    dot = B200CostVolumeManager(h, w, num_depth_bins=D, dot_impl=dot_impl).cuda()
+    print(f"dot[{dot_impl}] manager (layout + prep + kernel) ms:", timeit(lambda: dot(min_depth=mn, max_depth=mx, **t)))
+    print(f"dot[{dot_impl}] pixel-major (prep + kernel) ms:",
+          timeit(lambda: dot.forward_pixel_major(cur_pm, src_pm, *geo, False, B, K, h, w)))
 cur_pm, src_pm = pm(1)
 for impl in ("tc", "simt"):
     if impl == "simt" and os.environ.get("NO_SIMT"): continue

@@ -58,13 +58,14 @@ def load_mlp(mgr, g):
             mgr.mlp.net[li].bias.copy_(torch.from_numpy(g[f"mlp_b{i}"]))
 
 
+@pytest.mark.parametrize("dot_impl", ["band", "gather"])
 @pytest.mark.parametrize("name", list(VOLUME_CASES))
-def test_dot_volume_vs_reference_golden(name):
+def test_dot_volume_vs_reference_golden(name, dot_impl):
     seed, B, K, C, h, w, D = VOLUME_CASES[name]
     g = load_golden(name)
     inp = synthetic.make_volume_inputs(seed, B, K, C, h, w)
     t = dev(inp)
-    mgr = B200CostVolumeManager(h, w, num_depth_bins=D).cuda()
+    mgr = B200CostVolumeManager(h, w, num_depth_bins=D, dot_impl=dot_impl).cuda()
     mn, mx = depth_range()
     cost, lowest, planes_bdhw, mask = mgr(min_depth=mn, max_depth=mx, **t)
     assert mask is None and tuple(cost.shape) == (B, D, h, w) and tuple(planes_bdhw.shape) == (B, D, h, w)
@@ -74,7 +75,7 @@ def test_dot_volume_vs_reference_golden(name):
     assert rel_err(cost, g["dot_cost"]) < TOL
     idx = planes_to_idx(lowest, planes)
     np.testing.assert_array_equal(idx, np.argmax(cost, 1))  # kernel argmax == first max of its own volume
-    n_bad, n_near = argmax_exactness(f"dot_volume/{name}", idx, np.argmax(g["dot_cost"], 1),
+    n_bad, n_near = argmax_exactness(f"dot_volume[{dot_impl}]/{name}", idx, np.argmax(g["dot_cost"], 1),
                                      fp64_arbiter(g, "dot_cost_f64", inp, h))
     assert n_bad == n_near, f"{n_bad} argmax mismatches, only {n_near} at fp64 near-ties"
 
@@ -256,3 +257,29 @@ def test_per_frame_depth_range_like_the_reference_broadcast():
                                    O.generate_depth_planes(float(mn[b]), float(mx[b]), D), rtol=1e-6)
     with pytest.raises(ValueError):
         mgr(min_depth=mn[:2], max_depth=mx[:2], **t)
+
+
+@pytest.mark.parametrize("shape", [(4, 7, 96, 128, 64), (2, 8, 37, 53, 10), (1, 1, 9, 7, 1), (1, 3, 120, 160, 96),
+                                   (2, 5, 24, 32, 256)])
+def test_band_kernel_is_bit_identical_to_gather_kernel(shape):
+    """cv_dot_band_kernel (TMA-staged source bands in shared memory) against cv_dot_kernel (per-tap global loads): the
+    same arithmetic in the same order, so cost volume and argmax must agree bit for bit -- at the BASELINE cfg2 / cfg4
+    shapes, ragged maps, one view / one plane, D not a multiple of 4, and with views that leave the frustum (global and
+    skip iterations)."""
+    B, K, h, w, D = shape
+    inp = synthetic.make_volume_inputs(900 + h, B, K, 16, h, w)
+    if K >= 3:  # one view looking backwards (every box off the image), one rotated far enough that boxes do not fit
+        flip = np.diag([-1.0, 1.0, -1.0, 1.0]).astype(np.float32)
+        inp["src_extrinsics"][:, 0] = flip @ inp["src_extrinsics"][:, 0]
+        c, s_ = np.cos(0.6), np.sin(0.6)
+        rot = np.array([[c, -s_, 0, 0.3], [s_, c, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], np.float32)
+        inp["src_extrinsics"][:, 1] = rot @ inp["src_extrinsics"][:, 1]
+    t = dev(inp)
+    mn, mx = depth_range()
+    outs = {}
+    for impl in ("band", "gather"):
+        mgr = B200CostVolumeManager(h, w, num_depth_bins=D, dot_impl=impl).cuda()
+        cost, lowest, _, _ = mgr(min_depth=mn, max_depth=mx, **t)
+        outs[impl] = (cost, lowest)
+    assert torch.equal(outs["band"][0], outs["gather"][0])
+    assert torch.equal(outs["band"][1], outs["gather"][1])
