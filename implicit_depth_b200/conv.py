@@ -23,7 +23,8 @@ class _Desc(ctypes.Structure):
                 ("bias", ctypes.c_void_p), ("res_hi", ctypes.c_void_p), ("res_lo", ctypes.c_void_p),
                 ("out_hi", ctypes.c_void_p), ("out_lo", ctypes.c_void_p), ("out_f32", ctypes.c_void_p),
                 ("B", ctypes.c_int), ("OH", ctypes.c_int), ("OW", ctypes.c_int), ("Cout", ctypes.c_int),
-                ("act", ctypes.c_int), ("slope", ctypes.c_float), ("max_ctas", ctypes.c_int)]
+                ("act", ctypes.c_int), ("slope", ctypes.c_float), ("max_ctas", ctypes.c_int),
+                ("tile_hint", ctypes.c_int)]
 
 
 class SplitAct:
@@ -136,7 +137,7 @@ class ConvPlan:
     """One convolution launch with everything (tensor maps, weight image, buffers) fixed at plan time."""
 
     def __init__(self, segs, weights, bias, out, B, cout, act="none", slope=0.2, residual=None, out_f32=None,
-                 max_ctas=0):
+                 max_ctas=0, tile_hint=0):
         """segs: list of (SplitAct, ksize, stride, pad); `pad` is an int (torch-style symmetric padding) or a pair
         (top/left, bottom/right) -- (0, 1) is the TF "SAME" padding of a stride-2 3x3 conv on an even-sized map;
         weights: one [Cout, C, k, k] fp32 tensor per segment; out: SplitAct or None; residual: SplitAct or None;
@@ -161,6 +162,7 @@ class ConvPlan:
         d.act = ACT[act]
         d.slope = slope
         d.max_ctas = int(max_ctas)
+        d.tile_hint = int(tile_hint)
         lib = _abi.load()
         self.halo = bool(lib.b200_conv_uses_halo(ctypes.byref(d)))  # decides the weight-image layout
         self.nt = int(lib.b200_conv_ntile_for(ctypes.byref(d)))  # N tile of this conv (weight-image layout)

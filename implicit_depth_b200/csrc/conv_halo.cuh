@@ -26,9 +26,16 @@
 // memory, and after a cluster barrier reduces the column slice [r NT/ksplit, (r+1) NT/ksplit) of all partials through
 // distributed shared memory -- in rank order, so the sum is deterministic -- applies bias / residual / activation and
 // stores its slice.  grid = items x ksplit exactly (one item per cluster).
-template <int SUB, int NT /* N tile: 128, 64, or 16 (direct-store epilogue, no residual) */, bool KSPLIT = false>
-__global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvKParams prm) {
+// TWO (SUB = 1, NT = 64): compiled for two resident CTAs per SM (<= 102 registers, half of tensor memory, <= 113 KB of
+// shared memory): while one CTA waits on a barrier, drains an accumulator or runs out of items, the other keeps the
+// tensor pipe busy -- the single-CTA form leaves it idle 60 % of the time on the 64-channel layers
+// (profiles/r02c_conv64_roles.md).
+template <int SUB, int NT /* N tile: 128, 64, or 16 (direct-store epilogue, no residual) */, bool KSPLIT = false,
+          bool TWO = false>
+__global__ void __launch_bounds__(CVH_THREADS, TWO ? 2 : 1) conv_halo_kernel(const __grid_constant__ ConvKParams prm) {
   static_assert(!KSPLIT || (SUB == 1 && NT >= 64), "split-K variant: one M=128 sub-tile, 64- or 128-wide N tile");
+  static_assert(!TWO || (SUB == 1 && NT == 64 && !KSPLIT), "two-CTAs-per-SM variant: M = 128, N = 64");
+  constexpr uint32_t TMEM_COLS = TWO ? 256u : 512u;  // two accumulator sets of SUB * 2 * NT columns
   constexpr int NTC = NT / 64;  // 64-channel store boxes per N tile (0 for the 16-wide tile)
   constexpr int PW = 8 * SUB + 2;
   constexpr uint32_t PATCH_PLANE = (18u * PW * 64u + 1023u) & ~1023u;  // one bf16 plane of a 32-channel patch
@@ -85,7 +92,7 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
     }
     tc::mbar_fence_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -351,53 +358,59 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
       tc::mbar_wait(&acc_full[a], (tile_i >> 1) & 1u);
       tc::fence_after_sync();
       const float* bias_t = bias_s + nt * NT + half * COLS;
+      // The drain is instruction-bound (64 outputs per thread and item on the 64-channel layers): activation and
+      // residual are compile-time cases of ONE body, selected once per item, not tested per element.
+      auto drain = [&](auto act_c, auto res_c) {
+        constexpr int ACT = decltype(act_c)::value;
+        constexpr bool RES = decltype(res_c)::value;
 #pragma unroll
-      for (int sub = 0; sub < SUB; ++sub) {
-        uint8_t* sg = staging + sub * STAGING;
-        if (has_res) tc::mbar_wait(&res_full[sub], tile_i & 1u);
-        const uint32_t t_main = tmem + lane_base + a * ACC_COLS + sub * 2 * NT + half * COLS;
+        for (int sub = 0; sub < SUB; ++sub) {
+          uint8_t* sg = staging + sub * STAGING;
+          if (RES) tc::mbar_wait(&res_full[sub], tile_i & 1u);
+          const uint32_t t_main = tmem + lane_base + a * ACC_COLS + sub * 2 * NT + half * COLS;
 #pragma unroll
-        for (int c0 = 0; c0 < COLS; c0 += 32) {
-          uint32_t rm[32], rc[32];
-          tc::tmem_ld32(t_main + c0, rm);
-          tc::tmem_ld32(t_main + NT + c0, rc);
-          tc::wait_ld();
-          // this thread's 32 channels = 4 chunks of 16 B in the row's 128-byte record of column block `blk`
-          const int col = half * COLS + c0;  // first channel within the N tile
-          const int blk = col >> 6;
-          const int chunk0 = (col & 63) >> 3;
-          uint8_t* row_hi = sg + blk * STAGE_BLK + row * 128;
-          uint8_t* row_lo = sg + (NTC + blk) * STAGE_BLK + row * 128;
+          for (int c0 = 0; c0 < COLS; c0 += 32) {
+            uint32_t rm[32], rc[32];
+            tc::tmem_ld32(t_main + c0, rm);
+            tc::tmem_ld32(t_main + NT + c0, rc);
+            tc::wait_ld();
+            // this thread's 32 channels = 4 chunks of 16 B in the row's 128-byte record of column block `blk`
+            const int col = half * COLS + c0;  // first channel within the N tile
+            const int blk = col >> 6;
+            const int chunk0 = (col & 63) >> 3;
+            uint8_t* row_hi = sg + blk * STAGE_BLK + row * 128;
+            uint8_t* row_lo = sg + (NTC + blk) * STAGE_BLK + row * 128;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t off = ((uint32_t)(chunk0 + q) ^ swz) << 4;
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_t + c0 + 8 * q);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias_t + c0 + 8 * q + 4);
-            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float v[8];
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t off = ((uint32_t)(chunk0 + q) ^ swz) << 4;
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_t + c0 + 8 * q);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_t + c0 + 8 * q + 4);
+              const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              v[j] = (__uint_as_float(rm[8 * q + j]) + __uint_as_float(rc[8 * q + j])) + bv[j];
-            if (has_res) {
-              const uint4 h4 = *reinterpret_cast<const uint4*>(row_hi + off);
-              const uint4 l4 = *reinterpret_cast<const uint4*>(row_lo + off);
-              const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+              for (int j = 0; j < 8; ++j)
+                v[j] = (__uint_as_float(rm[8 * q + j]) + __uint_as_float(rc[8 * q + j])) + bv[j];
+              if (RES) {
+                const uint4 h4 = *reinterpret_cast<const uint4*>(row_hi + off);
+                const uint4 l4 = *reinterpret_cast<const uint4*>(row_lo + off);
+                const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
-                v[2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+                for (int e = 0; e < 4; ++e) {
+                  v[2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+                  v[2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+                }
               }
-            }
-            uint32_t hi[4], lo[4];
+              uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              tc::split2(apply_act(v[2 * e], prm.act, prm.slope), apply_act(v[2 * e + 1], prm.act, prm.slope), hi[e],
-                         lo[e]);
-            *reinterpret_cast<uint4*>(row_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(row_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              for (int e = 0; e < 4; ++e)
+                tc::split2(act_t<ACT>(v[2 * e], prm.slope), act_t<ACT>(v[2 * e + 1], prm.slope), hi[e], lo[e]);
+              *reinterpret_cast<uint4*>(row_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(row_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
           }
         }
-      }
+      };
+      dispatch_act_res(prm.act, has_res, drain);
       // accumulator drained: hand it back to the MMA warp; staging written: publish to the async proxy
       tc::fence_before_sync();
       tc::mbar_arrive(&acc_empty[a]);
@@ -419,7 +432,7 @@ __global__ void __launch_bounds__(CVH_THREADS, 1) conv_halo_kernel(const __grid_
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem, 512);
+  if (warp == 1) tc::tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // shared-memory footprint of the halo kernel for (SUB, NT, stages, n_ntiles)

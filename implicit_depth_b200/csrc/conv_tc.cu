@@ -48,6 +48,7 @@ struct ConvKParams {
   int B, OH, OW, Cout, NT, n_ntiles, act, total_chunks, tiles_x, tiles_y, stages;
   float slope;
   int halo, sub, has_res, tps;
+  int two;                     // halo kernel: two CTAs per SM (SUB = 1, NT = 64)
   int ksplit, total_patches;   // halo kernel, split-K over a cluster of `ksplit` CTAs (1 = off); 32-channel patches per item
   int seg_chunk0[CV_MAX_SEG];  // index of each segment's first chunk in the weight image
 };
@@ -58,6 +59,37 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   if (act == ACT_ELU) return elu1(v);
   if (act == ACT_SILU) return silu(v);
   return v;
+}
+
+#include <type_traits>
+
+// activation with the kind fixed at compile time (apply_act tests it per element)
+template <int ACT>
+__device__ __forceinline__ float act_t(float v, float slope) {
+  if (ACT == ACT_LRELU) return v >= 0.f ? v : v * slope;
+  if (ACT == ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == ACT_ELU) return elu1(v);
+  if (ACT == ACT_SILU) return silu(v);
+  return v;
+}
+// calls f(integral_constant<int, act>, bool_constant<res>): one uniform branch per call instead of one per element
+template <class F>
+__device__ __forceinline__ void dispatch_act_res(int act, bool res, F&& f) {
+#define B200_ACT_CASE(A)                                                          \
+  case A:                                                                         \
+    if (res) f(std::integral_constant<int, A>{}, std::true_type{});               \
+    else f(std::integral_constant<int, A>{}, std::false_type{});                  \
+    break;
+  switch (act) {
+    B200_ACT_CASE(ACT_LRELU)
+    B200_ACT_CASE(ACT_RELU)
+    B200_ACT_CASE(ACT_ELU)
+    B200_ACT_CASE(ACT_SILU)
+    default:
+      if (res) f(std::integral_constant<int, ACT_NONE>{}, std::true_type{});
+      else f(std::integral_constant<int, ACT_NONE>{}, std::false_type{});
+  }
+#undef B200_ACT_CASE
 }
 
 __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvKParams prm) {
@@ -192,49 +224,55 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
       const bool live = (oy < prm.OH) && (ox < prm.OW);
       const size_t pix = ((size_t)b * prm.OH + oy) * prm.OW + ox;
       const int n_base = nt * NT;
-      for (int n0 = 0; n0 < NT; n0 += 16) {
-        uint32_t r[16];
-        tc::tmem_ld16(tmem + lane_base + a * NT + n0, r);
-        tc::wait_ld();
-        if (live) {
-          const int n = n_base + n0;
-          float v[16];
+      // activation / residual as compile-time cases of one body (the drain is instruction-bound)
+      auto drain = [&](auto act_c, auto res_c) {
+        constexpr int ACT = decltype(act_c)::value;
+        constexpr bool RES = decltype(res_c)::value;
+        for (int n0 = 0; n0 < NT; n0 += 16) {
+          uint32_t r[16];
+          tc::tmem_ld16(tmem + lane_base + a * NT + n0, r);
+          tc::wait_ld();
+          if (live) {
+            const int n = n_base + n0;
+            float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (prm.bias ? __ldg(prm.bias + n + j) : 0.f);
-          if (prm.res_hi) {
-            const uint4* rh = reinterpret_cast<const uint4*>(prm.res_hi + pix * prm.Cout + n);
-            const uint4* rl = reinterpret_cast<const uint4*>(prm.res_lo + pix * prm.Cout + n);
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (prm.bias ? __ldg(prm.bias + n + j) : 0.f);
+            if (RES) {
+              const uint4* rh = reinterpret_cast<const uint4*>(prm.res_hi + pix * prm.Cout + n);
+              const uint4* rl = reinterpret_cast<const uint4*>(prm.res_lo + pix * prm.Cout + n);
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const uint4 h4 = __ldg(rh + q), l4 = __ldg(rl + q);
-              const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+              for (int q = 0; q < 2; ++q) {
+                const uint4 h4 = __ldg(rh + q), l4 = __ldg(rl + q);
+                const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[8 * q + 2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
-                v[8 * q + 2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+                for (int e = 0; e < 4; ++e) {
+                  v[8 * q + 2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+                  v[8 * q + 2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+                }
               }
             }
-          }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], prm.act, prm.slope);
-          if (prm.out_hi) {
-            uint32_t hi[8], lo[8];
+            for (int j = 0; j < 16; ++j) v[j] = act_t<ACT>(v[j], prm.slope);
+            if (prm.out_hi) {
+              uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) tc::split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-            uint4* oh = reinterpret_cast<uint4*>(prm.out_hi + pix * prm.Cout + n);
-            uint4* ol = reinterpret_cast<uint4*>(prm.out_lo + pix * prm.Cout + n);
-            oh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            oh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-          }
-          if (prm.out_f32) {
-            float4* of = reinterpret_cast<float4*>(prm.out_f32 + pix * prm.Cout + n);
+              for (int j = 0; j < 8; ++j) tc::split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+              uint4* oh = reinterpret_cast<uint4*>(prm.out_hi + pix * prm.Cout + n);
+              uint4* ol = reinterpret_cast<uint4*>(prm.out_lo + pix * prm.Cout + n);
+              oh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              oh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            }
+            if (prm.out_f32) {
+              float4* of = reinterpret_cast<float4*>(prm.out_f32 + pix * prm.Cout + n);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) of[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              for (int q = 0; q < 4; ++q) of[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
           }
         }
-      }
+      };
+      dispatch_act_res(prm.act, prm.res_hi != nullptr, drain);
       tc::fence_before_sync();
       tc::mbar_arrive(&acc_empty[a]);
     }
@@ -279,6 +317,8 @@ struct b200_conv_desc {
   float slope;
   int max_ctas;  // upper bound on the CTAs of this (persistent) launch, 0 = all SMs: lets the caller keep SMs free
                  // for work on another stream
+  int tile_hint; // halo kernel, 64-wide N tile: 0 = automatic, 1 = M = 128 items with two CTAs per SM, 2 = M = 256 items
+                 // with one CTA per SM (tuning / tests; results do not depend on it)
 };
 
 extern "C" int b200_conv_ntile(int Cout) { return Cout <= 128 ? Cout : 128; }
@@ -371,6 +411,8 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
       const int items1 = d->B * ((d->OW + 7) / 8) * rows * k.n_ntiles;
       const int waves2 = (items2 + n_sm - 1) / n_sm, waves1 = (items1 + n_sm - 1) / n_sm;
       if (items2 < n_sm || 10 * waves1 < 17 * waves2) k.sub = 1;
+      if (d->tile_hint == 1) k.sub = 1;
+      if (d->tile_hint == 2) k.sub = 2;
     }
   }
   // Split-K over a thread-block cluster (conv_halo.cuh): for layers whose item count leaves most of the machine idle
@@ -467,7 +509,16 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
     // overhead per MMA); single taps for the 128-wide tile whose stages would otherwise be 48 KB
     k.tps = (k.NT <= 64) ? 3 : 1;
     int S = 12 / k.tps;
-    while (S > 2 && conv_halo_smem(k.sub, k.NT, S, k.tps, k.n_ntiles) > 227 * 1024) --S;
+    // two CTAs per SM for the 64-channel layers that run M = 128 items on a full grid: half the shared memory each
+    // (measured, profiles/r02k_time_conv.log: once the drain was specialised the one-CTA M = 256 form wins everywhere,
+    // so this form is only taken on request)
+    k.two = (k.NT == 64 && k.sub == 1 && k.ksplit == 1 && d->tile_hint == 1) ? 1 : 0;
+    if (k.two) {
+      k.tps = 1;
+      S = 4;
+    }
+    while (S > 2 && conv_halo_smem(k.sub, k.NT, S, k.tps, k.n_ntiles) > (k.two ? 113 : 227) * 1024) --S;
+    if (k.two && conv_halo_smem(k.sub, k.NT, S, k.tps, k.n_ntiles) > 113 * 1024) k.two = 0;
     k.stages = S;
     p->smem = conv_halo_smem(k.sub, k.NT, S, k.tps, k.n_ntiles);
   } else {
@@ -486,14 +537,12 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   if (k.ksplit > 1) {
     p->grid = items * k.ksplit;
   } else {
-  // Balanced persistent grid: with `rounds` = ceil(items / SMs) items per CTA anyway, ceil(items / rounds) CTAs finish
-  // at the same time as a full grid would (e.g. 768 items: 128 CTAs x 6 instead of 148 CTAs of which 28 do 6 and 120
-  // do 5) and leave the other SMs to kernels of concurrent streams (the launch plans run independent layers side by
-  // side).
   int cap = n_sm;
   if (d->max_ctas > 0 && cap > d->max_ctas) cap = d->max_ctas;
-  const int rounds = (items + cap - 1) / cap;
-  p->grid = (items + rounds - 1) / rounds;
+  if (k.two) cap *= 2;
+  // (a "balanced" grid of ceil(items / rounds) CTAs was tried and loses: 384 items on 128 CTAs x 3 take 55 us, on 148
+  // CTAs 46 us -- the items of the last, partial round run faster on the emptier machine)
+  p->grid = items < cap ? items : cap;
   }
   static bool attr_done = false;
   if (!attr_done) {
@@ -508,6 +557,8 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
       e = cudaFuncSetAttribute(conv_halo_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_halo_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_halo_kernel<1, 64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_halo_kernel<1, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
@@ -556,6 +607,7 @@ extern "C" int b200_conv_run(void* plan, void* stream) {
   else if (p->k.NT == 16 && p->k.sub == 2) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<2, 16>, p->k);
   else if (p->k.NT == 16) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 16>, p->k);
   else if (p->k.sub == 2) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<2, 64>, p->k);
+  else if (p->k.two) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 64, false, true>, p->k);
   else le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 64>, p->k);
   if (le != cudaSuccess) {
     b200_set_error("conv_run: launch failed: %s", cudaGetErrorString(le));

@@ -123,6 +123,7 @@ typedef struct {
   int B, OH, OW, Cout /* %16==0; >128 => %128==0 */, act /*0 none,1 leaky(slope),2 ELU,3 ReLU*/;
   float slope;
   int max_ctas;         /* CTA cap of this persistent launch, 0 = all SMs */
+  int tile_hint;        /* 0 = automatic; 64-channel halo convs: 1 = M=128 items, two CTAs per SM; 2 = M=256 items */
 } b200_conv_desc;
 int b200_conv_ntile(int Cout);
 /* N tile of this particular conv (64 instead of 128 for ring-kernel convs with few M tiles); the weight image must be
