@@ -168,6 +168,7 @@ class B200BDModel(nn.Module):
         return super()._apply(fn, *a, **k)
 
     FRONT_SM_FRACTION = 0.61  # see _front_sm_cap
+    FV_SM_FRACTION = None     # CTA cap of the plane sweep as a fraction of the SMs; None = the front-end cap
 
     def _front_sm_cap(self):
         """CTA cap for the persistent kernels of the matching encoder and the plane sweep while the image encoder
@@ -321,7 +322,8 @@ class B200BDModel(nn.Module):
         mx = torch.tensor(self.run_opts.max_matching_depth, device=cur_image.device).view(1, 1, 1, 1) \
             if not hasattr(self, "_mx") or self._mx.device != cur_image.device else self._mx
         self._mn, self._mx = mn, mx
-        self.cost_volume.max_ctas = st.front_cap
+        self.cost_volume.max_ctas = st.front_cap if (self.FV_SM_FRACTION is None or not st.front_cap) else round(
+            self.FV_SM_FRACTION * torch.cuda.get_device_properties(cur_image.device).multi_processor_count)
         try:
             cost_volume, lowest_cost, _, overall_mask = self.cost_volume.forward_pixel_major(
                 cur_pm, src_pm, src_cam_T_cur_cam, cur_cam_T_src_cam, src_K, cur_invK, mn, mx, None, return_mask, B, K,

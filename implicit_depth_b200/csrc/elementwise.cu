@@ -429,7 +429,7 @@ __device__ __forceinline__ void mbp_load_row(const __nv_bfloat16* ih, const __nv
     }
   }
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 maxblurpool_slide_kernel(const __nv_bfloat16* __restrict__ ih, const __nv_bfloat16* __restrict__ il,
                          __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, int B, int H, int W, int C,
                          int OH, int OW, int oy_lo, int oy_hi) {

@@ -36,13 +36,16 @@ def timeit(n=15):
     ts.sort(); return ts[len(ts) // 2]
 
 
-# front-end CTA cap (matching encoder + plane sweep while the image encoder runs beside them; 0 = no cap)
-CAPS = [int(a) for a in sys.argv[1:]] or [0, 64, 74, 80, 86, 96, 110, 124]
+# front-end CTA cap (matching encoder [+ plane sweep] while the image encoder runs beside them; 0 = no cap) and, after
+# a colon, the plane sweep's own cap: "90" or "90:120"
+SETTINGS = sys.argv[1:] or ["0", "80", "90", "100", "90:110", "90:130", "90:148", "100:148", "110:148"]
 n_sm = torch.cuda.get_device_properties(0).multi_processor_count
-for cap in CAPS:
-    m.FRONT_SM_FRACTION = cap / n_sm
+for spec in SETTINGS:
+    front, _, fv = spec.partition(":")
+    m.FRONT_SM_FRACTION = int(front) / n_sm
+    m.FV_SM_FRACTION = (int(fv) / n_sm) if fv else None
     m._state, m._graphs = {}, {}  # the plans bake the cap
     torch.cuda.synchronize()
     ms = timeit()
-    print(json.dumps({"front_cap": cap, "ms_per_forward": round(ms, 3), "frames_per_s": round(1000.0 * B / ms, 1)}),
-          flush=True)
+    print(json.dumps({"front_cap": int(front), "fv_cap": int(fv) if fv else int(front), "ms_per_forward": round(ms, 3),
+                      "frames_per_s": round(1000.0 * B / ms, 1)}), flush=True)
