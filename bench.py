@@ -33,9 +33,12 @@ WORKLOAD = "cfg2: B=4 per GPU, 512x384, 7 source views, 64 depth planes, implici
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2 (B=4) from the committed `ncu --set full` captures
 # (the cost volume written by either kernel stays in the 126 MB L2 for the consuming kernel, hence ~ the input bytes)
-NCU_SOURCE = "profiles/r01e_ncu_full_volume.md"
-NCU_FV_TC_WARP_INST = 491767150.0  # smsp__inst_executed.sum of fv_tc_kernel<7> at cfg2, B=4 (same capture)
-NCU_DRAM_BYTES = {"fv_tc_kernel": 24.3e6, "cv_dot_kernel": 23.6e6}
+NCU_SOURCE = "profiles/r02n_ncu_volume_conv.md"
+NCU_FV_TC_WARP_INST = 491774956.0  # smsp__inst_executed.sum of fv_tc_kernel<7> at cfg2, B=4 (same capture)
+NCU_DRAM_BYTES = {"fv_tc_kernel": 24.3e6, "cv_dot_kernel": 23.7e6}
+# l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed of cv_dot_kernel in that capture (312 us launch):
+# the unit that actually limits the gather, together with the L2 -> SM fabric
+NCU_CV_DOT_LSU_PCT = 55.75
 
 
 def parse():
@@ -495,7 +498,9 @@ def main_b200(args):
         l1_peak = n_sm * 128.0 * sm_mhz * 1e6 / 1e9
         roofline_dot["secondary_bound"] = {"what": "gathered bytes through the L1 data pipe (128 B/clk/SM)",
                                            "peak_GBps": l1_peak,
-                                           "frac": roofline_dot["secondary_gather_GBps"] / l1_peak}
+                                           "frac": roofline_dot["secondary_gather_GBps"] / l1_peak,
+                                           "ncu_lsu_wavefronts_pct_of_peak": NCU_CV_DOT_LSU_PCT,
+                                           "ncu_source": NCU_SOURCE}
     except Exception:
         pass
 
