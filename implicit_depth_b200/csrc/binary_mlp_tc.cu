@@ -11,14 +11,18 @@
 //            the depth and prior columns of W1 are rank-1 terms added in fp32 by the row threads
 //   layer 2  H1 re-split by the row threads into TENSOR MEMORY (A operand) x W2 (smem) -> same accumulator
 //   layer 3  dot with w3 in registers; planes mode stores the logit, search mode updates the bisection bounds.
-// Two row groups (2 x 128 threads, thread = pixel = TMEM lane) ping-pong so one group's MMAs overlap the
-// other's ELU / split work; warp 8 issues all MMAs, warp 9 is the TMA producer.
+// Two row groups ping-pong so one group's MMAs overlap the other's ELU / split work.  A group is 8 warps: a pixel
+// (= TMEM lane) is shared by TWO threads, each owning 64 of the 128 hidden channels (warps w and w+4 of a group read
+// the same TMEM lane quarter), so 16 row warps hide the SFU / TMEM latencies of the two epilogues; the halves of the
+// layer-3 dot product meet through shared memory.  Warp 16 issues all MMAs, warp 17 is the TMA producer.
 // TMEM (512 columns): group g: accumulator [256g, 256g+128), H1 operand [256g+128, 256g+256) (64 hi | 64 lo).
 #include "common.cuh"
 #include "tc.cuh"
 #include "tmap.cuh"
 
-#define BM_THREADS 320
+#define BM_THREADS 576
+#define BM_MMA_WARP 16
+#define BM_TMA_WARP 17
 #define BM_ROWS 128
 #define BM_FEAT_C 64
 
@@ -42,7 +46,7 @@ struct BmSync {
   uint64_t feat_full, feat_empty, acc1_full, h_full, acc2_full, acc_free;
 };
 
-template <bool SEARCH>
+template <bool SEARCH, bool PRIOR>
 __global__ void __launch_bounds__(BM_THREADS, 1) binary_mlp_tc_kernel(const __grid_constant__ BmParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -50,8 +54,11 @@ __global__ void __launch_bounds__(BM_THREADS, 1) binary_mlp_tc_kernel(const __gr
   uint8_t* w1_lo = base + 16384;
   uint8_t* w2 = base + 32768;             // chunk c: hi at w2 + c*32768, lo at +16384
   uint8_t* feat = base + 98304;           // group g: hi at feat + g*32768, lo at +16384
-  float* vec_s = reinterpret_cast<float*>(base + 163840);  // [6][128]
-  BmSync* sync = reinterpret_cast<BmSync*>(vec_s + 6 * 128);
+  float4* e1_s = reinterpret_cast<float4*>(base + 163840);  // [64] {b1[c], w_d[c], b1[c+1], w_d[c+1]}, c = 2i
+  float4* e2_s = e1_s + 64;                                 // [64] {b2[c], w3[c], b2[c+1], w3[c+1]}
+  float2* wp_s = reinterpret_cast<float2*>(e2_s + 64);      // [64] {w_p[c], w_p[c+1]}
+  float* part_s = reinterpret_cast<float*>(wp_s + 64);      // [2 groups][2 parities][2 halves][128] layer-3 partials
+  BmSync* sync = reinterpret_cast<BmSync*>(part_s + 1024);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sync + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -61,22 +68,29 @@ __global__ void __launch_bounds__(BM_THREADS, 1) binary_mlp_tc_kernel(const __gr
 
   for (int i = tid; i < 98304 / 16; i += BM_THREADS)
     reinterpret_cast<uint4*>(base)[i] = __ldg(reinterpret_cast<const uint4*>(prm.wimage) + i);
-  for (int i = tid; i < 6 * 128; i += BM_THREADS) vec_s[i] = prm.vecs[i];
-  if (warp == 8) {
+  if (tid < 64) {
+    const float* v = prm.vecs;
+    const int c = 2 * tid;
+    e1_s[tid] = make_float4(v[c], v[128 + c], v[c + 1], v[128 + c + 1]);
+    e2_s[tid] = make_float4(v[384 + c], v[512 + c], v[384 + c + 1], v[512 + c + 1]);
+    wp_s[tid] = make_float2(v[256 + c], v[256 + c + 1]);
+  }
+  const float b3v = __ldg(prm.vecs + 640);
+  if (warp == BM_MMA_WARP) {
     tc::tmem_alloc(tmem_slot, 512);
     if (lane == 0) {
       for (int g = 0; g < 2; ++g) {
         tc::mbar_init(&sync[g].feat_full, 1);
         tc::mbar_init(&sync[g].feat_empty, 1);
         tc::mbar_init(&sync[g].acc1_full, 1);
-        tc::mbar_init(&sync[g].h_full, 128);
+        tc::mbar_init(&sync[g].h_full, 256);
         tc::mbar_init(&sync[g].acc2_full, 1);
-        tc::mbar_init(&sync[g].acc_free, 128);
+        tc::mbar_init(&sync[g].acc_free, 256);
       }
       tc::mbar_fence_init();
     }
   }
-  if (warp == 9 && lane == 0) {
+  if (warp == BM_TMA_WARP && lane == 0) {
     tc::prefetch_tmap(&prm.map_hi);
     tc::prefetch_tmap(&prm.map_lo);
   }
@@ -86,20 +100,15 @@ __global__ void __launch_bounds__(BM_THREADS, 1) binary_mlp_tc_kernel(const __gr
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 8) {
-    // =============================== row groups: thread = pixel = TMEM lane ===============================
-    const int g = warp >> 2;
-    const int row = tid & 127;
+  if (warp < 16) {
+    // =============================== row groups: two threads per pixel (= TMEM lane) ======================
+    const int g = warp >> 3;
+    const int quarter = warp & 3, ch = (warp >> 2) & 1;  // TMEM lane quarter; which 64 hidden channels
+    const int row = quarter * 32 + lane;
     BmSync* gs = &sync[g];
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const uint32_t acc = tmem + lane_base + g * 256;
     const uint32_t a_op = acc + 128;
-    const float* b1_s = vec_s;
-    const float* wd_s = vec_s + 128;
-    const float* wp_s = vec_s + 256;
-    const float* b2_s = vec_s + 384;
-    const float* w3_s = vec_s + 512;
-    const float b3v = vec_s[640];
     uint32_t n = 0;  // evaluation steps done so far by this group (barrier parity)
     for (long long t = blockIdx.x * 2 + g; t < n_tiles; t += G) {
       const long long pix = t * BM_ROWS + row;
@@ -107,7 +116,7 @@ __global__ void __launch_bounds__(BM_THREADS, 1) binary_mlp_tc_kernel(const __gr
       const long long pc = live ? pix : prm.npix - 1;
       const int b = (int)(pc / prm.HW), pin = (int)(pc - (long long)b * prm.HW);
       float pr = 0.f;
-      if (prm.use_prior) pr = prm.prior ? __ldg(prm.prior + (size_t)b * prm.HW + pin) : -1.f;  // bd_model.py:433-434
+      if (PRIOR) pr = prm.prior ? __ldg(prm.prior + (size_t)b * prm.HW + pin) : -1.f;  // bd_model.py:433-434
       float lo = prm.lo0, hi = prm.hi0, z = prm.z0, logit = 0.f;
       for (int s = 0; s < steps; ++s, ++n) {
         if (!SEARCH) z = __ldg(prm.depth + ((size_t)b * prm.P + s) * prm.HW + pin);
@@ -115,43 +124,54 @@ __global__ void __launch_bounds__(BM_THREADS, 1) binary_mlp_tc_kernel(const __gr
         tc::mbar_wait(&gs->acc1_full, n & 1u);
         tc::fence_after_sync();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
           uint32_t r[32];
-          tc::tmem_ld32(acc + 32 * q, r);
+          tc::tmem_ld32(acc + 64 * ch + 32 * q, r);
           tc::wait_ld();
           uint32_t h[16], l[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int c = 32 * q + 2 * j;
-            float v0 = __uint_as_float(r[2 * j]) + fmaf(wd_s[c], z, b1_s[c]);
-            float v1 = __uint_as_float(r[2 * j + 1]) + fmaf(wd_s[c + 1], z, b1_s[c + 1]);
-            if (prm.use_prior) {
-              v0 = fmaf(wp_s[c], pr, v0);
-              v1 = fmaf(wp_s[c + 1], pr, v1);
+            const int i = 32 * ch + 16 * q + j;  // channel pair
+            const float4 e = e1_s[i];
+            float v0 = __uint_as_float(r[2 * j]) + fmaf(e.y, z, e.x);
+            float v1 = __uint_as_float(r[2 * j + 1]) + fmaf(e.w, z, e.z);
+            if (PRIOR) {
+              const float2 w = wp_s[i];
+              v0 = fmaf(w.x, pr, v0);
+              v1 = fmaf(w.y, pr, v1);
             }
             tc::split2(elu1(v0), elu1(v1), h[j], l[j]);
           }
-          tc::tmem_st16(a_op + 16 * q, h);
-          tc::tmem_st16(a_op + 64 + 16 * q, l);
+          tc::tmem_st16(a_op + 32 * ch + 16 * q, h);
+          tc::tmem_st16(a_op + 64 + 32 * ch + 16 * q, l);
         }
         tc::wait_st();
         tc::fence_before_sync();
         tc::mbar_arrive(&gs->h_full);
-        // ---- epilogue 2: logit = w3 . elu(acc + b2) + b3 ----
+        // ---- epilogue 2: logit = w3 . elu(acc + b2) + b3; each thread sums its 64 channels ----
         tc::mbar_wait(&gs->acc2_full, n & 1u);
         tc::fence_after_sync();
         float o = 0.f;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
           uint32_t r[32];
-          tc::tmem_ld32(acc + 32 * q, r);
+          tc::tmem_ld32(acc + 64 * ch + 32 * q, r);
           tc::wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o = fmaf(elu1(__uint_as_float(r[j]) + b2_s[32 * q + j]), w3_s[32 * q + j], o);
+          for (int j = 0; j < 16; ++j) {
+            const float4 e = e2_s[32 * ch + 16 * q + j];
+            o = fmaf(elu1(__uint_as_float(r[2 * j]) + e.x), e.y, o);
+            o = fmaf(elu1(__uint_as_float(r[2 * j + 1]) + e.z), e.w, o);
+          }
         }
         tc::fence_before_sync();
         tc::mbar_arrive(&gs->acc_free);
-        logit = o + b3v;
+        // the two halves of the dot product meet in shared memory (double-buffered by step parity: the barrier of
+        // step n+1 orders these reads before the writes of step n+2); both threads form the same sum
+        float* part = part_s + ((g * 2 + (n & 1u)) * 2) * 128;
+        part[ch * 128 + row] = o;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+        logit = (part[row] + part[128 + row]) + b3v;
         if (SEARCH) {
           // bd_model.py:281-291: visible = sigmoid(pred) < threshold(z); max_bound[visible] = z; min_bound[~visible] = z
           float thr = 0.5f;
@@ -163,16 +183,16 @@ __global__ void __launch_bounds__(BM_THREADS, 1) binary_mlp_tc_kernel(const __gr
           const bool visible = (1.f / (1.f + expf(-logit))) < thr;
           if (visible) hi = z; else lo = z;
           z = (hi + lo) / 2.f;
-        } else if (live) {
+        } else if (live && ch == 0) {
           prm.pred[((size_t)b * prm.P + s) * prm.HW + pin] = logit;
         }
       }
-      if (SEARCH && live) {
+      if (SEARCH && live && ch == 0) {
         prm.pred[(size_t)b * prm.HW + pin] = logit;
         prm.search[(size_t)b * prm.HW + pin] = z;
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == BM_MMA_WARP) {
     // =============================== MMA issuer (whole warp loops, one elected lane issues) ==========
     constexpr uint32_t IDESC = tc::idesc_bf16_f32(128, 128);
     long long t_cur[2];
@@ -251,7 +271,7 @@ __global__ void __launch_bounds__(BM_THREADS, 1) binary_mlp_tc_kernel(const __gr
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+  if (warp == BM_MMA_WARP) tc::tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -270,7 +290,7 @@ struct b200_binary_mlp_desc {
   int use_prior;
 };
 
-static const size_t BM_SMEM = 1024 + 163840 + 6 * 128 * 4 + 2 * sizeof(BmSync) + 16;
+static const size_t BM_SMEM = 1024 + 163840 + 2 * 64 * 16 + 64 * 8 + 1024 * 4 + 2 * sizeof(BmSync) + 16;
 
 extern "C" int b200_binary_mlp_create(const b200_binary_mlp_desc* d, void** plan_out) {
   B200_CHECK_ARG(d && plan_out, "binary_mlp_create: null pointer");
@@ -307,10 +327,11 @@ extern "C" int b200_binary_mlp_create(const b200_binary_mlp_desc* d, void** plan
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   const long long n_tiles = (d->npix + BM_ROWS - 1) / BM_ROWS;
   p->grid = (int)((n_tiles + 1) / 2 < n_sm ? (n_tiles + 1) / 2 : n_sm);
-  cudaError_t e = cudaFuncSetAttribute(binary_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)BM_SMEM);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(binary_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BM_SMEM);
+  cudaError_t e = cudaSuccess;
+  const void* kernels[4] = {(const void*)binary_mlp_tc_kernel<false, false>, (const void*)binary_mlp_tc_kernel<false, true>,
+                            (const void*)binary_mlp_tc_kernel<true, false>, (const void*)binary_mlp_tc_kernel<true, true>};
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+    e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BM_SMEM);
   if (e != cudaSuccess) {
     delete p;
     b200_set_error("binary_mlp_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -329,7 +350,10 @@ extern "C" int b200_binary_mlp_planes(void* plan, const float* depth, int P, con
   k.prior = prior;
   k.pred = pred;
   k.P = P;
-  binary_mlp_tc_kernel<false><<<p->grid, BM_THREADS, BM_SMEM, (cudaStream_t)stream>>>(k);
+  if (k.use_prior)
+    binary_mlp_tc_kernel<false, true><<<p->grid, BM_THREADS, BM_SMEM, (cudaStream_t)stream>>>(k);
+  else
+    binary_mlp_tc_kernel<false, false><<<p->grid, BM_THREADS, BM_SMEM, (cudaStream_t)stream>>>(k);
   B200_CHECK_LAUNCH("binary_mlp_planes");
   return 0;
 }
@@ -352,7 +376,10 @@ extern "C" int b200_binary_mlp_search(void* plan, const float* prior, int iters,
   k.thr_bins = thr_bins;
   k.thr_vals = thr_vals;
   k.n_thr = thr_bins ? n_thr : 0;
-  binary_mlp_tc_kernel<true><<<p->grid, BM_THREADS, BM_SMEM, (cudaStream_t)stream>>>(k);
+  if (k.use_prior)
+    binary_mlp_tc_kernel<true, true><<<p->grid, BM_THREADS, BM_SMEM, (cudaStream_t)stream>>>(k);
+  else
+    binary_mlp_tc_kernel<true, false><<<p->grid, BM_THREADS, BM_SMEM, (cudaStream_t)stream>>>(k);
   B200_CHECK_LAUNCH("binary_mlp_search");
   return 0;
 }
