@@ -118,8 +118,13 @@ __global__ void __launch_bounds__(BM_THREADS, 1) binary_mlp_tc_kernel(const __gr
       float pr = 0.f;
       if (PRIOR) pr = prm.prior ? __ldg(prm.prior + (size_t)b * prm.HW + pin) : -1.f;  // bd_model.py:433-434
       float lo = prm.lo0, hi = prm.hi0, z = prm.z0, logit = 0.f;
+      const float* zp = SEARCH ? nullptr : prm.depth + (size_t)b * prm.P * prm.HW + pin;
+      float z_next = SEARCH ? 0.f : __ldg(zp);
       for (int s = 0; s < steps; ++s, ++n) {
-        if (!SEARCH) z = __ldg(prm.depth + ((size_t)b * prm.P + s) * prm.HW + pin);
+        if (!SEARCH) {  // the plane depth of the NEXT step is fetched now: a DRAM miss hides under this step
+          z = z_next;
+          if (s + 1 < steps) z_next = __ldg(zp + (size_t)(s + 1) * prm.HW);
+        }
         // ---- epilogue 1: H1 = elu(acc + b1 + w_d z + w_p prior) -> split -> TMEM A operand ----
         tc::mbar_wait(&gs->acc1_full, n & 1u);
         tc::fence_after_sync();

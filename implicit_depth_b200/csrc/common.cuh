@@ -64,13 +64,27 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 
 __device__ __forceinline__ float leaky(float x, float slope) { return x >= 0.f ? x : x * slope; }
 
-// ELU(alpha = 1).  exp through the SFU (ex2.approx, 2^-22 relative) minus one: absolute error < 3e-7 on values of
-// order one, far inside the 1e-3 parity budget, at 3 instructions instead of expm1f's ~50.
-__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
+// SFU exponential / reciprocal with flush-to-zero: ONE MUFU each.  (`__expf` / `__fdividef` without -use_fast_math
+// compile to the non-ftz forms, whose denormal range handling costs ~5 extra predicated instructions per call -- half
+// of the binary MLP's instruction stream before this.)  ex2.approx: 2^-22 relative error.
+__device__ __forceinline__ float exp_fast(float v) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
+  return e;
+}
+__device__ __forceinline__ float rcp_fast(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+// ELU(alpha = 1): exp through the SFU minus one: absolute error < 3e-7 on values of order one, far inside the 1e-3
+// parity budget, at 4 instructions instead of expm1f's ~50.
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : exp_fast(v) - 1.f; }
 
 // SiLU x * sigmoid(x) (EfficientNetV2 image encoder): SFU exp and reciprocal, relative error ~1e-6.
-__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
-__device__ __forceinline__ float sigmoidf_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+__device__ __forceinline__ float silu(float v) { return v * rcp_fast(1.f + exp_fast(-v)); }
+__device__ __forceinline__ float sigmoidf_fast(float v) { return rcp_fast(1.f + exp_fast(-v)); }
 
 // Projection of the pixel-centre ray through plane depth zd into one source view.
 // Mp = M @ (x+.5, y+.5, 1); returns source pixel coords and clamped depth
