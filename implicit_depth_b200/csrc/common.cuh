@@ -62,7 +62,7 @@ void b200_set_error(const char* fmt, ...);
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-__device__ __forceinline__ float leaky(float x, float slope) { return x >= 0.f ? x : x * slope; }
+__device__ __forceinline__ float leaky(float x, float slope) { return fmaxf(x, x * slope); }  // 0 < slope < 1
 
 // SFU exponential / reciprocal with flush-to-zero: ONE MUFU each.  (`__expf` / `__fdividef` without -use_fast_math
 // compile to the non-ftz forms, whose denormal range handling costs ~5 extra predicated instructions per call -- half

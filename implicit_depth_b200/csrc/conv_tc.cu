@@ -54,7 +54,7 @@ struct ConvKParams {
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
-  if (act == ACT_LRELU) return v >= 0.f ? v : v * slope;
+  if (act == ACT_LRELU) return fmaxf(v, v * slope);  // slope in [0, 1], checked at plan creation
   if (act == ACT_RELU) return fmaxf(v, 0.f);
   if (act == ACT_ELU) return elu1(v);
   if (act == ACT_SILU) return silu(v);
@@ -66,7 +66,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 // activation with the kind fixed at compile time (apply_act tests it per element)
 template <int ACT>
 __device__ __forceinline__ float act_t(float v, float slope) {
-  if (ACT == ACT_LRELU) return v >= 0.f ? v : v * slope;
+  if (ACT == ACT_LRELU) return fmaxf(v, v * slope);
   if (ACT == ACT_RELU) return fmaxf(v, 0.f);
   if (ACT == ACT_ELU) return elu1(v);
   if (ACT == ACT_SILU) return silu(v);
@@ -385,6 +385,8 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   B200_CHECK_ARG(d->wimage && (d->out_hi || d->out_f32), "conv_create: missing weights or output");
   B200_CHECK_ARG((d->out_hi == nullptr) == (d->out_lo == nullptr), "conv_create: out_hi/out_lo must come together");
   B200_CHECK_ARG((d->res_hi == nullptr) == (d->res_lo == nullptr), "conv_create: res_hi/res_lo must come together");
+  B200_CHECK_ARG(d->act != ACT_LRELU || (d->slope >= 0.f && d->slope <= 1.f),
+                 "conv_create: leaky-ReLU slope must be in [0, 1] (got %g)", (double)d->slope);
   EncodeTiledFn enc = get_encode();
   B200_CHECK_ARG(enc != nullptr, "conv_create: cuTensorMapEncodeTiled not available from the driver");
   ConvPlan* p = new ConvPlan();
