@@ -25,7 +25,7 @@
 #include "tc.cuh"
 #include "tmap.cuh"
 
-#define CV_THREADS 192
+#define CV_THREADS 320  // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue (two per TMEM lane quarter)
 #define CV_TH 8
 #define CV_TW 16
 #define CV_MAX_SEG 4
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(&acc_full[a], 1);
-      tc::mbar_init(&acc_empty[a], 128);
+      tc::mbar_init(&acc_empty[a], 256);
     }
     tc::mbar_fence_init();
   }
@@ -206,8 +206,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
       }
     }
   } else {
-    // =========================== epilogue (warps 2..5) ===========================
-    const int quarter = warp & 3;
+    // =========================== epilogue (warps 2..9) ===========================
+    // a pixel (= TMEM lane) is drained by two threads: warps w and w + 4 read the same lane quarter and take the even /
+    // the odd 16-channel chunks of the tile (1x1 and strided layers are drain-bound: few MMAs per output value)
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     uint32_t tile_i = 0;
@@ -228,15 +230,24 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
       auto drain = [&](auto act_c, auto res_c) {
         constexpr int ACT = decltype(act_c)::value;
         constexpr bool RES = decltype(res_c)::value;
-        for (int n0 = 0; n0 < NT; n0 += 16) {
+        for (int n0 = 16 * half; n0 < NT; n0 += 32) {
+          const int n = n_base + n0;
+          float4 bv[4];  // bias of the chunk: four 16-byte loads issued before the TMEM read is waited for
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            bv[q] = prm.bias ? __ldg(reinterpret_cast<const float4*>(prm.bias + n) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
           uint32_t r[16];
           tc::tmem_ld16(tmem + lane_base + a * NT + n0, r);
           tc::wait_ld();
           if (live) {
-            const int n = n_base + n0;
             float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (prm.bias ? __ldg(prm.bias + n + j) : 0.f);
+            for (int q = 0; q < 4; ++q) {
+              v[4 * q] = __uint_as_float(r[4 * q]) + bv[q].x;
+              v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bv[q].y;
+              v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bv[q].z;
+              v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bv[q].w;
+            }
             if (RES) {
               const uint4* rh = reinterpret_cast<const uint4*>(prm.res_hi + pix * prm.Cout + n);
               const uint4* rl = reinterpret_cast<const uint4*>(prm.res_lo + pix * prm.Cout + n);
@@ -385,6 +396,7 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   B200_CHECK_ARG(d->wimage && (d->out_hi || d->out_f32), "conv_create: missing weights or output");
   B200_CHECK_ARG((d->out_hi == nullptr) == (d->out_lo == nullptr), "conv_create: out_hi/out_lo must come together");
   B200_CHECK_ARG((d->res_hi == nullptr) == (d->res_lo == nullptr), "conv_create: res_hi/res_lo must come together");
+  B200_CHECK_ARG(((uintptr_t)d->bias & 15) == 0, "conv_create: bias must be 16-byte aligned");
   B200_CHECK_ARG(d->act != ACT_LRELU || (d->slope >= 0.f && d->slope <= 1.f),
                  "conv_create: leaky-ReLU slope must be in [0, 1] (got %g)", (double)d->slope);
   EncodeTiledFn enc = get_encode();
