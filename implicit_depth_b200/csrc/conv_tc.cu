@@ -49,6 +49,7 @@ struct ConvKParams {
   float slope;
   int halo, sub, has_res, tps;
   int two;                     // halo kernel: two CTAs per SM (SUB = 1, NT = 64)
+  int staged;                  // plain kernel: coalesced stores through a per-warp shared-memory transpose (NT 64 / 128)
   int ksplit, total_patches;   // halo kernel, split-K over a cluster of `ksplit` CTAs (1 = off); 32-channel patches per item
   int seg_chunk0[CV_MAX_SEG];  // index of each segment's first chunk in the weight image
 };
@@ -104,6 +105,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
   uint64_t* acc_full = empty + S;    // [2]
   uint64_t* acc_empty = acc_full + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint4* stage_out = reinterpret_cast<uint4*>(
+      (reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~uintptr_t(127));  // [8 warps][256] uint4 (staged stores)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m_tiles = prm.B * prm.tiles_y * prm.tiles_x;
@@ -283,7 +286,81 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
           }
         }
       };
-      dispatch_act_res(prm.act, prm.res_hi != nullptr, drain);
+      // Staged drain (NT = 64 / 128, split-bf16 output only): the thread owns NT/2 CONTIGUOUS channels of its pixel and
+      // drains them in rounds of 32.  A direct store puts every lane's 16 bytes into a different 128-byte line (pixel
+      // stride = Cout * 2 bytes): 32 L1 tags per instruction, which bounded the 1x1 layers.  Here the warp transposes
+      // its 32 pixels x 4 16-byte pieces per plane through shared memory (XOR-swizzled, conflict-free) so that 4 lanes
+      // write one pixel's contiguous 64 bytes: 8 lines per store instruction.
+      auto drain_staged = [&](auto act_c, auto res_c) {
+        constexpr int ACT = decltype(act_c)::value;
+        constexpr bool RES = decltype(res_c)::value;
+        const int nch = NT >> 1;                       // channels per thread: 32 or 64
+        uint4* st_hi = stage_out + (warp - 2) * 256;   // [32 pixels][4 pieces]
+        uint4* st_lo = st_hi + 128;
+        const int sw = (lane >> 1) & 3;
+        for (int rd = 0; rd < (nch >> 5); ++rd) {
+          const int c_base = n_base + half * nch + 32 * rd;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int n = c_base + 16 * c;
+            float4 bv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              bv[q] = prm.bias ? __ldg(reinterpret_cast<const float4*>(prm.bias + n) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t r[16];
+            tc::tmem_ld16(tmem + lane_base + a * NT + half * nch + 32 * rd + 16 * c, r);
+            tc::wait_ld();
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              v[4 * q] = __uint_as_float(r[4 * q]) + bv[q].x;
+              v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bv[q].y;
+              v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bv[q].z;
+              v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bv[q].w;
+            }
+            if (RES && live) {
+              const uint4* rh = reinterpret_cast<const uint4*>(prm.res_hi + pix * prm.Cout + n);
+              const uint4* rl = reinterpret_cast<const uint4*>(prm.res_lo + pix * prm.Cout + n);
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const uint4 h4 = __ldg(rh + q), l4 = __ldg(rl + q);
+                const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[8 * q + 2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+                  v[8 * q + 2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+                }
+              }
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              tc::split2(act_t<ACT>(v[2 * j], prm.slope), act_t<ACT>(v[2 * j + 1], prm.slope), hi[j], lo[j]);
+            st_hi[lane * 4 + ((2 * c) ^ sw)] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            st_hi[lane * 4 + ((2 * c + 1) ^ sw)] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            st_lo[lane * 4 + ((2 * c) ^ sw)] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            st_lo[lane * 4 + ((2 * c + 1) ^ sw)] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          }
+          __syncwarp();
+          const int u = lane & 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int pp = j * 8 + (lane >> 2);
+            const int prow = quarter * 32 + pp;
+            const int poy = ty * CV_TH + (prow >> 4), pox = tx * CV_TW + (prow & 15);
+            const int slot = pp * 4 + (u ^ ((pp >> 1) & 3));
+            const uint4 wh = st_hi[slot], wl = st_lo[slot];
+            if (poy < prm.OH && pox < prm.OW) {
+              const size_t o = (((size_t)b * prm.OH + poy) * prm.OW + pox) * prm.Cout + c_base + 8 * u;
+              *reinterpret_cast<uint4*>(prm.out_hi + o) = wh;
+              *reinterpret_cast<uint4*>(prm.out_lo + o) = wl;
+            }
+          }
+          __syncwarp();
+        }
+      };
+      if (prm.staged) dispatch_act_res(prm.act, prm.res_hi != nullptr, drain_staged);
+      else dispatch_act_res(prm.act, prm.res_hi != nullptr, drain);
       tc::fence_before_sync();
       tc::mbar_arrive(&acc_empty[a]);
     }
@@ -539,11 +616,12 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
     k.tiles_x = (d->OW + CV_TW - 1) / CV_TW;
     k.tiles_y = (d->OH + CV_TH - 1) / CV_TH;
     const size_t stage_bytes = 32768 + (((size_t)k.NT * 256 + 1023) & ~(size_t)1023);
-    int S = (int)((200 * 1024) / stage_bytes);
+    int S = (int)((192 * 1024) / stage_bytes);
     if (S > 6) S = 6;
     if (S > k.total_chunks) S = k.total_chunks < 2 ? 2 : k.total_chunks;
     k.stages = S;
-    p->smem = 1024 + S * stage_bytes + (2 * S + 4) * 8 + 16;
+    k.staged = (k.NT == 64 || k.NT == 128) && d->out_hi != nullptr && d->out_f32 == nullptr;
+    p->smem = 1024 + S * stage_bytes + (2 * S + 4) * 8 + 16 + 128 + 8 * 256 * 16;  // + store staging, 4 KB per drain warp
   }
   const int items = k.B * k.tiles_x * k.tiles_y * k.n_ntiles;
   // Split-K over a thread-block cluster (conv_halo.cuh): for layers whose item count leaves most of the machine idle
