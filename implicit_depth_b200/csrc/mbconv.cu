@@ -5,8 +5,9 @@
 //   se_pool_kernel     squeeze: per-(frame, channel) mean over the image, deterministic two-level reduction
 //   se_fc_kernel       excitation: fc1 + SiLU + fc2 + sigmoid -> scale[b, c]  (fc2 weights transposed)
 //   se_scale_kernel    x * scale[b, c]
-//   dwconv3x3_pool_kernel / se_fc1_kernel / se_fc2_kernel   the same chain with the squeeze fused into the depthwise
-//                      conv and the excitation spread over many blocks (b200_mbconv_dw_se: what the encoder plan uses)
+//   dwconv3x3_pool_kernel / se_fc1_kernel / se_fc2_scale_kernel   the same chain in three launches: squeeze fused into
+//                      the depthwise conv, fc1 spread over many blocks, fc2 + sigmoid + scale fused (b200_mbconv_dw_se:
+//                      what the encoder plan uses)
 // The 1x1 expand / project convolutions and the fused 3x3 convolutions run on the tensor-core conv kernels.
 #include <cuda_bf16.h>
 
@@ -381,6 +382,52 @@ se_fc2_kernel(const float* __restrict__ s1, const float* __restrict__ w2t, const
   }
 }
 
+// fc2 + sigmoid + scale in one launch: block = (strip of SEF_PIX pixels, 64 channels, frame).  The block first forms the
+// 64 scales of its channels (4 threads per channel over interleaved quarters of the squeeze vector, summed in a fixed
+// order), then multiplies its strip in place.  Re-computing the 64 x S dot products per strip is cheaper than a launch.
+#define SEF_PIX 128
+__global__ void __launch_bounds__(256)
+se_fc2_scale_kernel(const float* __restrict__ s1, const float* __restrict__ w2t, const float* __restrict__ b2,
+                    __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ xl, int HW, int C, int S) {
+  __shared__ float s1s[128];
+  __shared__ float red[4][64];
+  __shared__ float scale_s[64];
+  const int b = blockIdx.z, c0 = blockIdx.y * 64;
+  if (threadIdx.x < S) s1s[threadIdx.x] = s1[(size_t)b * S + threadIdx.x];
+  __syncthreads();
+  {
+    const int cl = threadIdx.x & 63, part = threadIdx.x >> 6;
+    const int c = c0 + cl;
+    float acc = 0.f;
+    if (c < C) {
+#pragma unroll 8
+      for (int j = part; j < S; j += 4) acc = fmaf(__ldg(w2t + (size_t)j * C + c), s1s[j], acc);
+    }
+    red[part][cl] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < 64 && c0 + threadIdx.x < C) {
+    const int cl = threadIdx.x;
+    scale_s[cl] = sigmoidf_fast(((red[0][cl] + red[1][cl]) + (red[2][cl] + red[3][cl])) + b2[c0 + cl]);
+  }
+  __syncthreads();
+  const int c8 = threadIdx.x & 7, prow = threadIdx.x >> 3;
+  const int c = c0 + c8 * 8;
+  if (c >= C) return;
+  float sc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sc[e] = scale_s[c8 * 8 + e];
+  const int p_end = min((int)(blockIdx.x + 1) * SEF_PIX, HW);
+  for (int p = blockIdx.x * SEF_PIX + prow; p < p_end; p += 32) {
+    const size_t off = ((size_t)b * HW + p) * C + c;
+    float v[8];
+    mb_load8(xh, xl, off, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= sc[e];
+    mb_store8(xh, xl, off, v);
+  }
+}
+
 // Depthwise 3x3 (+ folded BatchNorm bias, SiLU) followed by the squeeze-and-excitation of one MBConv block
 // (torchvision MBConv.block[1:3]): out = dw(x) * sigmoid(fc2(silu(fc1(mean_hw(dw(x)))))).
 //   wt [9][C], bias [C]; w1 [S][C], b1 [S], w2t [S][C], b2 [C] (fp32, S <= 128);
@@ -404,12 +451,9 @@ extern "C" int b200_mbconv_dw_se(const void* in_hi, const void* in_lo, const flo
       (__nv_bfloat16*)out_lo, partial_ws, H, W, C, stride, OH, OW, pad_lo);
   se_fc1_kernel<<<dim3((S + FC1_ROWS - 1) / FC1_ROWS, B), 256, (size_t)C * sizeof(float), st>>>(
       partial_ws, w1, b1, s1_ws, C, S, nPB, 1.f / (float)OHW);
-  se_fc2_kernel<<<dim3((C + 127) / 128, B), 128, 0, st>>>(s1_ws, w2t, b2, scale_ws, C, S);
-  const size_t total = (size_t)B * OHW * (C / 8);
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  se_scale_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)out_hi, (const __nv_bfloat16*)out_lo, scale_ws,
-                                         (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, B, OHW, C);
+  (void)scale_ws;  // (the scales live in shared memory of the fused fc2 + scale kernel)
+  se_fc2_scale_kernel<<<dim3((OHW + SEF_PIX - 1) / SEF_PIX, (C + 63) / 64, B), 256, 0, st>>>(
+      s1_ws, w2t, b2, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, OHW, C, S);
   B200_CHECK_LAUNCH("mbconv_dw_se");
   return 0;
 }
