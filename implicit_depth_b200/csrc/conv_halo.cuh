@@ -154,6 +154,9 @@ __global__ void __launch_bounds__(CVH_THREADS, TWO ? 2 : 1) conv_halo_kernel(con
     constexpr uint32_t IDESC_MERGED = tc::idesc_bf16_f32(128, 2 * NT);
     constexpr uint32_t IDESC_HI = tc::idesc_bf16_f32(128, NT);
     constexpr uint32_t SBO = PW * 64u;
+    const bool leader = tc::elect_one();  // the one issuing lane (every commit must come from the lane that issued)
+    const uint64_t a_base = tc::smem_desc_sw64(tc::smem_u32(patch0), SBO);
+    const uint64_t b_base = tc::smem_desc_sw64(tc::smem_u32(bring));
     uint32_t pit = 0, tile_i = 0;
     uint32_t bst = 0, bround = 0;
     for (int item = item0; item < items; item += item_step, ++tile_i) {
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(CVH_THREADS, TWO ? 2 : 1) conv_halo_kernel(con
           const uint32_t pb = pit & 1u;
           tc::mbar_wait(&p_full[pb], (pit >> 1) & 1u);
           tc::fence_after_sync();
-          const uint32_t pa = tc::smem_u32(patch0 + (size_t)pb * 2u * PATCH_PLANE);
+          const uint64_t a_slot = a_base + (uint64_t)(pb * (2u * PATCH_PLANE >> 4));
           const int ksteps = (min(32, C - cb * 32) + 15) >> 4;
           const int ntaps = ks * ks;
           int dy = (ks == 3) ? 0 : 1, dx = (ks == 3) ? 0 : 1;
@@ -182,14 +185,15 @@ __global__ void __launch_bounds__(CVH_THREADS, TWO ? 2 : 1) conv_halo_kernel(con
             tc::mbar_wait(&b_full[st], bround & 1u);
             if (++bst == (uint32_t)S) { bst = 0; ++bround; }
             tc::fence_after_sync();
-            const uint32_t sb = tc::smem_u32(bring) + st * (TPS * B_BYTES);
-            if (tc::elect_one()) {
+            // descriptors by addition: the start-address field (bytes >> 4) of a pre-built descriptor never carries
+            const uint64_t b0 = b_base + (uint64_t)(st * (TPS * (B_BYTES >> 4)));
+            const uint64_t a0 = a_slot + (uint64_t)((dy * PW + dx) * 4);
+            if (leader) {
               for (int t = 0; t < nt_g; ++t) {
-                const uint64_t b_m = tc::smem_desc_sw64(sb + t * B_BYTES);
-                const uint32_t row0 = (uint32_t)(dy * PW + dx + t) * 64u;  // a group never crosses a kernel row
+                const uint64_t b_m = b0 + (uint64_t)(t * (B_BYTES >> 4));
 #pragma unroll
                 for (int sub = 0; sub < SUB; ++sub) {  // sub-tile 1 sits 8 pixel records = 512 B to the right
-                  const uint64_t a_hi = tc::smem_desc_sw64(pa + row0 + sub * 512u, SBO);
+                  const uint64_t a_hi = a0 + (uint64_t)(t * 4 + sub * 32);  // a group never crosses a kernel row
                   const uint64_t a_lo = a_hi + (PATCH_PLANE >> 4);
                   const uint32_t d = acc + sub * 2 * NT;
                   // hi*hi -> columns [0,NT), hi*lo -> columns [NT,2NT): one N = 2*NT instruction per k-step
@@ -202,17 +206,15 @@ __global__ void __launch_bounds__(CVH_THREADS, TWO ? 2 : 1) conv_halo_kernel(con
               }
               tc::mma_commit(&b_empty[st]);
             }
-            __syncwarp();
             first = 0;
             dx += nt_g;
             if (dx >= 3) { dx = 0; ++dy; }
           }
-          if (tc::elect_one()) tc::mma_commit(&p_empty[pb]);
-          __syncwarp();
+          if (leader) tc::mma_commit(&p_empty[pb]);
           ++pit;
         }
       }
-      if (tc::elect_one()) tc::mma_commit(&acc_full[a]);
+      if (leader) tc::mma_commit(&acc_full[a]);
       __syncwarp();
     }
     if (KSPLIT) { tc::cluster_sync(); tc::cluster_sync(); }

@@ -36,6 +36,9 @@ CASES = [
     (1, 13, 19, [192], 128, 3, 1, "elu", True),       # split-K x2, ragged map: border rows / columns of the slice stores
     (4, 12, 16, [384, 256], 384, 3, 1, "lrelu", False),  # CVEncoder level 3 at cfg2: 24 items x 4 CTAs
     (1, 24, 32, [512], 64, 3, 1, "relu", True),       # 64-wide N tile, split-K x8 (8 items, 16 patches), residual
+    (2, 13, 19, [96], 128, 1, 1, "elu", True),        # plain kernel, staged (transposed) stores: ragged map, residual
+    (1, 11, 21, [40], 64, 1, 1, "relu", False),       # plain kernel, staged stores with the 64-wide N tile
+    (2, 21, 27, [64], 256, 3, 2, "lrelu", False),     # stride 2, two staged N tiles, ragged output (11 x 14)
 ]
 
 
