@@ -596,10 +596,12 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
   if (halo) {
     k.tiles_x = (d->OW + 8 * k.sub - 1) / (8 * k.sub);
     k.tiles_y = (d->OH + CVH_ROWS - 1) / CVH_ROWS;
-    // weight stages: a whole kernel row (3 taps) per barrier round for the 64-wide N tile (halves the issue-loop
-    // overhead per MMA); single taps for the 128-wide tile whose stages would otherwise be 48 KB
-    k.tps = (k.NT <= 64) ? 3 : 1;
-    int S = 12 / k.tps;
+    // weight stages: a whole kernel row (3 taps) per barrier round.  The tensor pipe queues only a few MMAs, so the
+    // ~200-300 cycles the issuing warp spends between two rounds (barrier check, ring bookkeeping) are mostly idle
+    // pipe time: fewer, longer rounds win even when the ring gets shallower (128-wide tile: 2 stages of 48 KB instead
+    // of 7 of 16 KB measured 5-9 % faster on the three-segment layers, profiles/r02u_time_conv.log)
+    k.tps = 3;
+    int S = 4;
     // two CTAs per SM for the 64-channel layers that run M = 128 items on a full grid: half the shared memory each
     // (measured, profiles/r02k_time_conv.log: once the drain was specialised the one-CTA M = 256 form wins everywhere,
     // so this form is only taken on request)
