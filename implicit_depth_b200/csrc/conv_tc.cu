@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
   if (warp == 0) {
     {
       // =========================== TMA producer (whole warp loops, one elected lane issues) ===========
-      uint32_t it = 0;  // global chunk counter -> stage ring
+      const bool leader = tc::elect_one();
+      uint32_t stage = 0, round = 0;  // stage ring position / wrap count
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int nt = item % prm.n_ntiles;
         const int mt = item / prm.n_ntiles;
@@ -151,19 +152,17 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
             const int dy = tap / ks, dx = tap % ks;
             const int x0 = (tx * CV_TW) * st + dx - pd;
             const int y0 = (ty * CV_TH) * st + dy - pd;
-            for (int cb = 0; cb < cblocks; ++cb, ++it) {
-              const int stage = it % S;
-              const uint32_t round = it / S;
+            for (int cb = 0; cb < cblocks; ++cb) {
               if (round > 0) tc::mbar_wait(&empty[stage], (round - 1) & 1u);
               uint8_t* sa = base + (size_t)stage * stage_bytes;
-              if (tc::elect_one()) {
+              if (leader) {
                 tc::mbar_expect_tx(&full[stage], 32768u + b_bytes);
                 tc::tma_load_4d(sa, &prm.maps[2 * s], cb * 64, x0, y0, b, &full[stage]);
                 tc::tma_load_4d(sa + 16384, &prm.maps[2 * s + 1], cb * 64, x0, y0, b, &full[stage]);
                 tc::bulk_load(sa + 32768, wsrc, b_bytes, &full[stage]);
               }
-              __syncwarp();
               wsrc += b_bytes;
+              if (++stage == (uint32_t)S) { stage = 0; ++round; }
             }
           }
         }
@@ -173,7 +172,13 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
     {
       // =========================== MMA issuer (whole warp loops, one elected lane issues) ============
       const uint32_t idesc = tc::idesc_bf16_f32(128, NT);
-      uint32_t it = 0, tile_i = 0;
+      // (ring position kept incrementally, descriptors by addition to a pre-built base, one issuing lane for the whole
+      // loop and no per-round warp sync: the tensor pipe queues only a few MMAs, so every cycle between the last MMA
+      // of a round and the first of the next is idle pipe time -- see the halo kernel)
+      const bool leader = tc::elect_one();
+      const uint64_t a_base = tc::smem_desc_sw128(tc::smem_u32(base));
+      const uint32_t stage_units = stage_bytes >> 4;
+      uint32_t stage = 0, phase = 0, tile_i = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_i) {
         const uint32_t a = tile_i & 1u;
         const uint32_t use = tile_i >> 1;  // how often accumulator a was used before
@@ -186,25 +191,22 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
           const int C = prm.seg_C[s];
           const int cblocks = (C + 63) >> 6;
           for (int tap = 0; tap < taps; ++tap) {
-            for (int cb = 0; cb < cblocks; ++cb, ++it) {
-              const int stage = it % S;
-              tc::mbar_wait(&full[stage], (it / S) & 1u);
+            for (int cb = 0; cb < cblocks; ++cb) {
+              tc::mbar_wait(&full[stage], phase);
               tc::fence_after_sync();
-              const uint32_t sa = tc::smem_u32(base + (size_t)stage * stage_bytes);
-              const uint32_t sb = sa + 32768u;
               const int ksteps = (min(64, C - cb * 64) + 15) >> 4;
-              if (tc::elect_one()) {
-                const uint64_t a_hi = tc::smem_desc_sw128(sa), b_hi = tc::smem_desc_sw128(sb);
+              if (leader) {
+                const uint64_t a_hi = a_base + (uint64_t)(stage * stage_units), b_hi = a_hi + (32768u >> 4);
                 tc::mma_split_ss_n(ksteps, acc, a_hi, a_hi + (16384u >> 4), b_hi, b_hi + (((uint32_t)NT * 128u) >> 4),
                                    idesc, first);
                 tc::mma_commit(&empty[stage]);
               }
-              __syncwarp();
               first = 0;
+              if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; }
             }
           }
         }
-        if (tc::elect_one()) tc::mma_commit(&acc_full[a]);
+        if (leader) tc::mma_commit(&acc_full[a]);
         __syncwarp();
       }
     }
