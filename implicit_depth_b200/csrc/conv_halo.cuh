@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(CVH_THREADS, TWO ? 2 : 1) conv_halo_kernel(con
 
   if (warp == 0) {
     // =========================== TMA producer (whole warp loops, one elected lane issues) ===========
+    const bool leader = tc::elect_one();  // one issuing lane for the whole loop, no per-step warp sync
     uint32_t pit = 0;                 // patch counter
     uint32_t bst = 0, bround = 0;     // weight-stage ring position / wrap count
     for (int item = item0; item < items; item += item_step) {
@@ -123,12 +124,11 @@ __global__ void __launch_bounds__(CVH_THREADS, TWO ? 2 : 1) conv_halo_kernel(con
           const uint32_t pb = pit & 1u, round = pit >> 1;
           if (round > 0) tc::mbar_wait(&p_empty[pb], (round - 1) & 1u);
           uint8_t* pa = patch0 + (size_t)pb * 2u * PATCH_PLANE;
-          if (tc::elect_one()) {
+          if (leader) {
             tc::mbar_expect_tx(&p_full[pb], 2u * (uint32_t)(18 * PW * 64));
             tc::tma_load_4d(pa, &prm.maps[2 * s], cb * 32, x0, y0, b, &p_full[pb]);
             tc::tma_load_4d(pa + PATCH_PLANE, &prm.maps[2 * s + 1], cb * 32, x0, y0, b, &p_full[pb]);
           }
-          __syncwarp();
           // weights: TPS taps per stage (a kernel row of a 3x3 segment when TPS = 3), chunks ordered (seg, cb, tap)
           const int ntaps = ks * ks;
           for (int tap = 0; tap < ntaps; tap += TPS) {
@@ -136,13 +136,12 @@ __global__ void __launch_bounds__(CVH_THREADS, TWO ? 2 : 1) conv_halo_kernel(con
             const uint32_t st = bst, r2 = bround;
             if (++bst == (uint32_t)S) { bst = 0; ++bround; }
             if (r2 > 0) tc::mbar_wait(&b_empty[st], (r2 - 1) & 1u);
-            if (tc::elect_one()) {
+            if (leader) {
               tc::mbar_expect_tx(&b_full[st], nt_g * B_BYTES);
               tc::bulk_load(bring + (size_t)st * (TPS * B_BYTES),
                             wbase + (size_t)(prm.seg_chunk0[s] + cb * ntaps + tap) * B_BYTES, nt_g * B_BYTES,
                             &b_full[st]);
             }
-            __syncwarp();
           }
           ++pit;
         }
