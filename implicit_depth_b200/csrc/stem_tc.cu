@@ -91,34 +91,41 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
     uint8_t* my_stage = staging + g * 32768;
     uint32_t nfill[2] = {0, 0};
     uint32_t tiles = 0;
+    // The image patch of tile t+1 is fetched into REGISTERS (20 independent loads per thread) while tile t is built
+    // and drained: the global-memory latency of the patch was a quarter of this kernel's stall samples when the loads
+    // sat between the two barriers of the same tile.
+    constexpr int PER_THREAD = (3 * ST_PH * ST_PW + 127) / 128;
+    float pv[PER_THREAD];
+    auto fetch_patch = [&](long long tt) {
+      const int ftx = (int)(tt % prm.tiles_x);
+      const int fty = (int)((tt / prm.tiles_x) % prm.tiles_y);
+      const int fn = (int)(tt / ((long long)prm.tiles_x * prm.tiles_y));
+      const int iy0 = fty * ST_TY * 2 - 3, ix0 = ftx * ST_TX * 2 - 3;
+      const float* im = prm.img + (size_t)fn * 3 * prm.H * prm.W;
+#pragma unroll
+      for (int j = 0; j < PER_THREAD; ++j) {
+        const int i = row + 128 * j;
+        const int c = i / (ST_PH * ST_PW), r = (i / ST_PW) % ST_PH, q = i % ST_PW;
+        const int y = iy0 + r, x = ix0 + q;
+        pv[j] = 0.f;
+        if (i < 3 * ST_PH * ST_PW && y >= 0 && y < prm.H && x >= 0 && x < prm.W)
+          pv[j] = __ldg(im + ((size_t)c * prm.H + y) * prm.W + x);
+      }
+    };
+    if ((long long)blockIdx.x * 2 + g < total_tiles) fetch_patch((long long)blockIdx.x * 2 + g);
     for (long long t = blockIdx.x * 2 + g; t < total_tiles; t += G, ++tiles) {
       const int tx = (int)(t % prm.tiles_x);
       const int ty = (int)((t / prm.tiles_x) % prm.tiles_y);
       const int n = (int)(t / ((long long)prm.tiles_x * prm.tiles_y));
-      // ---- image patch -> shared memory (zero padded) ----
+      // ---- image patch (zero padded, fetched one tile ahead) -> shared memory ----
       tc::named_sync(1 + g, 128);  // everyone is done reading the previous patch
-      {
-        const int iy0 = ty * ST_TY * 2 - 3, ix0 = tx * ST_TX * 2 - 3;
-        const float* im = prm.img + (size_t)n * 3 * prm.H * prm.W;
-        // all loads of a thread are issued before the first store (20 independent requests in flight per thread)
-        constexpr int PER_THREAD = (3 * ST_PH * ST_PW + 127) / 128;
-        float v[PER_THREAD];
 #pragma unroll
-        for (int j = 0; j < PER_THREAD; ++j) {
-          const int i = row + 128 * j;
-          const int c = i / (ST_PH * ST_PW), r = (i / ST_PW) % ST_PH, q = i % ST_PW;
-          const int y = iy0 + r, x = ix0 + q;
-          v[j] = 0.f;
-          if (i < 3 * ST_PH * ST_PW && y >= 0 && y < prm.H && x >= 0 && x < prm.W)
-            v[j] = __ldg(im + ((size_t)c * prm.H + y) * prm.W + x);
-        }
-#pragma unroll
-        for (int j = 0; j < PER_THREAD; ++j) {
-          const int i = row + 128 * j;
-          if (i < 3 * ST_PH * ST_PW) my_patch[i] = v[j];
-        }
+      for (int j = 0; j < PER_THREAD; ++j) {
+        const int i = row + 128 * j;
+        if (i < 3 * ST_PH * ST_PW) my_patch[i] = pv[j];
       }
       tc::named_sync(1 + g, 128);
+      if (t + G < total_tiles) fetch_patch(t + G);
       // ---- build the row: 21 slices of 8 floats -> bf16 hi/lo -> TMEM, 64 K values (8 slices) per ring slot ----
 #pragma unroll
       for (int ch = 0; ch < ST_NCHUNK; ++ch) {
