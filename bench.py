@@ -33,9 +33,10 @@ WORKLOAD = "cfg2: B=4 per GPU, 512x384, 7 source views, 64 depth planes, implici
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2 (B=4) from the committed `ncu --set full` captures
 # (the cost volume written by either kernel stays in the 126 MB L2 for the consuming kernel, hence ~ the input bytes)
-NCU_SOURCE = "profiles/r02n_ncu_volume_conv.md"
-NCU_FV_TC_WARP_INST = 491774956.0  # smsp__inst_executed.sum of fv_tc_kernel<7> at cfg2, B=4 (same capture)
-NCU_DRAM_BYTES = {"fv_tc_kernel": 24.3e6, "cv_dot_kernel": 23.7e6}
+NCU_SOURCE = "profiles/r02n_ncu_volume_conv.md"      # cv_dot_kernel (unchanged since that capture)
+NCU_SOURCE_FV = "profiles/r02v_ncu_summary.md"       # fv_tc_kernel<7> inside one forward step, end of round 2
+NCU_FV_TC_WARP_INST = 486830973.0  # smsp__inst_executed.sum of fv_tc_kernel<7> at cfg2, B=4 (NCU_SOURCE_FV)
+NCU_DRAM_BYTES = {"fv_tc_kernel": 23.3e6, "cv_dot_kernel": 23.7e6}
 # l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed of cv_dot_kernel in that capture (312 us launch):
 # the unit that actually limits the gather, together with the L2 -> SM fabric
 NCU_CV_DOT_LSU_PCT = 55.75
@@ -477,7 +478,7 @@ def main_b200(args):
     roofline = {"kernel": "fv_tc_kernel (fused warp + metadata MLP, tcgen05)", "bound": "tensor",
                 "achieved": fv_flops / (fv_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
                 "frac": fv_flops / (fv_ms * 1e-3) / 1e12 / tf_peak, "traffic": NCU_DRAM_BYTES["fv_tc_kernel"],
-                "traffic_source": NCU_SOURCE, "ms_per_launch": fv_ms,
+                "traffic_source": NCU_SOURCE_FV, "ms_per_launch": fv_ms,
                 "algorithmic_flops_per_launch": fv_flops, "peak_source": peak_src + ", bf16 burst",
                 "note": "algorithmic fp32 FLOPs of the reference MLP; the kernel issues 3 bf16 MMAs per product"}
     roofline_dot = {"kernel": "cv_dot_kernel (fused warp + dot + view-sum + argmax)", "bound": "hbm",
@@ -493,7 +494,7 @@ def main_b200(args):
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         issue_floor_ms = NCU_FV_TC_WARP_INST * (B / 4.0) / (n_sm * 4.0 * sm_mhz * 1e6) * 1e3
         roofline["secondary_bound"] = {"what": "warp-instruction issue (4 schedulers per SM), instruction count from "
-                                               + NCU_SOURCE, "floor_ms_per_launch": issue_floor_ms,
+                                               + NCU_SOURCE_FV, "floor_ms_per_launch": issue_floor_ms,
                                        "frac": issue_floor_ms / fv_ms}
         l1_peak = n_sm * 128.0 * sm_mhz * 1e6 / 1e9
         roofline_dot["secondary_bound"] = {"what": "gathered bytes through the L1 data pipe (128 B/clk/SM)",
