@@ -105,41 +105,66 @@ extern "C" int b200_split_to_nchw(const void* hi, const void* lo, float* out, in
 
 // ---------------------------------------------------------------------------------------
 // x2 upsampling: mode 0 = bilinear, align_corners=False (utils/generic_utils.py:94-103, used by
-// BDDecoderPP networks.py:72,75); mode 1 = nearest (networks_fast.py:42).  One thread = one output
-// pixel x 8 channels.
+// BDDecoderPP networks.py:72,75); mode 1 = nearest (networks_fast.py:42).  One thread = one INPUT pixel x 8
+// channels = a 2x2 block of outputs: the four outputs blend the 3x3 input neighbourhood, 9 pixel loads instead of
+// 16 (the kernel was issue-bound on unpacking its inputs).  Every output is formed by the same expression and
+// weights as ATen's upsample_bilinear2d (src = max(0, (dst + 0.5) / 2 - 0.5)): the same values as the
+// one-output-per-thread form it replaces.
 // ---------------------------------------------------------------------------------------
-__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ ih, const __nv_bfloat16* __restrict__ il,
-                                  __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, int B, int H, int W,
-                                  int C, int mode) {
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const __nv_bfloat16* __restrict__ ih, const __nv_bfloat16* __restrict__ il,
+                  __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, int B, int H, int W, int C, int mode) {
   const int cg = C >> 3;
-  const size_t total = (size_t)B * (2 * H) * (2 * W) * cg;
+  const size_t total = (size_t)B * H * W * cg;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % cg);
     size_t r = i / cg;
-    const int ox = (int)(r % (2 * W));
-    r /= (2 * W);
-    const int oy = (int)(r % (2 * H));
-    const int b = (int)(r / (2 * H));
-    float v[8];
+    const int X = (int)(r % W);
+    r /= W;
+    const int Y = (int)(r % H);
+    const int b = (int)(r / H);
     const size_t img = (size_t)b * H * W;
+    const size_t obase = (((size_t)b * 2 * H + 2 * Y) * 2 * W + 2 * X) * C + c8 * 8;
+    const size_t orow = (size_t)2 * W * C;
     if (mode == 1) {
-      load8(ih, il, (img + (size_t)(oy >> 1) * W + (ox >> 1)) * C + c8 * 8, v);
-    } else {
-      // ATen upsample_bilinear2d: src = max(0, (dst + 0.5) * 0.5 - 0.5)
-      const float sy = fmaxf(0.f, (oy + 0.5f) * 0.5f - 0.5f), sx = fmaxf(0.f, (ox + 0.5f) * 0.5f - 0.5f);
-      const int y0 = (int)sy, x0 = (int)sx;
-      const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-      const float ly = sy - y0, lx = sx - x0;
-      float a[8], bq[8], c[8], d[8];
-      load8(ih, il, (img + (size_t)y0 * W + x0) * C + c8 * 8, a);
-      load8(ih, il, (img + (size_t)y0 * W + x1) * C + c8 * 8, bq);
-      load8(ih, il, (img + (size_t)y1 * W + x0) * C + c8 * 8, c);
-      load8(ih, il, (img + (size_t)y1 * W + x1) * C + c8 * 8, d);
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        v[e] = (1.f - ly) * ((1.f - lx) * a[e] + lx * bq[e]) + ly * ((1.f - lx) * c[e] + lx * d[e]);
+      float v[8];
+      load8(ih, il, (img + (size_t)Y * W + X) * C + c8 * 8, v);
+      store8(oh, ol, obase, v);
+      store8(oh, ol, obase + C, v);
+      store8(oh, ol, obase + orow, v);
+      store8(oh, ol, obase + orow + C, v);
+      continue;
     }
-    store8(oh, ol, (((size_t)b * 2 * H + oy) * 2 * W + ox) * C + c8 * 8, v);
+    // rows / columns of the neighbourhood: index 0 = previous (clamped), 1 = centre, 2 = next (clamped)
+    const int ys[3] = {max(Y - 1, 0), Y, min(Y + 1, H - 1)};
+    const int xs[3] = {max(X - 1, 0), X, min(X + 1, W - 1)};
+    float v[3][3][8];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) load8(ih, il, (img + (size_t)ys[a] * W + xs[q]) * C + c8 * 8, v[a][q]);
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+      const int oy = 2 * Y + py;
+      const float sy = fmaxf(0.f, (oy + 0.5f) * 0.5f - 0.5f);
+      const int y0 = (int)sy;
+      const float ly = sy - y0;
+      // taps: rows (Y-1, Y) for the even output row, (Y, Y+1) for the odd one, clamped.  At the top border ATen's
+      // taps are rows (0, 1) with ly = 0; rows (0, 0) with ly = 0 give the same value.  Columns alike.
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const int ox = 2 * X + px;
+        const float sx = fmaxf(0.f, (ox + 0.5f) * 0.5f - 0.5f);
+        const int x0 = (int)sx;
+        const float lx = sx - x0;
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          o[e] = (1.f - ly) * ((1.f - lx) * v[py][px][e] + lx * v[py][px + 1][e]) +
+                 ly * ((1.f - lx) * v[py + 1][px][e] + lx * v[py + 1][px + 1][e]);
+        store8(oh, ol, obase + (size_t)py * orow + (size_t)px * C, o);
+      }
+    }
   }
 }
 
@@ -148,7 +173,7 @@ extern "C" int b200_upsample2x(const void* in_hi, const void* in_lo, void* out_h
   B200_CHECK_ARG(in_hi && in_lo && out_hi && out_lo && B > 0 && H > 0 && W > 0, "upsample2x: bad arguments");
   B200_CHECK_ARG(C % 8 == 0, "upsample2x: C must be a multiple of 8 (got %d)", C);
   B200_CHECK_ARG(mode == 0 || mode == 1, "upsample2x: mode 0 (bilinear) or 1 (nearest)");
-  const size_t total = (size_t)B * 4 * H * W * (C / 8);
+  const size_t total = (size_t)B * H * W * (C / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   upsample2x_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in_hi, (const __nv_bfloat16*)in_lo,

@@ -154,6 +154,33 @@ def test_stem_conv7_tensor_core_matches_fp64(shape):
     assert (got - ref).abs().max().item() < 3e-5 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("mode", ["bilinear", "nearest"])
+@pytest.mark.parametrize("shape", [(2, 7, 9, 16), (1, 24, 32, 64), (3, 1, 5, 8), (1, 13, 1, 24)])
+def test_upsample2x_matches_torch(shape, mode):
+    """csrc/elementwise.cu upsample2x_kernel (one thread = a 2x2 output block from the 3x3 input neighbourhood) vs
+    F.interpolate(scale_factor=2; bilinear with align_corners=False as utils/generic_utils.py:94-103, or nearest),
+    incl. one-pixel-wide / -high maps where every tap clamps."""
+    from implicit_depth_b200 import _abi
+
+    B, H, W, C = shape
+    torch.manual_seed(B * 1000 + H * 10 + W)
+    a = SplitAct.from_nchw_torch(torch.randn(B, C, H, W, device="cuda"))
+    out = SplitAct(B, 2 * H, 2 * W, C, "cuda")
+    out.hi.fill_(float("nan")); out.lo.fill_(float("nan"))
+    _abi.call("b200_upsample2x", _abi.ptr(a.hi), _abi.ptr(a.lo), _abi.ptr(out.hi), _abi.ptr(out.lo), B, H, W, C,
+              0 if mode == "bilinear" else 1, _abi.stream_ptr())
+    torch.cuda.synchronize()
+    x = a.float_nchw()
+    ref = F.interpolate(x, scale_factor=2, mode=mode, align_corners=False) if mode == "bilinear" else \
+        F.interpolate(x, scale_factor=2, mode=mode)
+    got = out.float_nchw()
+    assert torch.isfinite(got).all()
+    if mode == "nearest":
+        assert torch.equal(got, ref)
+    else:  # + the split-bf16 storage rounding of the output (2^-17 relative) and FMA contraction
+        assert (got - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
 @pytest.mark.parametrize("shape", [(2, 48, 64, 64), (1, 31, 45, 16), (3, 20, 18, 64), (1, 192, 256, 64), (1, 5, 7, 8)])
 def test_maxblurpool_matches_torch(shape):
     """MaxPool2d(2, stride 1) + BlurPool(filt 4, stride 2, reflect pad (1,2,1,2)) of antialiased-cnns 0.3 (call site
