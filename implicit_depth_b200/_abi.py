@@ -47,6 +47,7 @@ SIGNATURES = {
     "b200_mbconv_dw_se": [c_f] * 13 + [c_i] * 7 + [ctypes.c_void_p],
     "b200_mbconv_pool_block": [],
     "b200_split_add": [c_f] * 6 + [c_ll, ctypes.c_void_p],
+    "b200_stem3x3_s2_silu": [c_f] * 5 + [c_i] * 5 + [c_ll] * 4 + [ctypes.c_void_p],
     "b200_channel_dot_exp": [c_f] * 6 + [c_ll, c_i, ctypes.c_void_p],
     "b200_sigmoid_resize": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, ctypes.c_float, c_i, c_i, ctypes.c_void_p],
     "b200_sample_prior": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],

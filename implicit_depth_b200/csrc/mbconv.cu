@@ -458,6 +458,75 @@ extern "C" int b200_mbconv_dw_se(const void* in_hi, const void* in_lo, const flo
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// Stem of the image-prior encoder: Conv2d(3, 24, 3, stride 2) + folded BatchNorm + SiLU straight from the fp32 NCHW
+// image (timm `conv_stem` / `bn1`, TF "SAME" padding (0, 1) on even sizes; torchvision features[0], padding 1).
+// K = 27: nothing for a tensor core -- the image -> split-bf16 conversion plus the per-tap tensor-core kernel on a
+// channel-padded copy took 133 us, this takes ~10.  Thread = one output pixel x 8 output channels; the 27 x Cp weights
+// sit in shared memory; fp32 FMAs in (c, dy, dx) order.
+//   img [B, 3, H, W] fp32 (strides sB, sC, sH, sW in elements); w [27][Cp] (k = (c*3 + dy)*3 + dx), bias [Cp];
+//   out: split NHWC [B, OH, OW, Cp], OH = (H + pad_lo + 1 - 3) / 2 + 1.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stem3x3_s2_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+                  __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, int B, int H, int W, int Cp, int OH,
+                  int OW, int pad_lo, long long sB, long long sC, long long sH, long long sW) {
+  extern __shared__ float w_s[];  // [27][Cp] then bias [Cp]
+  for (int i = threadIdx.x; i < 28 * Cp; i += blockDim.x) w_s[i] = i < 27 * Cp ? w[i] : bias[i - 27 * Cp];
+  __syncthreads();
+  const int cg = Cp >> 3;
+  const size_t total = (size_t)B * OH * OW * cg;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg);
+    size_t r = i / cg;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const int b = (int)(r / OH);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = w_s[27 * Cp + c8 * 8 + e];
+    const float* ib = img + (size_t)b * sB;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int y = 2 * oy + dy - pad_lo;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int x = 2 * ox + dx - pad_lo;
+          float v = 0.f;
+          if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(ib + c * sC + y * sH + x * sW);
+          const float4 w0 = *reinterpret_cast<const float4*>(w_s + ((c * 3 + dy) * 3 + dx) * Cp + c8 * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(w_s + ((c * 3 + dy) * 3 + dx) * Cp + c8 * 8 + 4);
+          acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+          acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+          acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+          acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+        }
+      }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = silu(acc[e]);
+    mb_store8(oh, ol, (((size_t)b * OH + oy) * OW + ox) * Cp + c8 * 8, acc);
+  }
+}
+
+extern "C" int b200_stem3x3_s2_silu(const float* img, const float* w, const float* bias, void* out_hi, void* out_lo,
+                                    int B, int H, int W, int Cp, int pad_lo, long long sB, long long sC, long long sH,
+                                    long long sW, void* stream) {
+  B200_CHECK_ARG(img && w && bias && out_hi && out_lo, "stem3x3_s2_silu: null pointer");
+  B200_CHECK_ARG(B > 0 && H > 2 && W > 2 && Cp > 0 && Cp % 8 == 0 && Cp <= 256 && (pad_lo == 0 || pad_lo == 1),
+                 "stem3x3_s2_silu: bad arguments (Cp %% 8 == 0, <= 256; pad_lo 0|1; got Cp=%d pad_lo=%d)", Cp, pad_lo);
+  const int OH = (H + pad_lo + 1 - 3) / 2 + 1, OW = (W + pad_lo + 1 - 3) / 2 + 1;
+  const size_t total = (size_t)B * OH * OW * (Cp / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  stem3x3_s2_kernel<<<blocks, 256, (size_t)28 * Cp * sizeof(float), (cudaStream_t)stream>>>(
+      img, w, bias, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, B, H, W, Cp, OH, OW, pad_lo, sB, sC, sH, sW);
+  B200_CHECK_LAUNCH("stem3x3_s2_silu");
+  return 0;
+}
+
 // a + b on split activations (8 channels per thread).
 __global__ void __launch_bounds__(256)
 split_add_kernel(const __nv_bfloat16* __restrict__ ah, const __nv_bfloat16* __restrict__ al,

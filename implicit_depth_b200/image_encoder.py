@@ -69,6 +69,38 @@ def _cna(g: Plan, x, cna, act, stride=1, residual=None, same=False):
     return y
 
 
+def _stem(g: Plan, get_image, cna, B, H, W, same):
+    """Stem conv 3 -> Cout, 3x3, stride 2 (+ folded BN + SiLU) straight from the fp32 image: one small CUDA-core kernel
+    (`b200_stem3x3_s2_silu`; K = 27 is nothing for a tensor core) instead of image -> split-bf16 conversion of a
+    channel-padded copy + the per-tap tensor-core conv."""
+    conv, bn = cna[0], cna[1]
+    assert conv.in_channels == 3 and conv.kernel_size[0] == 3 and conv.stride[0] == 2
+    w, b = _fold_bn(conv.weight, bn)  # [Cout, 3, 3, 3]
+    cout = conv.out_channels
+    cp = pad_ch(cout)
+    wk = torch.zeros((27, cp), dtype=torch.float32, device=g.device)
+    wk[:, :cout] = w.detach().to(g.device).float().reshape(cout, 27).t()
+    bias = _padv(b.to(g.device), cp)
+    lo, hi = same_pad(H, W, 3, 2) if same else (1, 1)
+    assert hi == 1 and lo in (0, 1)
+    OH, OW = out_size(H, W, 3, 2, (lo, 1))
+    y = g.act(B, OH, OW, cp)
+    y.Cl = cout
+    g._keep += [wk, bias]
+
+    def op():
+        img = get_image()
+        if img.dtype != torch.float32:
+            img = img.float()
+        assert tuple(img.shape) == (B, 3, H, W), f"expected {(B, 3, H, W)}, got {tuple(img.shape)}"
+        _abi.require_cuda(img)
+        _abi.call("b200_stem3x3_s2_silu", _abi.ptr(img), _abi.ptr(wk), _abi.ptr(bias), _abi.ptr(y.hi), _abi.ptr(y.lo),
+                  B, H, W, cp, lo, img.stride(0), img.stride(1), img.stride(2), img.stride(3), _abi.stream_ptr())
+
+    g.add(op, reads=[], writes=[y])
+    return y
+
+
 def _dw_pad(x, stride, same):
     lo, hi = (same_pad(x.H, x.W, 3, stride) if same else (1, 1))
     assert hi == 1 and lo in (0, 1)
@@ -323,18 +355,7 @@ def plan_efficientnet_v2_s(g: Plan, encoder, get_image, B, H, W, taps=None):
     Returns their SplitActs (channels [24, 48, 64, 160, 256] at /2 .. /32; `.Cl` holds the logical channel count)."""
     stem, stages, same = describe(encoder)
     taps = (0, 1, 2, 4, 5) if taps is None else tuple(taps)
-    dev = g.device
-    img8 = torch.zeros((B, 8, H, W), device=dev, dtype=torch.float32)  # channels 3..7 stay zero
-    g._keep.append(img8)
-
-    def load():
-        img = get_image()
-        assert tuple(img.shape) == (B, 3, H, W), f"expected {(B, 3, H, W)}, got {tuple(img.shape)}"
-        img8[:, :3].copy_(img)
-        return img8
-
-    x = g.from_f32(load, B, 8, H, W)
-    x = _cna(g, x, stem, "silu", stride=2, same=same)
+    x = _stem(g, get_image, stem, B, H, W, same)
     outs = []
     for si, blocks in enumerate(stages):
         for blk in blocks:

@@ -138,6 +138,15 @@ int b200_conv_create(const b200_conv_desc* desc, void** plan_out);
 int b200_conv_run(void* plan, void* stream);
 int b200_conv_destroy(void* plan);
 
+/* Stem of the image-prior encoder: Conv2d(3, Cout, 3, stride 2) + folded BatchNorm + SiLU straight from the fp32 image
+ * (replaces timm `conv_stem` + `bn1` + SiLU of `tf_efficientnetv2_s`, reference call site
+ * experiment_modules/bd_model.py:46-51; torchvision `features[0]` alike).  img [B,3,H,W] fp32 with element strides
+ * sB,sC,sH,sW; w [27][Cp] (k = (c*3+dy)*3+dx, output channels zero-padded to Cp % 8 == 0), bias [Cp]; pad_lo = 0 (TF
+ * "SAME" at stride 2 on even sizes: padding (0,1)) or 1 (symmetric); out: split-bf16 NHWC [B,OH,OW,Cp]. */
+int b200_stem3x3_s2_silu(const float* img, const float* w, const float* bias, void* out_hi, void* out_lo, int B, int H,
+                         int W, int Cp, int pad_lo, long long sB, long long sC, long long sH, long long sW,
+                         void* stream);
+
 /* ---- layout / elementwise kernels of the conv path (csrc/elementwise.cu) -------------------- */
 /* fp32 [B,C,H,W] with element strides (NCHW or channels_last) -> NHWC split-bf16 planes. */
 int b200_f32_to_split(const float* in, void* hi, void* lo, int B, int C, int H, int W, long long sB, long long sC,
