@@ -30,7 +30,7 @@
 // shared memory): while one CTA waits on a barrier, drains an accumulator or runs out of items, the other keeps the
 // tensor pipe busy -- the single-CTA form leaves it idle 60 % of the time on the 64-channel layers
 // (profiles/r02c_conv64_roles.md).
-template <int SUB, int NT /* N tile: 128, 64, or 16 (direct-store epilogue, no residual) */, bool KSPLIT = false,
+template <int SUB, int NT /* N tile: 128, 64, or 32 / 16 (direct-store epilogue, no residual) */, bool KSPLIT = false,
           bool TWO = false>
 __global__ void __launch_bounds__(CVH_THREADS, TWO ? 2 : 1) conv_halo_kernel(const __grid_constant__ ConvKParams prm) {
   static_assert(!KSPLIT || (SUB == 1 && NT >= 64), "split-K variant: one M=128 sub-tile, 64- or 128-wide N tile");
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(CVH_THREADS, TWO ? 2 : 1) conv_halo_kernel(con
     bias_s[i] = (prm.bias != nullptr && i < prm.Cout) ? prm.bias[i] : 0.f;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < 2 * prm.nseg; ++s) tc::prefetch_tmap(&prm.maps[s]);
-    if (NT != 16) {
+    if (NT >= 64) {
       tc::prefetch_tmap(&prm.out_maps[0]);
       tc::prefetch_tmap(&prm.out_maps[1]);
     }
@@ -292,9 +292,10 @@ __global__ void __launch_bounds__(CVH_THREADS, TWO ? 2 : 1) conv_halo_kernel(con
         }
       }
       tc::cluster_sync();  // #2: nobody reads this CTA's shared memory any more
-    } else if constexpr (NT == 16) {
-      // 16-wide N tile (the 3x3 128 -> 16 head of the matching encoder): warp group `half` drains sub-tile `half`;
-      // a thread holds all 16 channels of its pixel and stores them directly (32 B per plane, image border by test)
+    } else if constexpr (NT <= 32) {
+      // narrow N tile, Cout = NT = 16 or 32 (the 3x3 128 -> 16 head of the matching encoder; the 24-channel, padded to
+      // 32, first stage of the image encoder): warp group `half` drains sub-tile `half`; a thread holds all NT channels
+      // of its pixel and stores them directly (2 NT bytes per plane, image border by test)
       for (int item = item0; item < items; item += item_step, ++tile_i) {
         const int mt = item;  // n_ntiles == 1
         const int tx = mt % prm.tiles_x;
@@ -304,27 +305,33 @@ __global__ void __launch_bounds__(CVH_THREADS, TWO ? 2 : 1) conv_halo_kernel(con
         tc::mbar_wait(&acc_full[a], (tile_i >> 1) & 1u);
         tc::fence_after_sync();
         if (half < SUB) {
-          uint32_t rm[16], rc[16];
+          uint32_t rm[NT / 16][16], rc[NT / 16][16];
           const uint32_t t_main = tmem + lane_base + a * ACC_COLS + half * 2 * NT;
-          tc::tmem_ld16(t_main, rm);
-          tc::tmem_ld16(t_main + NT, rc);
+#pragma unroll
+          for (int q = 0; q < NT / 16; ++q) {
+            tc::tmem_ld16(t_main + 16 * q, rm[q]);
+            tc::tmem_ld16(t_main + NT + 16 * q, rc[q]);
+          }
           tc::wait_ld();
           const int oy = ty * CVH_ROWS + (row >> 3), ox = tx * 8 * SUB + half * 8 + (row & 7);
           if (oy < prm.OH && ox < prm.OW) {
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              v[j] = apply_act((__uint_as_float(rm[j]) + __uint_as_float(rc[j])) + bias_s[j], prm.act, prm.slope);
-            uint32_t hi[8], lo[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) tc::split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-            const size_t o = (((size_t)b * prm.OH + oy) * prm.OW + ox) * 16;
+            const size_t o = (((size_t)b * prm.OH + oy) * prm.OW + ox) * NT;
             uint4* oh = reinterpret_cast<uint4*>(prm.out_hi + o);
             uint4* ol = reinterpret_cast<uint4*>(prm.out_lo + o);
-            oh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            oh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+#pragma unroll
+            for (int c0 = 0; c0 < NT; c0 += 8) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                v[j] = apply_act((__uint_as_float(rm[c0 >> 4][(c0 & 15) + j]) + __uint_as_float(rc[c0 >> 4][(c0 & 15) + j])) +
+                                     bias_s[c0 + j],
+                                 prm.act, prm.slope);
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) tc::split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+              oh[c0 >> 3] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              ol[c0 >> 3] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
           }
         }
         tc::fence_before_sync();
@@ -429,7 +436,7 @@ __global__ void __launch_bounds__(CVH_THREADS, TWO ? 2 : 1) conv_halo_kernel(con
         tc::tma_store_commit();
       }
     }
-    if (NT != 16 && !KSPLIT && leader) tc::tma_store_wait_all<0>();
+    if (NT >= 64 && !KSPLIT && leader) tc::tma_store_wait_all<0>();
   }
   tc::fence_before_sync();
   __syncthreads();

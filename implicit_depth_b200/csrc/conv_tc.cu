@@ -430,7 +430,7 @@ extern "C" int b200_conv_ntile_for(const b200_conv_desc* d) {
 // chunk), 0 for the plain kernel (64-channel chunks, 128-byte swizzle).  Pure function of the geometry.
 extern "C" int b200_conv_uses_halo(const b200_conv_desc* d) {
   if (!d) return 0;
-  const bool n16 = d->Cout == 16;  // 16-wide N tile: 3x3 stride-1 segments only, no residual (matching-encoder head)
+  const bool n16 = d->Cout == 16 || d->Cout == 32;  // narrow N tile: 3x3 stride-1 segments only, no residual
   if ((d->Cout % 64 != 0 && !n16) || d->out_f32 != nullptr || d->out_hi == nullptr) return 0;
   if (n16 && d->res_hi != nullptr) return 0;
   // a pure 1x1 conv uses every halo patch for a single tap, so the halo kernel's 2-deep patch ring exposes the TMA
@@ -566,7 +566,7 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
       }
     }
   }
-  if (halo && k.NT != 16) {
+  if (halo && k.NT >= 64) {
     const cuuint32_t obox[4] = {64, 8, CVH_ROWS, 1};
     for (int part = 0; part < 2; ++part) {
       int r = encode_nhwc(enc, &k.out_maps[part], part ? d->out_lo : d->out_hi, d->Cout, d->OW, d->OH, d->B, obox, 1,
@@ -654,6 +654,10 @@ extern "C" int b200_conv_create(const b200_conv_desc* d, void** plan_out) {
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_halo_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_halo_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_halo_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_halo_kernel<1, 64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_halo_kernel<1, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -702,6 +706,8 @@ extern "C" int b200_conv_run(void* plan, void* stream) {
   else if (p->k.NT == 128) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 128>, p->k);
   else if (p->k.NT == 16 && p->k.sub == 2) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<2, 16>, p->k);
   else if (p->k.NT == 16) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 16>, p->k);
+  else if (p->k.NT == 32 && p->k.sub == 2) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<2, 32>, p->k);
+  else if (p->k.NT == 32) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 32>, p->k);
   else if (p->k.sub == 2) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<2, 64>, p->k);
   else if (p->k.two) le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 64, false, true>, p->k);
   else le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 64>, p->k);

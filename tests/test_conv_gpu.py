@@ -15,6 +15,8 @@ def act_ref(x, act, slope):
         return F.elu(x)
     if act == "relu":
         return F.relu(x)
+    if act == "silu":
+        return F.silu(x)
     return x
 
 
@@ -36,6 +38,8 @@ CASES = [
     (1, 13, 19, [192], 128, 3, 1, "elu", True),       # split-K x2, ragged map: border rows / columns of the slice stores
     (4, 12, 16, [384, 256], 384, 3, 1, "lrelu", False),  # CVEncoder level 3 at cfg2: 24 items x 4 CTAs
     (1, 24, 32, [512], 64, 3, 1, "relu", True),       # 64-wide N tile, split-K x8 (8 items, 16 patches), residual
+    (2, 37, 45, [24], 32, 3, 1, "silu", False),       # 32-wide narrow N tile (image-encoder stage 1), ragged size
+    (4, 96, 128, [32], 32, 3, 1, "silu", False),      # 32-wide narrow N tile, M=256 double tiles on a full grid
     (2, 13, 19, [96], 128, 1, 1, "elu", True),        # plain kernel, staged (transposed) stores: ragged map, residual
     (1, 11, 21, [40], 64, 1, 1, "relu", False),       # plain kernel, staged stores with the 64-wide N tile
     (2, 21, 27, [64], 256, 3, 2, "lrelu", False),     # stride 2, two staged N tiles, ragged output (11 x 14)
@@ -63,8 +67,8 @@ def test_conv_matches_fp64(case, with_f32):
         res = SplitAct.from_nchw_torch(rx)
     plan = ConvPlan([(a, k, stride, pad) for a in acts], ws, bias, out, B, Cout, act=act, slope=0.2,
                     residual=res, out_f32=out_f32)
-    # pure 1x1 convs and fp32 copies: per-tap kernel; Cout == 16 without residual: the 16-wide halo variant
-    assert plan.halo == (not with_f32 and stride == 1 and k == 3 and (Cout % 64 == 0 or (Cout == 16 and not use_res)))
+    # pure 1x1 convs and fp32 copies: per-tap kernel; Cout == 16 / 32 without residual: the narrow halo variants
+    assert plan.halo == (not with_f32 and stride == 1 and k == 3 and (Cout % 64 == 0 or (Cout in (16, 32) and not use_res)))
     plan.run()
     plan.run()  # a second launch must give the same answer (persistent state fully re-initialised)
     torch.cuda.synchronize()
