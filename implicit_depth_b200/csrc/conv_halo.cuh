@@ -436,7 +436,9 @@ __global__ void __launch_bounds__(CVH_THREADS, TWO ? 2 : 1) conv_halo_kernel(con
         tc::tma_store_commit();
       }
     }
-    if (NT >= 64 && !KSPLIT && leader) tc::tma_store_wait_all<0>();
+    // the staging tile must outlive the stores' READS; their global writes complete with the grid (and are visible to
+    // the next kernel through its griddepcontrol.wait / the stream order)
+    if (NT >= 64 && !KSPLIT && leader) tc::tma_store_wait_read<0>();
   }
   tc::fence_before_sync();
   __syncthreads();

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
         tc::tma_store_commit();
       }
     }
-    if (row == 0) tc::tma_store_wait_all<0>();
+    if (row == 0) tc::tma_store_wait_read<0>();  // (the writes complete with the grid)
   } else {
     // =============================== MMA issuer (whole warp loops, one elected lane issues) ==========
     constexpr uint32_t IDESC_MERGED = tc::idesc_bf16_f32(128, 128);
