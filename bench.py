@@ -34,8 +34,8 @@ WORKLOAD = "cfg2: B=4 per GPU, 512x384, 7 source views, 64 depth planes, implici
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at cfg2 (B=4) from the committed `ncu --set full` captures
 # (the cost volume written by either kernel stays in the 126 MB L2 for the consuming kernel, hence ~ the input bytes)
 NCU_SOURCE = "profiles/r02n_ncu_volume_conv.md"      # cv_dot_kernel (unchanged since that capture)
-NCU_SOURCE_FV = "profiles/r02v_ncu_summary.md"       # fv_tc_kernel<7> inside one forward step, end of round 2
-NCU_FV_TC_WARP_INST = 486830973.0  # smsp__inst_executed.sum of fv_tc_kernel<7> at cfg2, B=4 (NCU_SOURCE_FV)
+NCU_SOURCE_FV = "profiles/r02x_ncu_summary.md"       # fv_tc_kernel<7> inside one forward step, end of round 2
+NCU_FV_TC_WARP_INST = 486890230.0  # smsp__inst_executed.sum of fv_tc_kernel<7> at cfg2, B=4 (NCU_SOURCE_FV)
 NCU_DRAM_BYTES = {"fv_tc_kernel": 23.3e6, "cv_dot_kernel": 23.7e6}
 # l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed of cv_dot_kernel in that capture (312 us launch):
 # the unit that actually limits the gather, together with the L2 -> SM fabric

@@ -167,7 +167,7 @@ class B200BDModel(nn.Module):
         self._enc_graphs, self._enc_pending = {}, None
         return super()._apply(fn, *a, **k)
 
-    FRONT_SM_FRACTION = 0.61  # see _front_sm_cap
+    FRONT_SM_FRACTION = 0.65  # see _front_sm_cap (96 of 148 SMs)
     FV_SM_FRACTION = None     # CTA cap of the plane sweep as a fraction of the SMs; None = the front-end cap
 
     def _front_sm_cap(self):
@@ -177,8 +177,9 @@ class B200BDModel(nn.Module):
             return 0
         if self.encoder_ahead:  # the encoder is not inside this forward
             return 0
-        # a little over half the machine: measured optimum on B200 (scripts/sm_cap_sweep.py, ms per step at cfg2, round 2
-        # kernels: no cap -> 8.98, 70 -> 8.96, 80 -> 8.77, 90 -> 8.73, 100 -> 8.74; round 1: profiles/r01f_sm_cap_sweep.md)
+        # about two thirds of the machine: measured optimum on B200 (scripts/sm_cap_sweep.py, ms per step at cfg2 with the
+        # end-of-round-2 kernels: 86 -> 6.99, 90 -> 6.92, 94 -> 6.82, 98 -> 6.80, 102 -> 6.95, 106 -> 6.95,
+        # profiles/r02x_sm_cap_sweep.jsonl; the optimum moved up from 80-90 as the image encoder's chain got shorter)
         return round(self.FRONT_SM_FRACTION *
                      torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count)
 

@@ -12,14 +12,14 @@ timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --cloc
 python scripts/summarize_launches.py gpurun_out/launches.csv 40 > gpurun_out/launches_summary.txt; head -24 gpurun_out/launches_summary.txt
 cap() {  # name regex skip
   timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 \
-      -f -o gpurun_out/prof_v_$1 python scripts/profile_step.py > gpurun_out/ncu_v_$1.log 2>&1; tail -1 gpurun_out/ncu_v_$1.log
+      -f -o gpurun_out/prof_x_$1 python scripts/profile_step.py > gpurun_out/ncu_x_$1.log 2>&1; tail -1 gpurun_out/ncu_x_$1.log
 }
 cap fvtc fv_tc_kernel 0
-cap halo64 "conv_halo_kernel<2,.64" 8
-cap halo128 "conv_halo_kernel<1,.128,.0" 8
-cap convtc conv_tc_kernel 73
+cap halo64 conv_halo_kernel 8
+cap halo128 conv_halo_kernel 2
+cap convtc conv_tc_kernel 70
 cap bmlp binary_mlp_tc_kernel 0
 cap stem stem_tc_kernel 0
-python scripts/ncu_summary.py gpurun_out/prof_v_fvtc.ncu-rep gpurun_out/prof_v_halo64.ncu-rep gpurun_out/prof_v_halo128.ncu-rep \
-    gpurun_out/prof_v_convtc.ncu-rep gpurun_out/prof_v_bmlp.ncu-rep gpurun_out/prof_v_stem.ncu-rep > gpurun_out/ncu_summary_v.md
+python scripts/ncu_summary.py gpurun_out/prof_x_fvtc.ncu-rep gpurun_out/prof_x_halo64.ncu-rep gpurun_out/prof_x_halo128.ncu-rep \
+    gpurun_out/prof_x_convtc.ncu-rep gpurun_out/prof_x_bmlp.ncu-rep gpurun_out/prof_x_stem.ncu-rep > gpurun_out/ncu_summary_x.md
 timeout 300 python scripts/time_configs.py > gpurun_out/time_configs.log 2>&1; cat gpurun_out/time_configs.log | cut -c1-250
