@@ -48,6 +48,8 @@ SIGNATURES = {
     "b200_mbconv_pool_block": [],
     "b200_split_add": [c_f] * 6 + [c_ll, ctypes.c_void_p],
     "b200_stem3x3_s2_silu": [c_f] * 5 + [c_i] * 5 + [c_ll] * 4 + [ctypes.c_void_p],
+    "b200_stream_create": [c_i, ctypes.POINTER(ctypes.c_void_p)],
+    "b200_stream_destroy": [ctypes.c_void_p],
     "b200_channel_dot_exp": [c_f] * 6 + [c_ll, c_i, ctypes.c_void_p],
     "b200_sigmoid_resize": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, ctypes.c_float, c_i, c_i, ctypes.c_void_p],
     "b200_sample_prior": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_void_p],
@@ -149,6 +151,22 @@ def ptr(t):
 
 def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def new_stream(device=None, priority=0):
+    """A dedicated CUDA stream (`b200_stream_create`) as a `torch.cuda.ExternalStream`.  Use this, not
+    `torch.cuda.Stream()`, for streams that must be distinct inside one CUDA-graph capture: torch hands its streams out
+    of a pool of 32 per device and aliases them once a process has created more.  The stream is never destroyed (like
+    torch's pooled streams): the caching allocator may still hold blocks keyed by it, and the handful of streams a
+    model / pipeline creates live as long as the process anyway."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    load()
+    out = ctypes.c_void_p()
+    with torch.cuda.device(dev):
+        call("b200_stream_create", int(priority), ctypes.byref(out))
+    return torch.cuda.ExternalStream(out.value, device=dev)
 
 
 def call(name, *args):

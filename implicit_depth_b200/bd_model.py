@@ -189,7 +189,7 @@ class B200BDModel(nn.Module):
             st.encp.run()
             return lambda: None
         if self._side is None:
-            self._side = torch.cuda.Stream(device=dev)
+            self._side = _abi.new_stream(dev)
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
@@ -215,7 +215,7 @@ class B200BDModel(nn.Module):
         if self._enc_fast is None or self._enc_fast[0] != key:
             self._enc_fast = (key, fold_batchnorm(self.encoder))
         if self._side is None:
-            self._side = torch.cuda.Stream(device=cur_image.device)
+            self._side = _abi.new_stream(cur_image.device)
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
@@ -386,7 +386,7 @@ class B200BDModel(nn.Module):
         else:
             key = (B, K, H, W, P, search, cur_image.data_ptr())
             if key not in self._enc_graphs:
-                s = torch.cuda.Stream()
+                s = _abi.new_stream()
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
                     st.slots["cur_image"] = cur_image
@@ -518,7 +518,7 @@ class B200BDModel(nn.Module):
         if key not in self._graphs:
             static = list(args) if images_all is not None else [a.clone() for a in args]
             sprior = None if prior is None else prior.clone()
-            s = torch.cuda.Stream()
+            s = _abi.new_stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 for _ in range(2):  # warm-up: builds plans, packs weights, sets kernel attributes

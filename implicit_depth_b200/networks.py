@@ -78,7 +78,7 @@ class Plan:
         main = torch.cuda.current_stream()
         ext_waited = set()
         if self._pool is None:
-            self._pool = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams)]
+            self._pool = [_abi.new_stream(self.device) for _ in range(self.n_streams)]
         streams = [main] + self._pool
         n = len(streams)
         tail = [None] * n            # index of the last op enqueued on each stream since the last barrier

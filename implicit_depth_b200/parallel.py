@@ -12,6 +12,8 @@ own so that step i's gather runs under step i+1's front phase, and only the root
 from __future__ import annotations
 
 import torch
+
+from . import _abi
 import torch.distributed as dist
 
 ALIGN = 256  # bytes: every field of a packed frame starts on a 256-byte boundary
@@ -132,7 +134,7 @@ class GatherPlan:
         self.recv = [torch.zeros(nb * world, dtype=torch.uint8, device=dev) if (holds_all and world > 1) else None
                      for _ in range(slots)]
         self.cuda = dev.type == "cuda"  # (CPU tensors + gloo: host-logic tests; everything is synchronous there)
-        self.stream = torch.cuda.Stream(device=dev) if self.cuda else None
+        self.stream = _abi.new_stream(dev) if self.cuda else None
         self.done = [None] * slots  # event: the collective that last used slot s has finished
 
     def send_views(self, slot):

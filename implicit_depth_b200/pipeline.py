@@ -13,6 +13,8 @@ from __future__ import annotations
 
 import torch
 
+from . import _abi
+
 from .staging import FrameStaging, StagedDict, StagedFrame
 
 
@@ -28,12 +30,12 @@ class FramePipeline:
         plane sweep on all SMs followed by the back phase.  Results are unchanged (same kernels, same order per
         batch)."""
         self.model, self.device, self.gather, self.kw = model, torch.device(device), gather, forward_kwargs
-        self.s_in = torch.cuda.Stream(device=self.device)
-        self.s_out = torch.cuda.Stream(device=self.device)
+        self.s_in = _abi.new_stream(self.device)
+        self.s_out = _abi.new_stream(self.device)
         self.encoder_ahead = bool(encoder_ahead)
         if self.encoder_ahead:
             model.encoder_ahead = True
-            self.s_enc = torch.cuda.Stream(device=self.device, priority=int(encoder_priority))
+            self.s_enc = _abi.new_stream(self.device, priority=int(encoder_priority))
         self.ev_enc = [None, None]         # encoder of the batch in slot s has finished (encoder_ahead)
         self.slots = [None, None]          # device input dictionaries
         self.HOST_SLOTS = 3                # a yielded dictionary stays valid while the next batch is being produced

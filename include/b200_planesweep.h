@@ -21,6 +21,11 @@ extern "C" {
 #endif
 
 int b200_abi_version(void);           /* 2: CTA caps are per-call arguments (`max_ctas`), no process-global state */
+/* A dedicated non-blocking CUDA stream for the host-side mirror (Plan scheduler pools, encoder / copy streams): streams
+ * that must be distinct within one CUDA-graph capture must not come from PyTorch's 32-entry stream pool, which aliases
+ * once a process has created more.  No reference counterpart (the reference runs on one stream). */
+int b200_stream_create(int priority, void** stream_out);
+int b200_stream_destroy(void* stream);
 const char* b200_last_error(void);    /* message of the last failing call on this thread */
 const char* b200_source_digest(void); /* sha256 of the sources the library was built from (checked by the loader) */
 /* `max_ctas` (b200_conv_desc, b200_fv_mlp_tc, b200_stem_conv7_tc): upper bound on the CTAs of that persistent launch,
