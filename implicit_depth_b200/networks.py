@@ -33,7 +33,8 @@ class Plan:
     """Preallocated buffers + an ordered list of kernel launches (CUDA-graph capturable)."""
 
     DAG = True       # False = strictly sequential launches on the caller's stream (the bit-identity tests compare both)
-    N_STREAMS = 3    # extra streams of the dependency scheduler
+    N_STREAMS = 5    # extra streams of the dependency scheduler (scripts/stream_sweep.py, ms per step at cfg2: 1 -> 6.92,
+                     # 2 -> 6.83, 3 -> 6.79, 4 -> 6.78, 5 -> 6.68, 6 -> 6.73, 8 -> 6.80; profiles/r02x_stream_sweep.jsonl)
 
     def __init__(self, device, max_ctas=0):
         self.device = torch.device(device)
