@@ -103,3 +103,34 @@ def test_mbconv_dw_se_bad_arguments():
     assert lib.b200_mbconv_dw_se(*([p] * 13), 1, 4, 4, 8, 3, 4, 1, None) == -1    # stride
     assert lib.b200_mbconv_dw_se(*([p] * 13), 1, 4, 4, 8, 1, 200, 1, None) == -1  # S > 128
     assert lib.b200_mbconv_dw_se(*([p] * 13), 1, 4, 4, 8, 2, 4, 2, None) == -1    # pad_lo
+
+
+@pytest.mark.parametrize("pad_lo", [0, 1])
+@pytest.mark.parametrize("shape", [(2, 24, 32, 24), (1, 37, 45, 32), (3, 6, 10, 8)])
+def test_encoder_stem_direct_conv_vs_torch(shape, pad_lo):
+    """`b200_stem3x3_s2_silu` (image-encoder stem: Conv2d(3, Cout, 3, stride 2) + bias + SiLU straight from the fp32
+    image) vs torch fp64: TF "SAME" padding (0, 1) and symmetric padding 1, ragged sizes, channel padding, and an
+    image that is a strided view (the forward passes slices of a staging buffer)."""
+    B, H, W, cout = shape
+    cp = (cout + 15) // 16 * 16
+    g = torch.Generator().manual_seed(B * 100 + H + pad_lo)
+    big = torch.randn(B, 4, H, W + 3, generator=g).cuda()
+    img = big[:, :3, :, 1:W + 1]                      # non-contiguous view
+    w = (torch.randn(cout, 3, 3, 3, generator=g) / 27 ** 0.5).cuda()
+    b = (0.1 * torch.randn(cout, generator=g)).cuda()
+    wk = torch.zeros(27, cp, device="cuda")
+    wk[:, :cout] = w.reshape(cout, 27).t()
+    bias = torch.zeros(cp, device="cuda")
+    bias[:cout] = b
+    OH, OW = (H + pad_lo + 1 - 3) // 2 + 1, (W + pad_lo + 1 - 3) // 2 + 1
+    out = SplitAct(B, OH, OW, cp, "cuda")
+    out.hi.fill_(float("nan")); out.lo.fill_(float("nan"))
+    _abi.call("b200_stem3x3_s2_silu", _abi.ptr(img), _abi.ptr(wk), _abi.ptr(bias), _abi.ptr(out.hi), _abi.ptr(out.lo),
+              B, H, W, cp, pad_lo, img.stride(0), img.stride(1), img.stride(2), img.stride(3), _abi.stream_ptr())
+    torch.cuda.synchronize()
+    ref = F.silu(F.conv2d(F.pad(img.double(), [pad_lo, 1, pad_lo, 1]), w.double(), b.double(), stride=2))
+    got = out.float_nchw().double()
+    assert torch.isfinite(got).all()
+    assert got.shape == (B, cp, OH, OW)
+    assert (got[:, :cout] - ref).abs().max().item() < 3e-5 * ref.abs().max().item()
+    assert (got[:, cout:] == 0).all()  # padded channels: zero weights and bias -> silu(0) = 0
